@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""Headline benchmark: Mpixel/s of `apply` + `combine_with(mode=3)` on batched 1080p frames (BASELINE.json, cfg 4).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+A step = one pass of the target-referenced hot path over one batch of B synthetic 1920x1080 frames per GPU:
+  (1) FlowBatch.apply(uint8x3 images, return_valid_area=True)   -> ofk_warp_t      (16 B/px algorithmic)
+  (2) FlowBatch.combine_with(other, mode=3)                      -> ofk_combine3    (27 B/px algorithmic)
+Pixels are counted once per pair of calls. `value` is device-resident throughput (CUDA events,
+max over ranks), `e2e` is the same pair of operations through the host-buffer API (pinned numpy in / numpy out, copies
+inside the timed region). `--impl reference` times the CPU oracle port of the reference (cv2.remap + numpy glue, all
+host threads OpenCV uses) on a bounded sample of the same workload.
+
+Multi-GPU: one process per GPU (torchrun), contiguous batch shards, no data-path collective; weak scaling.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+H, W = 1080, 1920
+BYTES_WARP = 16       # flow 8 + image 3 in + 3 out + flow mask 1 + valid 1
+BYTES_COMBINE = 27    # A 8+1, B 8+1, out 8+1
+METRIC = "Mpixel/s for apply + combine_with(mode=3) at 1080p"
+
+
+def frame_transforms(i):
+    import golden_inputs as gi
+    return gi.cfg4_transforms(i), gi.cfg4_transforms(i + 100000)
+
+
+def host_inputs(n_distinct, seed=0):
+    """Distinct host frames (masks 2 % invalid, uint8x3 images); tiled over the batch on the device."""
+    rng = np.random.default_rng(seed)
+    am = rng.random((n_distinct, H, W)) > 0.02
+    bm = rng.random((n_distinct, H, W)) > 0.02
+    img = rng.integers(0, 256, (n_distinct, H, W, 3), dtype=np.uint8)
+    return am, bm, img
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.stop_flag = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {'hw_slowdown': getattr(nv, 'nvmlClocksEventReasonHwSlowdown', 0x8),
+                 'hw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40),
+                 'sw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20),
+                 'sw_power_cap': getattr(nv, 'nvmlClocksEventReasonSwPowerCap', 0x4),
+                 'hw_power_brake': getattr(nv, 'nvmlClocksEventReasonHwPowerBrakeSlowdown', 0x80)}
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def result(self):
+        self.stop_flag.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_reference_step(frames, sample):
+    """The reference's CPU path (oracle port: cv2.remap + the numpy glue of Flow.apply / combine_with) on `sample`
+    frames; returns seconds."""
+    from oracle import flowref as R
+    t0 = time.perf_counter()
+    for (fa, fam, fb, fbm, img) in frames[:sample]:
+        a, b = R.make(fa, 't', fam), R.make(fb, 't', fbm)
+        R.apply(a, img, return_valid_area=True)
+        R.combine(a, b, 3)
+    return time.perf_counter() - t0
+
+
+def cpu_frames(count):
+    from oracle import flowref as R
+    am, bm, img = host_inputs(count, seed=0)
+    frames = []
+    for i in range(count):
+        ta, tb = frame_transforms(i)
+        frames.append((R.from_transforms(ta, (H, W), 't'), am[i], R.from_transforms(tb, (H, W), 't'), bm[i], img[i]))
+    return frames
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import cv2
+    sample = args.cpu_sample
+    frames = cpu_frames(sample)
+    for _ in range(args.warmup):
+        cpu_reference_step(frames, 1)
+    secs = [cpu_reference_step(frames, sample) for _ in range(args.steps)]
+    t = float(np.mean(secs))
+    value = sample * H * W / t / 1e6
+    cores = cv2.getNumThreads()
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8+f32", "data": "synthetic",
+            "config": {"workload": "cfg4: 1920x1080 apply(uint8x3, valid area) + combine_with(mode=3), ref 't'",
+                       "frames_per_step": sample},
+            "cpu_baseline": {"value": value, "unit": "Mpixel/s", "cores": cores, "kind": "port",
+                             "sample": "%d frames of 1920x1080 per step, per-frame Python loop (the reference has no "
+                                       "batch axis); cv2.remap uses %d threads, numpy glue 1" % (sample, cores)},
+            "e2e": {"value": value, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--batch', type=int, default=256, help='frames per GPU per step')
+    ap.add_argument('--e2e-batch', type=int, default=32, help='frames per GPU per end-to-end step (pinned host)')
+    ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--cpu-sample', type=int, default=8, help='frames per CPU-baseline step')
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == 'ours':
+        args.warmup = 3
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+
+    import oflibnumpy_b200 as of
+    from oflibnumpy_b200 import _lib, _ops
+    from oflibnumpy_b200.device import DeviceArray, Event, Stream
+    of.device.require_gpu()
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    of.device.set_device(local_rank)
+    stream = Stream()
+    of.device.set_stream(stream)
+
+    # ---------------------------------------------------------------- device-resident inputs (this rank's shard)
+    B = args.batch
+    base = rank * B                                   # weak scaling: every rank owns B frames of the global batch
+    n_distinct = min(B, 8)
+    am_h, bm_h, img_h = host_inputs(n_distinct, seed=rank)
+    ta, tb = zip(*[frame_transforms(base + i) for i in range(B)])
+    fa = of.FlowBatch.from_transforms(list(ta), (H, W), 't')
+    fb = of.FlowBatch.from_transforms(list(tb), (H, W), 't')
+    imgs = DeviceArray.empty((B, H, W, 3), np.uint8)
+    for i in range(B):
+        j = i % n_distinct
+        for dst, src in ((fa.masks, am_h), (fb.masks, bm_h), (imgs, img_h)):
+            d = dst.frames(i, i + 1)
+            _lib.call('ofk_rt_memcpy_h2d', d.ptr, np.ascontiguousarray(src[j]).ctypes.data, d.nbytes, stream.handle)
+        if i % 32 == 31:
+            stream.synchronize()
+    stream.synchronize()
+
+    # persistent outputs: the timed region launches kernels only (no allocation)
+    out_img = DeviceArray.empty((B, H, W, 3), np.uint8)
+    out_valid = DeviceArray.empty((B, H, W), np.uint8)
+    out_vecs = DeviceArray.empty((B, H, W, 2), np.float32)
+    out_mask = DeviceArray.empty((B, H, W), np.uint8)
+    flags = DeviceArray.empty((B, 2), np.int32)
+    arith, rule = _ops.promoted_rule(np.uint8, False)
+
+    def step(evs=None):
+        if evs:
+            evs[0].record(stream)
+        _lib.call('ofk_warp_t', imgs.ptr, _lib.U8, 3, arith, fa.vecs.ptr, -1.0, None, fa.masks.ptr, out_img.ptr,
+                  out_valid.ptr, rule, B, H, W, H, W, 0, 0, 1, stream.handle)
+        if evs:
+            evs[1].record(stream)
+        _lib.call('ofk_combine3', fa.vecs.ptr, fa.masks.ptr, fb.vecs.ptr, fb.masks.ptr, ord('t'), 0.0, out_vecs.ptr,
+                  out_mask.ptr, flags.ptr, B, H, W, stream.handle)
+        if evs:
+            evs[2].record(stream)
+
+    def barrier():
+        stream.synchronize()
+        of.device.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [[Event(), Event(), Event()] for _ in range(args.steps)]
+    launches0 = _lib.load().ofk_rt_launch_count()
+    t_start, t_stop = Event(), Event()
+    barrier()
+    t_start.record(stream)
+    for k in range(args.steps):
+        step(ev[k])
+    t_stop.record(stream)
+    barrier()
+    launches = _lib.load().ofk_rt_launch_count() - launches0
+    clocks = sampler.result()
+    total_ms = t_start.elapsed_ms(t_stop)
+    warp_ms = float(np.mean([e[0].elapsed_ms(e[1]) for e in ev]))
+    comb_ms = float(np.mean([e[1].elapsed_ms(e[2]) for e in ev]))
+
+    if dist is not None:
+        import torch
+        t = torch.tensor([total_ms, warp_ms, comb_ms], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, warp_ms, comb_ms = (float(x) for x in t.tolist())
+    ms_per_step = total_ms / args.steps
+    px_step = world * B * H * W
+    value = px_step / (ms_per_step * 1e-3) / 1e6
+
+    # ---------------------------------------------------------------- end to end through the host-buffer API
+    e2e = None
+    if not args.no_e2e:
+        EB = min(args.e2e_batch, B)
+        pin = {}
+        keep = []
+        for name, shape, dt in (('a', (EB, H, W, 2), np.float32), ('b', (EB, H, W, 2), np.float32),
+                                ('am', (EB, H, W), np.bool_), ('bm', (EB, H, W), np.bool_),
+                                ('img', (EB, H, W, 3), np.uint8), ('o_img', (EB, H, W, 3), np.uint8),
+                                ('o_valid', (EB, H, W), np.bool_), ('o_vecs', (EB, H, W, 2), np.float32),
+                                ('o_mask', (EB, H, W), np.bool_)):
+            arr, handle = of.device.pinned_empty(shape, dt)
+            pin[name] = arr
+            keep.append(handle)
+        fa.vecs.frames(0, EB).numpy(out=pin['a'])
+        fb.vecs.frames(0, EB).numpy(out=pin['b'])
+        for i in range(EB):
+            pin['am'][i], pin['bm'][i], pin['img'][i] = am_h[i % n_distinct], bm_h[i % n_distinct], img_h[i % n_distinct]
+
+        def e2e_step():
+            of.batch.apply_flow_host(pin['a'], pin['img'], flow_masks=pin['am'], return_valid_area=True,
+                                     out=pin['o_img'], out_valid=pin['o_valid'], device=local_rank)
+            of.batch.combine_flows_host(pin['a'], pin['b'], 3, 't', pin['am'], pin['bm'], out=pin['o_vecs'],
+                                        out_masks=pin['o_mask'], device=local_rank)
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        if dist is not None:
+            import torch
+            t = torch.tensor([dt], device='cuda', dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        px = EB * H * W
+        h2d = px * (8 + 1 + 3) + px * (8 + 8 + 1 + 1)     # call 1: flow, flow mask, image; call 2: A, B, masks
+        d2h = px * (3 + 1) + px * (8 + 1) + EB * 8
+        e2e = {"value": world * px / dt / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "frames_per_step": EB, "api": "batch.apply_flow_host + "
+               "batch.combine_flows_host (ofh_warp_t, ofh_combine3), pinned numpy buffers"}
+        # results of the two paths must agree
+        assert np.array_equal(pin['o_vecs'], out_vecs.frames(0, EB).numpy())
+        assert np.array_equal(pin['o_img'], out_img.frames(0, EB).numpy())
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---------------------------------------------------------------- roofline of the dominant kernel + CPU baseline
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    else:
+        peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+    px_rank = B * H * W
+    comb_gbs = px_rank * BYTES_COMBINE / (comb_ms * 1e-3) / 1e9
+    warp_gbs = px_rank * BYTES_WARP / (warp_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get('combine3_vec4_bytes_per_px')
+            traffic = traffic * px_rank if traffic else None
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "combine3_vec4<ref t>", "achieved": comb_gbs, "peak": peak,
+                "unit": "GB/s", "frac": comb_gbs / peak, "traffic": traffic, "peak_source": peak_src,
+                "bytes_per_px": BYTES_COMBINE, "ms_per_launch": comb_ms,
+                "other_kernels": {"warp_t_vec4<u8,3,rint>": {"achieved": warp_gbs, "frac": warp_gbs / peak,
+                                                            "bytes_per_px": BYTES_WARP, "ms_per_launch": warp_ms}},
+                "frac_of_nominal_8TBs": comb_gbs / 8000.0}
+    cpu = None
+    if not args.no_cpu_baseline:
+        import cv2
+        frames = cpu_frames(args.cpu_sample)
+        cpu_reference_step(frames, 1)
+        secs = cpu_reference_step(frames, args.cpu_sample)
+        cpu = {"value": args.cpu_sample * H * W / secs / 1e6, "unit": "Mpixel/s", "cores": cv2.getNumThreads(),
+               "kind": "port", "host_cpus": os.cpu_count(),
+               "sample": "%d frames of 1920x1080, per-frame loop of the oracle port (cv2.remap on %d threads + "
+                         "single-threaded numpy glue), %.1f s" % (args.cpu_sample, cv2.getNumThreads(), secs)}
+    line = {"metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8+f32", "data": "synthetic",
+            "config": {"workload": "cfg4: batched 1920x1080 apply(uint8x3, return_valid_area) + "
+                                   "combine_with(mode=3), ref 't'", "frames_per_gpu": B, "global_batch": world * B,
+                       "parallelism": "batch-sharded x%d, no collective" % world,
+                       "l2": "inputs (%.1f GB per GPU) exceed L2; no flush needed" %
+                             (px_rank * (8 + 8 + 1 + 1 + 3) / 1e9)},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

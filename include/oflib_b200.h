@@ -1,0 +1,233 @@
+/*
+ * oflib_b200 -- C ABI of the B200-native flow-field hot path (drop-in boundary for oflibnumpy's hot path).
+ *
+ * The reference (oflibnumpy v1.1.1) is pure Python: its "FFI" for this path is the set of call sites where its
+ * Python code enters third-party native code, plus the numpy array expressions around them. Each entry point below
+ * names the reference interface it replaces (file:line under /root/reference/src/oflibnumpy/). INTEGRATION.md shows
+ * the ctypes binding a maintainer of the reference would add at those call sites.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no C++/torch types.
+ *   - ofk_*  : device pointers owned by the caller, outputs pre-allocated by the caller, asynchronous on `stream`
+ *              (a cudaStream_t passed as void*; NULL = legacy default stream). No allocation inside unless a
+ *              workspace argument says so.
+ *   - ofh_*  : host pointers (numpy buffers, pinned or pageable); the library stages them through an internal
+ *              pinned/device ring and overlaps H2D, kernels and D2H. Synchronous: results are in the output buffers
+ *              on return.
+ *   - ofk_rt_*: the minimal runtime the Python shim needs (memory, streams, events); thin cudart wrappers.
+ *   - every function returns 0 on success or a negative OFK_E* code; ofk_last_error() returns a thread-local message.
+ *   - layouts are the reference's: flow vectors float32 [N,H,W,2] (channel 0 = horizontal u, +right; 1 = vertical v,
+ *     +down; flow_class.py:42-44), masks uint8 0/1 [N,H,W] (numpy bool), images [N,H,W,C] interleaved. N is the batch
+ *     axis this library adds (the reference has none; N = 1 reproduces it).
+ *   - base pointers should be 16-byte aligned (cudaMalloc / torch allocations are); unaligned pointers are accepted and
+ *     take a slower scalar path.
+ */
+#ifndef OFLIB_B200_H
+#define OFLIB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden; these are its exports */
+#endif
+
+#define OFK_VERSION 100
+
+/* error codes */
+#define OFK_OK 0
+#define OFK_EINVAL (-1)   /* bad argument (shape, enum, NULL) */
+#define OFK_ECUDA (-2)    /* CUDA runtime error, see ofk_last_error() */
+#define OFK_ENOMEM (-3)
+#define OFK_EUNSUPPORTED (-4)
+
+/* payload element types accepted by the warp (the dtypes cv2.remap accepts for the reference's calls) */
+#define OFK_U8 0
+#define OFK_I16 1
+#define OFK_U16 2
+#define OFK_F32 3
+#define OFK_F64 4
+
+/* interpolation arithmetic (OpenCV picks it from the dtype of the array handed to cv2.remap, which for Flow.apply is
+ * the numpy promotion of payload||mask -- flow_class.py:615,644):
+ *   NATIVE : by payload dtype: U8 -> 15-bit fixed point; I16/U16 -> float32 weights + round-half-even + saturate;
+ *            F32 -> float32; F64 -> float64 accumulation.
+ *   RINT   : U8 payload sampled as int16 (uint8 image || int8 ones-mask promotes to int16): float32 weights +
+ *            round-half-even. Ignored for other dtypes. */
+#define OFK_ARITH_NATIVE 0
+#define OFK_ARITH_RINT 1
+
+/* rule turning the valid-weight sum S (units of 1/1024) of a warped mask into a bool (the reference's `== 1` on the
+ * warped mask channel, flow_class.py:668, evaluated in the promoted dtype) */
+#define OFK_RULE_STRICT 0   /* float payloads:  S == 1024 */
+#define OFK_RULE_GT_HALF 1  /* int16 payloads:  S >  512  */
+#define OFK_RULE_GE_HALF 2  /* uint8 payloads:  S >= 512  */
+
+/* elementwise ops (flow_class.py:310-489) */
+#define OFK_OP_ADD 0
+#define OFK_OP_SUB 1
+#define OFK_OP_MUL 2
+#define OFK_OP_DIV 3
+#define OFK_OP_POW 4
+
+/* padding modes (flow_class.py:508-526 -> numpy.pad) */
+#define OFK_PAD_CONSTANT 0
+#define OFK_PAD_EDGE 1
+#define OFK_PAD_SYMMETRIC 2
+
+typedef void* ofk_stream_t; /* cudaStream_t */
+
+const char* ofk_last_error(void);
+int ofk_version(void);
+
+/* ------------------------------------------------------------------------------------------------ hot path, device */
+
+/* Target-referenced (backward) warp: replaces `cv2.remap(target, grid - flow, None, INTER_LINEAR)` in apply_flow
+ * (utils.py:231-236) together with the mask plumbing of Flow.apply around it (flow_class.py:631-680): the mask is
+ * warped in the same pass instead of being concatenated to the payload.
+ *   sample position of output pixel p: p + flow_sign * flow[p]   (flow_sign = -1 for a 't' flow; +1 evaluates
+ *   `flow.invert('t').apply(...)` of an 's' flow without materialising the negated field)
+ *   payload      [N,Hs,Ws,C] of `dtype`;  payload_mask [N,Hs,Ws] or NULL (= all valid)
+ *   flow         [N,H,W,2];               flow_mask    [N,H,W]  or NULL (= all valid), ANDed after warping
+ *   top,left     position of the flow frame inside the payload frame (Flow.apply `padding`; 0,0 if Hs==H, Ws==W)
+ *   cut != 0     out [N,H,W,C], out_mask [N,H,W];  cut == 0: out [N,Hs,Ws,C], out_mask [N,Hs,Ws] (flow = 0 and
+ *                out_mask = 0 outside the flow frame, flow_class.py:651-660,673-678)
+ *   out_mask may be NULL (no valid-area output); payload/out may be NULL with C = 0 (mask-only warp). */
+int ofk_warp_t(const void* payload, int dtype, int C, int arith, const float* flow, float flow_sign,
+               const uint8_t* payload_mask, const uint8_t* flow_mask, void* out, uint8_t* out_mask, int mask_rule,
+               int N, int H, int W, int Hs, int Ws, int top, int left, int cut, ofk_stream_t stream);
+
+/* Fused flow composition, mode 3: replaces `flow + flow.apply(self)` (ref 't', flow_class.py:1422) and
+ * `self + self.invert('t').apply(flow)` (ref 's', :1418) including the zero-flow early exits (:1338-1354):
+ *   ref 't': out[p] = B[p] + Q(A, p - B[p]),  out_mask[p] = Bm[p] & strict(Am taps)
+ *   ref 's': out[p] = A[p] + Q(B, p + A[p]),  out_mask[p] = Am[p] & strict(Bm taps)
+ * If A is zero on its valid pixels (|c| < thr when thr > 0, exact 0 otherwise) frame n of out is a copy of B (and of
+ * A if B is zero), as the reference returns that operand. flags (int32 [N][2], device) receives
+ * {A_nonzero, B_nonzero} per frame so the host can restore object identity; with flags == NULL the zero tests and
+ * the early exits are skipped (plain composition). Am/Bm may be NULL (all valid). */
+int ofk_combine3(const float* A, const uint8_t* Am, const float* B, const uint8_t* Bm, int ref /* 's' or 't' */,
+                 float thr, float* out, uint8_t* out_mask, int* flags, int N, int H, int W, ofk_stream_t stream);
+
+/* Valid area of a 't'-sampling warp without payload: replaces `apply_flow(+-vecs, np.ones(shape), 't') == 1` then
+ * `&= mask` in valid_target (ref 't', flow_class.py:1148-1150; flow_sign = -1) and valid_source (ref 's',
+ * :1179-1183; flow_sign = +1). */
+int ofk_valid_geom_t(const float* flow, float flow_sign, const uint8_t* flow_mask, uint8_t* out, int N, int H, int W,
+                     ofk_stream_t stream);
+
+/* Affine / projective field generator: replaces flow_from_matrix (utils.py:91-111). mats: N row-major 3x3 float64
+ * matrices (for ref 't' the caller passes pinv(M), utils.py:343), on the host if mats_on_host != 0 (N <= 64), else on
+ * the device. out[n,y,x] = sign * float32( proj(M_n [x,y,1]) - [x,y] ), float64 arithmetic in the reference's
+ * rounding sequence. sign = +1 for 's', -1 for 't'. */
+int ofk_from_matrix(const double* mats, int mats_on_host, float sign, float* out, int N, int H, int W,
+                    ofk_stream_t stream);
+
+/* Flow arithmetic: replaces Flow.__add__/__sub__ (flow_class.py:310-375): out = A op B (float32), and when out_mask
+ * is given out_mask = Am & Bm (NULL mask = all valid). op in {OFK_OP_ADD, OFK_OP_SUB}. */
+int ofk_addsub(int op, const float* A, const uint8_t* Am, const float* B, const uint8_t* Bm, float* out,
+               uint8_t* out_mask, int N, int H, int W, ofk_stream_t stream);
+
+/* Per-channel scaling: replaces Flow.__mul__/__truediv__/__pow__/__neg__ (flow_class.py:377-489) for scalar and
+ * 2-element multipliers: out[...,0] = A[...,0] op su, out[...,1] = A[...,1] op sv. in_f64 != 0 evaluates in float64
+ * and rounds to float32 (numpy promotion for list / array operands); otherwise float32 (python-scalar operands). */
+int ofk_scale(int op, const float* A, double su, double sv, int in_f64, float* out, size_t n_pixels,
+              ofk_stream_t stream);
+
+/* Array operands of the same family (also ADD / SUB of a float64 array, Flow + ndarray): M is float64 [N,H,W]
+ * (m_channels = 1) or [N,H,W,2] (m_channels = 2); evaluated in float64, rounded to float32 like numpy's promotion. */
+int ofk_scale_array(int op, const float* A, const double* M, int m_channels, float* out, size_t n_pixels,
+                    ofk_stream_t stream);
+
+/* Zero test gating the early exits: replaces Flow.is_zero / is_zero_flow (flow_class.py:1230-1245,
+ * utils.py:527-544). flags int32 [N] (device) receives 1 where frame n has a component c with |c| >= thr
+ * (thr > 0) or c != 0 (thr == 0) on a pixel whose mask is set (mask NULL = all pixels). The call zeroes flags. */
+int ofk_nonzero_flags(const float* F, const uint8_t* M, float thr, int* flags, int N, int H, int W,
+                      ofk_stream_t stream);
+
+/* Finite check done by the reference in every Flow construction (flow_class.py:78-79): flag (int32, device) is set
+ * to 1 if any of the n floats is NaN or +-Inf. The call zeroes flag. */
+int ofk_check_finite(const float* data, size_t n, int* flag, ofk_stream_t stream);
+
+/* Flow.pad (flow_class.py:508-526): vecs padded with mode, mask padded with 0. in [N,H,W,(2)] ->
+ * out [N,H+top+bottom,W+left+right,(2)]. Either pair (vecs/out_vecs or mask/out_mask) may be NULL. */
+int ofk_pad(const float* vecs, const uint8_t* mask, float* out_vecs, uint8_t* out_mask, int mode, int N, int H, int W,
+            int top, int bottom, int left, int right, ofk_stream_t stream);
+
+/* out = a & b for 0/1 masks (the `target_mask & self.mask` of Flow.apply for 's' flows, flow_class.py:634-643). */
+int ofk_mask_and(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, ofk_stream_t stream);
+
+/* Rectangular cut of an [N,H,W] array of elem_bytes-sized items to [N,h,w] at (y0,x0): the `cut` of Flow.apply
+ * (flow_class.py:663-664) and Flow.__getitem__ for contiguous windows. */
+int ofk_crop(const void* in, void* out, int elem_bytes, int N, int H, int W, int y0, int x0, int h, int w,
+             ofk_stream_t stream);
+
+/* Masked extent reduction of Flow.get_padding (flow_class.py:1197-1228): out4 (float32 [N][4], device) receives
+ * {min_y, max_y, min_x, max_x} of p - sign*threshold(flow)[p] over valid pixels (sign = +1 for 't', -1 for 's'). */
+int ofk_extent(const float* flow, const uint8_t* mask, float sign, float thr, float* out4, int N, int H, int W,
+               ofk_stream_t stream);
+
+/* points_inside_area (utils.py:283-295): pts float64 [n][2] (row, col) rounded half-even like numpy.round. */
+int ofk_points_inside_area(const double* pts, size_t n, int H, int W, uint8_t* out, ofk_stream_t stream);
+
+/* ------------------------------------------------------------------------------- source-referenced path, device */
+
+/* Source-referenced (forward) resampling: replaces `griddata(grid + flow, payload, grid, 'linear')` + nan_to_num in
+ * apply_flow (utils.py:237-258) with a rasterisation of the displaced pixel grid (two triangles per cell, Delaunay
+ * diagonal). payload is float32 [N,H,W,C] (C <= 8); the mask channel is resampled with the payload and thresholded
+ * `== 1` within OFK_FWD_MASK_EPS. point_mask (consider_mask, or NULL) removes invalid source points: cells touching
+ * a removed point are not rasterised (documented deviation from Qhull's gap bridging).
+ * ws: workspace of ofk_forward_s_workspace(N,H,W) bytes (device). */
+size_t ofk_forward_s_workspace(int N, int H, int W);
+int ofk_forward_s(const float* payload, int C, const float* flow, float flow_sign, const uint8_t* payload_mask,
+                  const uint8_t* point_mask, float* out, uint8_t* out_mask, int N, int H, int W, void* ws,
+                  size_t ws_bytes, ofk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ host-buffer API */
+
+/* Same operations on HOST buffers (what `apply_flow(flow, img, 't')` / `Flow.apply(..., return_valid_area=True)` and
+ * `combine_flows(a, b, 3, ref)` / `Flow.combine_with` look like from numpy): frames are streamed through an internal
+ * ring of pinned staging + device buffers on `device`, copies overlapped with kernels. Synchronous. */
+int ofh_warp_t(const void* payload, int dtype, int C, int arith, const float* flow, float flow_sign,
+               const uint8_t* payload_mask, const uint8_t* flow_mask, void* out, uint8_t* out_mask, int mask_rule,
+               int N, int H, int W, int device);
+int ofh_combine3(const float* A, const uint8_t* Am, const float* B, const uint8_t* Bm, int ref, float thr, float* out,
+                 uint8_t* out_mask, int* flags, int N, int H, int W, int device);
+/* release the internal ring (also done at process exit) */
+int ofh_release(void);
+
+/* ------------------------------------------------------------------------------------------------------- runtime */
+int ofk_rt_device_count(int* count);
+int ofk_rt_set_device(int device);
+int ofk_rt_get_device(int* device);
+int ofk_rt_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes, size_t* total_mem);
+int ofk_rt_malloc(void** dptr, size_t bytes, ofk_stream_t stream); /* stream-ordered pool allocation, current device */
+int ofk_rt_free(void* dptr, ofk_stream_t stream);
+int ofk_rt_host_alloc(void** hptr, size_t bytes);          /* pinned */
+int ofk_rt_host_free(void* hptr);
+int ofk_rt_host_register(void* hptr, size_t bytes);        /* pin an existing numpy buffer */
+int ofk_rt_host_unregister(void* hptr);
+int ofk_rt_memcpy_h2d(void* dst, const void* src, size_t bytes, ofk_stream_t stream);
+int ofk_rt_memcpy_d2h(void* dst, const void* src, size_t bytes, ofk_stream_t stream);
+int ofk_rt_memcpy_d2d(void* dst, const void* src, size_t bytes, ofk_stream_t stream);
+int ofk_rt_memset(void* dst, int value, size_t bytes, ofk_stream_t stream);
+int ofk_rt_stream_create(ofk_stream_t* stream);
+int ofk_rt_stream_destroy(ofk_stream_t stream);
+int ofk_rt_stream_sync(ofk_stream_t stream);
+int ofk_rt_device_sync(void);
+int ofk_rt_event_create(void** event);
+int ofk_rt_event_destroy(void* event);
+int ofk_rt_event_record(void* event, ofk_stream_t stream);
+int ofk_rt_event_sync(void* event);
+int ofk_rt_event_elapsed_ms(void* start, void* stop, float* ms);
+/* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */
+unsigned long long ofk_rt_launch_count(void);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* OFLIB_B200_H */

@@ -1,0 +1,187 @@
+"""Device-level operations on batched DeviceArrays: one function per C-ABI hot-path entry point.
+
+Shapes: flow vectors [N,H,W,2] float32, masks [N,H,W] uint8 (0/1), payloads [N,H,W,C]. Everything is asynchronous on
+the current stream (device.set_stream) unless a result has to be read on the host.
+"""
+import numpy as np
+
+from . import _lib
+from . import device as dev
+from .device import DeviceArray
+
+DTYPE_CODES = {np.dtype('uint8'): _lib.U8, np.dtype('int16'): _lib.I16, np.dtype('uint16'): _lib.U16,
+               np.dtype('float32'): _lib.F32, np.dtype('float64'): _lib.F64}
+
+
+def _p(a):
+    return None if a is None else a.ptr
+
+
+def dtype_code(dtype):
+    try:
+        return DTYPE_CODES[np.dtype(dtype)]
+    except KeyError:
+        raise TypeError("Error applying flow: target dtype {} is not supported by the bilinear warp (supported: "
+                        "uint8, int16, uint16, float32, float64 -- the dtypes cv2.remap accepts)".format(dtype))
+
+
+def promoted_rule(payload_dtype, mask_is_bool):
+    """(arith, mask_rule) of Flow.apply's `payload || mask` concatenation (flow_class.py:615,626,644): the numpy
+    promotion of the payload dtype with int8 (no target_mask: np.ones(..., 'b')) or bool (target_mask given) decides
+    which cv2.remap arithmetic samples both image and mask."""
+    dt = np.dtype(payload_dtype)
+    if dt == np.uint8:
+        return (_lib.ARITH_NATIVE, _lib.RULE_GE_HALF) if mask_is_bool else (_lib.ARITH_RINT, _lib.RULE_GT_HALF)
+    if dt == np.int16:
+        return _lib.ARITH_NATIVE, _lib.RULE_GT_HALF
+    if dt == np.uint16:
+        if not mask_is_bool:
+            raise TypeError("Error applying flow: a uint16 target with return_valid_area needs a boolean target_mask "
+                            "(uint16 || int8 promotes to int32, which the bilinear warp -- like cv2.remap -- rejects)")
+        return _lib.ARITH_NATIVE, _lib.RULE_GT_HALF
+    if dt in (np.float32, np.float64):
+        return _lib.ARITH_NATIVE, _lib.RULE_STRICT
+    dtype_code(dt)  # raises
+    raise AssertionError
+
+
+def warp_t(flow, sign, payload=None, payload_mask=None, flow_mask=None, want_mask=False, arith=_lib.ARITH_NATIVE,
+           rule=_lib.RULE_STRICT, placement=None, cut=True):
+    """Backward warp (ofk_warp_t). placement = (top, left) of the flow frame inside the payload frame."""
+    n, h, w = flow.shape[:3]
+    if payload is not None:
+        hs, ws, c = payload.shape[1:4]
+        code = dtype_code(payload.dtype)
+    else:
+        hs, ws = (payload_mask.shape[1:3] if payload_mask is not None else (h, w))
+        c, code = 0, _lib.U8
+    top, left = placement if placement is not None else (0, 0)
+    ho, wo = (h, w) if cut else (hs, ws)
+    out = DeviceArray.empty((n, ho, wo, c), payload.dtype) if payload is not None else None
+    omask = DeviceArray.empty((n, ho, wo), np.uint8) if want_mask else None
+    _lib.call('ofk_warp_t', _p(payload), code, c, arith, flow.ptr, float(sign), _p(payload_mask), _p(flow_mask),
+              _p(out), _p(omask), rule, n, h, w, hs, ws, top, left, 1 if cut else 0, dev.current_stream())
+    return out, omask
+
+
+def combine3(a, am, b, bm, ref, thr=0.0, want_flags=True):
+    n, h, w = a.shape[:3]
+    out = DeviceArray.empty((n, h, w, 2), np.float32)
+    omask = DeviceArray.empty((n, h, w), np.uint8)
+    flags = DeviceArray.empty((n, 2), np.int32) if want_flags else None
+    _lib.call('ofk_combine3', a.ptr, _p(am), b.ptr, _p(bm), ord(ref), float(thr), out.ptr, omask.ptr, _p(flags), n, h,
+              w, dev.current_stream())
+    return out, omask, flags
+
+
+def valid_geom_t(flow, sign, flow_mask):
+    n, h, w = flow.shape[:3]
+    out = DeviceArray.empty((n, h, w), np.uint8)
+    _lib.call('ofk_valid_geom_t', flow.ptr, float(sign), _p(flow_mask), out.ptr, n, h, w, dev.current_stream())
+    return out
+
+
+def from_matrix(mats, shape, sign):
+    """mats: numpy (N,3,3) float64 on the host (N <= 64) or a DeviceArray (N,3,3) float64."""
+    h, w = shape
+    if isinstance(mats, DeviceArray):
+        n = mats.shape[0]
+        out = DeviceArray.empty((n, h, w, 2), np.float32)
+        _lib.call('ofk_from_matrix', mats.ptr, 0, float(sign), out.ptr, n, h, w, dev.current_stream())
+        return out
+    m = np.ascontiguousarray(mats, dtype=np.float64).reshape(-1, 3, 3)
+    n = m.shape[0]
+    if n > 64:
+        return from_matrix(DeviceArray.from_numpy(m), shape, sign)
+    out = DeviceArray.empty((n, h, w, 2), np.float32)
+    _lib.call('ofk_from_matrix', m.ctypes.data, 1, float(sign), out.ptr, n, h, w, dev.current_stream())
+    return out
+
+
+def addsub(op, a, am, b, bm, want_mask=True):
+    n, h, w = a.shape[:3]
+    out = DeviceArray.empty((n, h, w, 2), np.float32)
+    omask = DeviceArray.empty((n, h, w), np.uint8) if want_mask else None
+    _lib.call('ofk_addsub', op, a.ptr, _p(am), b.ptr, _p(bm), out.ptr, _p(omask), n, h, w, dev.current_stream())
+    return out, omask
+
+
+def scale(op, a, su, sv, in_f64):
+    out = DeviceArray.empty(a.shape, np.float32)
+    _lib.call('ofk_scale', op, a.ptr, float(su), float(sv), 1 if in_f64 else 0, out.ptr, a.size // 2,
+              dev.current_stream())
+    return out
+
+
+def scale_array(op, a, m, channels):
+    out = DeviceArray.empty(a.shape, np.float32)
+    _lib.call('ofk_scale_array', op, a.ptr, m.ptr, channels, out.ptr, a.size // 2, dev.current_stream())
+    return out
+
+
+def nonzero_flags(flow, mask, thr):
+    """Host numpy int32 [N]: 1 where the frame has a non-zero (resp. >= thr) vector on a valid pixel. Synchronises."""
+    n, h, w = flow.shape[:3]
+    flags = DeviceArray.empty((n,), np.int32)
+    _lib.call('ofk_nonzero_flags', flow.ptr, _p(mask), float(thr), flags.ptr, n, h, w, dev.current_stream())
+    return flags.numpy()
+
+
+def all_finite(arr):
+    flag = DeviceArray.empty((1,), np.int32)
+    _lib.call('ofk_check_finite', arr.ptr, arr.size, flag.ptr, dev.current_stream())
+    return int(flag.numpy()[0]) == 0
+
+
+def pad(vecs, mask, padding, mode):
+    top, bottom, left, right = padding
+    n, h, w = (vecs if vecs is not None else mask).shape[:3]
+    ho, wo = h + top + bottom, w + left + right
+    ov = DeviceArray.empty((n, ho, wo, 2), np.float32) if vecs is not None else None
+    om = DeviceArray.empty((n, ho, wo), np.uint8)
+    _lib.call('ofk_pad', _p(vecs), _p(mask), _p(ov), om.ptr, _lib.PAD_MODES[mode], n, h, w, top, bottom, left, right,
+              dev.current_stream())
+    return ov, om
+
+
+def mask_and(a, b):
+    out = DeviceArray.empty(a.shape, np.uint8)
+    _lib.call('ofk_mask_and', a.ptr, b.ptr, out.ptr, a.size, dev.current_stream())
+    return out
+
+
+def crop(arr, y0, x0, h, w):
+    """Cut [N,H,W,...] to [N,h,w,...]."""
+    n, hh, ww = arr.shape[:3]
+    inner = int(np.prod(arr.shape[3:], dtype=np.int64)) * arr.dtype.itemsize
+    out = DeviceArray.empty((n, h, w) + arr.shape[3:], arr.dtype)
+    _lib.call('ofk_crop', arr.ptr, out.ptr, inner, n, hh, ww, y0, x0, h, w, dev.current_stream())
+    return out
+
+
+def extent(flow, mask, sign, thr):
+    n, h, w = flow.shape[:3]
+    out = DeviceArray.empty((n, 4), np.float32)
+    _lib.call('ofk_extent', flow.ptr, _p(mask), float(sign), float(thr), out.ptr, n, h, w, dev.current_stream())
+    return out.numpy()
+
+
+def points_inside_area(pts, shape):
+    p = np.ascontiguousarray(pts, dtype=np.float64)
+    d = DeviceArray.from_numpy(p)
+    out = DeviceArray.empty((p.shape[0],), np.uint8)
+    _lib.call('ofk_points_inside_area', d.ptr, p.shape[0], int(shape[0]), int(shape[1]), out.ptr, dev.current_stream())
+    return out.numpy().astype(bool)
+
+
+def forward_s(flow, sign, payload, payload_mask=None, point_mask=None, want_mask=True):
+    """Forward (source-referenced) resampling of a float32 payload [N,H,W,C] (ofk_forward_s)."""
+    n, h, w = flow.shape[:3]
+    c = payload.shape[3] if payload is not None else 0
+    out = DeviceArray.empty((n, h, w, c), np.float32) if c else None
+    omask = DeviceArray.empty((n, h, w), np.uint8) if want_mask else None
+    ws_bytes = _lib.call('ofk_forward_s_workspace', n, h, w)
+    ws = DeviceArray.empty((max(ws_bytes, 16),), np.uint8)
+    _lib.call('ofk_forward_s', _p(payload), c, flow.ptr, float(sign), _p(payload_mask), _p(point_mask), _p(out),
+              _p(omask), n, h, w, ws.ptr, ws_bytes, dev.current_stream())
+    return out, omask

@@ -1,0 +1,385 @@
+// Streaming (one-touch) kernels of the flow algebra for sm_100a: Flow.__add__/__sub__/__mul__/... (flow_class.py:310-489),
+// the zero / finite tests (flow_class.py:78-79,1230-1245; utils.py:298-316,527-544), Flow.pad (:508-526), the extent
+// reduction of get_padding (:1197-1228) and points_inside_area (utils.py:283-295). All HBM-bound; 128-bit accesses,
+// grid-stride loops sized to the SM count.
+#include <math.h>
+
+#include "ofk_common.cuh"
+
+namespace ofk {
+
+static inline int stream_grid(size_t work_items, int threads) {
+    size_t blocks = (work_items + threads - 1) / threads;
+    size_t cap = (size_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+// ------------------------------------------------------------------------------------------------- add / sub
+template <bool SUB>
+__global__ void __launch_bounds__(256) addsub_kernel(const float* __restrict__ A, const uint8_t* __restrict__ Am,
+                                                     const float* __restrict__ B, const uint8_t* __restrict__ Bm,
+                                                     float* __restrict__ out, uint8_t* __restrict__ om, size_t npix,
+                                                     int vec_ok) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    size_t done = 0;
+    if (vec_ok) {  // 4 pixels (8 floats, 4 mask bytes) per iteration
+        const size_t groups = npix / 4;
+        for (size_t g = tid; g < groups; g += nth) {
+            const float4* a4 = reinterpret_cast<const float4*>(A) + g * 2;
+            const float4* b4 = reinterpret_cast<const float4*>(B) + g * 2;
+            float4 a0 = ld_stream_f4(a4), a1 = ld_stream_f4(a4 + 1), b0 = ld_stream_f4(b4), b1 = ld_stream_f4(b4 + 1);
+            float4 r0, r1;
+            if (SUB) {
+                r0 = make_float4(a0.x - b0.x, a0.y - b0.y, a0.z - b0.z, a0.w - b0.w);
+                r1 = make_float4(a1.x - b1.x, a1.y - b1.y, a1.z - b1.z, a1.w - b1.w);
+            } else {
+                r0 = make_float4(a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w);
+                r1 = make_float4(a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w);
+            }
+            float4* o4 = reinterpret_cast<float4*>(out) + g * 2;
+            st_stream_f4(o4, r0);
+            st_stream_f4(o4 + 1, r1);
+            if (om != nullptr) {
+                uint32_t ma = Am ? ld_stream_u32(reinterpret_cast<const uint32_t*>(Am) + g) : 0x01010101u;
+                uint32_t mb = Bm ? ld_stream_u32(reinterpret_cast<const uint32_t*>(Bm) + g) : 0x01010101u;
+                st_stream_u32(reinterpret_cast<uint32_t*>(om) + g, ma & mb);
+            }
+        }
+        done = groups * 4;
+    }
+    for (size_t i = done + tid; i < npix; i += nth) {
+        out[i * 2] = SUB ? A[i * 2] - B[i * 2] : A[i * 2] + B[i * 2];
+        out[i * 2 + 1] = SUB ? A[i * 2 + 1] - B[i * 2 + 1] : A[i * 2 + 1] + B[i * 2 + 1];
+        if (om != nullptr) om[i] = ((Am ? Am[i] : 1) & (Bm ? Bm[i] : 1)) ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------- scaling family
+template <typename R>
+__device__ __forceinline__ R apply_op(int op, R a, R s) {
+    switch (op) {
+        case OFK_OP_ADD: return a + s;
+        case OFK_OP_SUB: return a - s;
+        case OFK_OP_MUL: return a * s;
+        case OFK_OP_DIV: return a / s;
+        default: return pow(a, s);
+    }
+}
+
+__global__ void __launch_bounds__(256) scale_kernel(int op, const float* __restrict__ A, double su, double sv,
+                                                    int in_f64, float* __restrict__ out, size_t npix) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    const float fu = (float)su, fv = (float)sv;
+    for (size_t i = tid; i < npix; i += nth) {
+        const float2 a = reinterpret_cast<const float2*>(A)[i];
+        float2 r;
+        if (in_f64) {
+            r.x = (float)apply_op<double>(op, (double)a.x, su);
+            r.y = (float)apply_op<double>(op, (double)a.y, sv);
+        } else {
+            r.x = apply_op<float>(op, a.x, fu);
+            r.y = apply_op<float>(op, a.y, fv);
+        }
+        reinterpret_cast<float2*>(out)[i] = r;
+    }
+}
+
+__global__ void __launch_bounds__(256) scale_array_kernel(int op, const float* __restrict__ A,
+                                                          const double* __restrict__ M, int mc,
+                                                          float* __restrict__ out, size_t npix) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = tid; i < npix; i += nth) {
+        const float2 a = reinterpret_cast<const float2*>(A)[i];
+        const double mu = mc == 1 ? M[i] : M[i * 2], mv = mc == 1 ? M[i] : M[i * 2 + 1];
+        float2 r;
+        r.x = (float)apply_op<double>(op, (double)a.x, mu);
+        r.y = (float)apply_op<double>(op, (double)a.y, mv);
+        reinterpret_cast<float2*>(out)[i] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------- reductions
+__device__ __forceinline__ bool nz(float c, float thr) { return thr > 0.f ? !(c < thr && c > -thr) : (c != 0.f); }
+
+__global__ void __launch_bounds__(256) nonzero_kernel(const float* __restrict__ F, const uint8_t* __restrict__ M,
+                                                      float thr, int* __restrict__ flags, size_t frame) {
+    const int n = blockIdx.y;
+    const float2* f = reinterpret_cast<const float2*>(F) + (size_t)n * frame;
+    const uint8_t* m = M ? M + (size_t)n * frame : nullptr;
+    bool any = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < frame; i += (size_t)gridDim.x * blockDim.x) {
+        const float2 v = f[i];
+        const bool valid = m ? m[i] != 0 : true;
+        any |= valid && (nz(v.x, thr) || nz(v.y, thr));
+    }
+    if (__syncthreads_or(any) && threadIdx.x == 0) flags[n] = 1;
+}
+
+__global__ void __launch_bounds__(256) finite_kernel(const float* __restrict__ d, size_t n, int* __restrict__ flag) {
+    bool bad = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        bad |= !isfinite(d[i]);
+    if (__syncthreads_or(bad) && threadIdx.x == 0) *flag = 1;
+}
+
+// float atomic min/max through the ordered-int trick
+__device__ __forceinline__ void atomic_min_f(float* addr, float v) {
+    if (v >= 0.f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f(float* addr, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+__global__ void extent_init_kernel(float* out4, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) {
+        out4[i * 4 + 0] = INFINITY;
+        out4[i * 4 + 1] = -INFINITY;
+        out4[i * 4 + 2] = INFINITY;
+        out4[i * 4 + 3] = -INFINITY;
+    }
+}
+
+// get_padding: v = threshold(flow); ('s': v *= -1); v[...,0] -= col; v[...,1] -= row; v *= -1  (all float32)
+__global__ void __launch_bounds__(256) extent_kernel(const float* __restrict__ F, const uint8_t* __restrict__ M,
+                                                     float sign, float thr, float* __restrict__ out4, int H, int W) {
+    const int n = blockIdx.y;
+    const size_t frame = (size_t)H * W;
+    const float2* f = reinterpret_cast<const float2*>(F) + (size_t)n * frame;
+    const uint8_t* m = M ? M + (size_t)n * frame : nullptr;
+    float mny = INFINITY, mxy = -INFINITY, mnx = INFINITY, mxx = -INFINITY;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < frame; i += (size_t)gridDim.x * blockDim.x) {
+        if (m && !m[i]) continue;
+        float2 v = f[i];
+        if (v.x < thr && v.x > -thr) v.x = 0.f;
+        if (v.y < thr && v.y > -thr) v.y = 0.f;
+        const int y = (int)(i / W), x = (int)(i - (size_t)y * W);
+        const float ex = -(__fsub_rn(sign * v.x, (float)x));
+        const float ey = -(__fsub_rn(sign * v.y, (float)y));
+        mny = fminf(mny, ey);
+        mxy = fmaxf(mxy, ey);
+        mnx = fminf(mnx, ex);
+        mxx = fmaxf(mxx, ex);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+        mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+        mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (mny != INFINITY) atomic_min_f(out4 + n * 4 + 0, mny);
+        if (mxy != -INFINITY) atomic_max_f(out4 + n * 4 + 1, mxy);
+        if (mnx != INFINITY) atomic_min_f(out4 + n * 4 + 2, mnx);
+        if (mxx != -INFINITY) atomic_max_f(out4 + n * 4 + 3, mxx);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------- pad
+__device__ __forceinline__ int pad_index(int i, int n, int mode) {  // i relative to the unpadded axis, may be outside
+    if ((unsigned)i < (unsigned)n) return i;
+    if (mode == OFK_PAD_EDGE) return i < 0 ? 0 : n - 1;
+    // numpy 'symmetric': reflect including the edge sample, period 2n
+    int p = 2 * n;
+    int r = i % p;
+    if (r < 0) r += p;
+    return r < n ? r : p - 1 - r;
+}
+
+__global__ void __launch_bounds__(256) pad_kernel(const float* __restrict__ vecs, const uint8_t* __restrict__ mask,
+                                                  float* __restrict__ ov, uint8_t* __restrict__ om, int mode, int H,
+                                                  int W, int Ho, int Wo, int top, int left) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int n = blockIdx.z;
+    if (x >= Wo || y >= Ho) return;
+    const int ys = y - top, xs = x - left;
+    const bool inside = (unsigned)ys < (unsigned)H && (unsigned)xs < (unsigned)W;
+    const size_t o = ((size_t)n * Ho + y) * Wo + x;
+    if (ov != nullptr) {
+        float2 v = make_float2(0.f, 0.f);
+        if (inside || mode != OFK_PAD_CONSTANT) {
+            const int yy = pad_index(ys, H, mode), xx = pad_index(xs, W, mode);
+            v = reinterpret_cast<const float2*>(vecs)[((size_t)n * H + yy) * W + xx];
+        }
+        reinterpret_cast<float2*>(ov)[o] = v;
+    }
+    if (om != nullptr) om[o] = inside ? (mask ? mask[((size_t)n * H + ys) * W + xs] : 1) : 0;
+}
+
+__global__ void __launch_bounds__(256) mask_and_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
+                                                       uint8_t* __restrict__ out, size_t n, int vec_ok) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    size_t done = 0;
+    if (vec_ok) {
+        const size_t words = n / 4;
+        for (size_t i = tid; i < words; i += nth)
+            reinterpret_cast<uint32_t*>(out)[i] =
+                reinterpret_cast<const uint32_t*>(a)[i] & reinterpret_cast<const uint32_t*>(b)[i];
+        done = words * 4;
+    }
+    for (size_t i = done + tid; i < n; i += nth) out[i] = (a[i] & b[i]) ? 1 : 0;
+}
+
+// rectangular crop of an [N,H,W] array of `eb`-byte elements to [N,h,w] starting at (y0,x0)
+__global__ void __launch_bounds__(256) crop_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int eb,
+                                                   int H, int W, int y0, int x0, int h, int w) {
+    const int n = blockIdx.z, y = blockIdx.y;
+    const size_t row_bytes = (size_t)w * eb;
+    const uint8_t* src = in + (((size_t)n * H + y0 + y) * W + x0) * eb;
+    uint8_t* dst = out + ((size_t)n * h + y) * row_bytes;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < row_bytes; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(256) inside_kernel(const double* __restrict__ pts, size_t n, int H, int W,
+                                                     uint8_t* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const long long r = __double2ll_rn(pts[i * 2]), c = __double2ll_rn(pts[i * 2 + 1]);  // numpy.round: half-even
+        out[i] = (r >= 0 && r <= H - 1 && c >= 0 && c <= W - 1) ? 1 : 0;
+    }
+}
+
+}  // namespace ofk
+
+using namespace ofk;
+
+extern "C" int ofk_addsub(int op, const float* A, const uint8_t* Am, const float* B, const uint8_t* Bm, float* out,
+                          uint8_t* out_mask, int N, int H, int W, ofk_stream_t stream) {
+    OFK_CHECK_ARG(op == OFK_OP_ADD || op == OFK_OP_SUB, "ofk_addsub: op must be ADD or SUB");
+    OFK_CHECK_ARG(A && B && out, "ofk_addsub: NULL operand");
+    OFK_CHECK_ARG(N >= 0 && H > 0 && W > 0, "ofk_addsub: bad shape");
+    const size_t npix = (size_t)N * H * W;
+    if (npix == 0) return OFK_OK;
+    const int vec_ok = aligned16(A) && aligned16(B) && aligned16(out) && (!Am || aligned16(Am)) &&
+                       (!Bm || aligned16(Bm)) && (!out_mask || aligned16(out_mask));
+    const int grid = stream_grid(npix / 4 + 1, 256);
+    if (op == OFK_OP_SUB)
+        addsub_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(A, Am, B, Bm, out, out_mask, npix, vec_ok);
+    else
+        addsub_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(A, Am, B, Bm, out, out_mask, npix, vec_ok);
+    OFK_LAUNCHED();
+    return OFK_OK;
+}
+
+extern "C" int ofk_scale(int op, const float* A, double su, double sv, int in_f64, float* out, size_t n_pixels,
+                         ofk_stream_t stream) {
+    OFK_CHECK_ARG(op >= OFK_OP_MUL && op <= OFK_OP_POW, "ofk_scale: op must be MUL, DIV or POW");
+    OFK_CHECK_ARG(A && out, "ofk_scale: NULL operand");
+    OFK_CHECK_ARG(((uintptr_t)A & 7) == 0 && ((uintptr_t)out & 7) == 0, "ofk_scale: pointers must be 8-byte aligned");
+    if (n_pixels == 0) return OFK_OK;
+    scale_kernel<<<stream_grid(n_pixels, 256), 256, 0, as_stream(stream)>>>(op, A, su, sv, in_f64, out, n_pixels);
+    OFK_LAUNCHED();
+    return OFK_OK;
+}
+
+extern "C" int ofk_scale_array(int op, const float* A, const double* M, int m_channels, float* out, size_t n_pixels,
+                               ofk_stream_t stream) {
+    OFK_CHECK_ARG(op >= OFK_OP_ADD && op <= OFK_OP_POW, "ofk_scale_array: unknown op %d", op);
+    OFK_CHECK_ARG(A && M && out, "ofk_scale_array: NULL operand");
+    OFK_CHECK_ARG(m_channels == 1 || m_channels == 2, "ofk_scale_array: m_channels must be 1 or 2");
+    OFK_CHECK_ARG(((uintptr_t)A & 7) == 0 && ((uintptr_t)out & 7) == 0, "ofk_scale_array: pointers must be 8-byte aligned");
+    if (n_pixels == 0) return OFK_OK;
+    scale_array_kernel<<<stream_grid(n_pixels, 256), 256, 0, as_stream(stream)>>>(op, A, M, m_channels, out, n_pixels);
+    OFK_LAUNCHED();
+    return OFK_OK;
+}
+
+extern "C" int ofk_nonzero_flags(const float* F, const uint8_t* M, float thr, int* flags, int N, int H, int W,
+                                 ofk_stream_t stream) {
+    OFK_CHECK_ARG(F && flags, "ofk_nonzero_flags: NULL argument");
+    OFK_CHECK_ARG(N >= 0 && H > 0 && W > 0 && N <= 65535, "ofk_nonzero_flags: bad shape");
+    OFK_CHECK_ARG(((uintptr_t)F & 7) == 0, "ofk_nonzero_flags: F must be 8-byte aligned");
+    if (N == 0) return OFK_OK;
+    cudaStream_t st = as_stream(stream);
+    OFK_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)N, st));
+    const size_t frame = (size_t)H * W;
+    int bx = (int)((frame + 256 * 8 - 1) / (256 * 8));
+    const int cap = (sm_count() * 16 + N - 1) / N;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    nonzero_kernel<<<dim3(bx, N), 256, 0, st>>>(F, M, thr, flags, frame);
+    OFK_LAUNCHED();
+    return OFK_OK;
+}
+
+extern "C" int ofk_check_finite(const float* data, size_t n, int* flag, ofk_stream_t stream) {
+    OFK_CHECK_ARG(data && flag, "ofk_check_finite: NULL argument");
+    cudaStream_t st = as_stream(stream);
+    OFK_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    if (n == 0) return OFK_OK;
+    finite_kernel<<<stream_grid(n / 4 + 1, 256), 256, 0, st>>>(data, n, flag);
+    OFK_LAUNCHED();
+    return OFK_OK;
+}
+
+extern "C" int ofk_pad(const float* vecs, const uint8_t* mask, float* out_vecs, uint8_t* out_mask, int mode, int N,
+                       int H, int W, int top, int bottom, int left, int right, ofk_stream_t stream) {
+    OFK_CHECK_ARG(mode >= OFK_PAD_CONSTANT && mode <= OFK_PAD_SYMMETRIC, "ofk_pad: unknown mode %d", mode);
+    OFK_CHECK_ARG(N >= 0 && H > 0 && W > 0 && top >= 0 && bottom >= 0 && left >= 0 && right >= 0, "ofk_pad: bad shape");
+    OFK_CHECK_ARG((out_vecs == nullptr) || vecs != nullptr, "ofk_pad: out_vecs given without vecs");
+    OFK_CHECK_ARG(out_vecs != nullptr || out_mask != nullptr, "ofk_pad: nothing to do");
+    OFK_CHECK_ARG(!out_vecs || ((((uintptr_t)vecs | (uintptr_t)out_vecs) & 7) == 0), "ofk_pad: vecs must be 8-byte aligned");
+    if (N == 0) return OFK_OK;
+    OFK_CHECK_ARG(N <= 65535, "ofk_pad: N too large");
+    const int Ho = H + top + bottom, Wo = W + left + right;
+    dim3 grid((Wo + 31) / 32, (Ho + 7) / 8, N);
+    pad_kernel<<<grid, 256, 0, as_stream(stream)>>>(vecs, mask, out_vecs, out_mask, mode, H, W, Ho, Wo, top, left);
+    OFK_LAUNCHED();
+    return OFK_OK;
+}
+
+extern "C" int ofk_extent(const float* flow, const uint8_t* mask, float sign, float thr, float* out4, int N, int H,
+                          int W, ofk_stream_t stream) {
+    OFK_CHECK_ARG(flow && out4, "ofk_extent: NULL argument");
+    OFK_CHECK_ARG(N >= 0 && H > 0 && W > 0 && N <= 65535, "ofk_extent: bad shape");
+    OFK_CHECK_ARG(((uintptr_t)flow & 7) == 0, "ofk_extent: flow must be 8-byte aligned");
+    if (N == 0) return OFK_OK;
+    cudaStream_t st = as_stream(stream);
+    extent_init_kernel<<<(N + 255) / 256, 256, 0, st>>>(out4, N);
+    OFK_LAUNCHED();
+    const size_t frame = (size_t)H * W;
+    int bx = (int)((frame + 256 * 8 - 1) / (256 * 8));
+    const int cap = (sm_count() * 8 + N - 1) / N;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    extent_kernel<<<dim3(bx, N), 256, 0, st>>>(flow, mask, sign, thr, out4, H, W);
+    OFK_LAUNCHED();
+    return OFK_OK;
+}
+
+extern "C" int ofk_mask_and(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, ofk_stream_t stream) {
+    OFK_CHECK_ARG(a && b && out, "ofk_mask_and: NULL argument");
+    if (n == 0) return OFK_OK;
+    const int vec_ok = (((uintptr_t)a | (uintptr_t)b | (uintptr_t)out) & 3) == 0;
+    mask_and_kernel<<<stream_grid(n / 4 + 1, 256), 256, 0, as_stream(stream)>>>(a, b, out, n, vec_ok);
+    OFK_LAUNCHED();
+    return OFK_OK;
+}
+
+extern "C" int ofk_crop(const void* in, void* out, int elem_bytes, int N, int H, int W, int y0, int x0, int h, int w,
+                        ofk_stream_t stream) {
+    OFK_CHECK_ARG(in && out && elem_bytes > 0, "ofk_crop: bad argument");
+    OFK_CHECK_ARG(N >= 0 && y0 >= 0 && x0 >= 0 && h > 0 && w > 0 && y0 + h <= H && x0 + w <= W && h <= 65535 &&
+                      N <= 65535,
+                  "ofk_crop: window (%d,%d)+(%d,%d) outside (%d,%d)", y0, x0, h, w, H, W);
+    if (N == 0) return OFK_OK;
+    int bx = (int)(((size_t)w * elem_bytes + 255) / 256);
+    if (bx > 8) bx = 8;
+    crop_kernel<<<dim3(bx, h, N), 256, 0, as_stream(stream)>>>((const uint8_t*)in, (uint8_t*)out, elem_bytes, H, W, y0,
+                                                              x0, h, w);
+    OFK_LAUNCHED();
+    return OFK_OK;
+}
+
+extern "C" int ofk_points_inside_area(const double* pts, size_t n, int H, int W, uint8_t* out, ofk_stream_t stream) {
+    OFK_CHECK_ARG(pts && out, "ofk_points_inside_area: NULL argument");
+    if (n == 0) return OFK_OK;
+    inside_kernel<<<stream_grid(n, 256), 256, 0, as_stream(stream)>>>(pts, n, H, W, out);
+    OFK_LAUNCHED();
+    return OFK_OK;
+}

@@ -1,0 +1,86 @@
+// Affine / projective flow-field generator for sm_100a (utils.py:91-111,319-344 of the reference).
+//
+// out[y,x] = sign * float32( proj(M [x,y,1]) - [x,y] ) in float64, reproducing the rounding sequence of the
+// reference's `np.matmul(M, grid[..., None])` (OpenBLAS dgemv: t = m1*y; t = fma(m0, x, t); r = t + m2), then the
+// perspective divide, the subtraction of the float32 grid and the cast to float32. Write-only: 8 B/px.
+#include "ofk_common.cuh"
+
+namespace ofk {
+
+struct Mat3 {
+    double m[9];
+};
+struct MatBatch {
+    Mat3 mats[8];
+};
+
+__device__ __forceinline__ void eval_pixel(const double* __restrict__ m, int x, int y, float sign, float& u, float& v) {
+    const double gx = static_cast<double>(x), gy = static_cast<double>(y);
+    const double tx = __dadd_rn(__fma_rn(m[0], gx, __dmul_rn(m[1], gy)), m[2]);
+    const double ty = __dadd_rn(__fma_rn(m[3], gx, __dmul_rn(m[4], gy)), m[5]);
+    const double tz = __dadd_rn(__fma_rn(m[6], gx, __dmul_rn(m[7], gy)), m[8]);
+    u = sign * __double2float_rn(__dsub_rn(__ddiv_rn(tx, tz), gx));
+    v = sign * __double2float_rn(__dsub_rn(__ddiv_rn(ty, tz), gy));
+}
+
+// 2 pixels per thread -> one 16-byte store; rows are walked with a grid-stride loop over "pixel pairs".
+__global__ void __launch_bounds__(256) from_matrix_kernel(const double* __restrict__ mats_dev, MatBatch host_mats,
+                                                          int use_host, int n0, float sign, float* __restrict__ out,
+                                                          int H, int W, int vec_ok) {
+    const int n = blockIdx.z;
+    double m[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) m[k] = use_host ? host_mats.mats[n].m[k] : mats_dev[(size_t)(n0 + n) * 9 + k];
+    const int y = blockIdx.y;
+    float* row = out + (((size_t)(n0 + n) * H + y) * W) * 2;
+    if (vec_ok) {
+        for (int x = (blockIdx.x * blockDim.x + threadIdx.x) * 2; x < W; x += gridDim.x * blockDim.x * 2) {
+            float u0, v0, u1, v1;
+            eval_pixel(m, x, y, sign, u0, v0);
+            eval_pixel(m, x + 1, y, sign, u1, v1);
+            st_stream_f4(reinterpret_cast<float4*>(row + (size_t)x * 2), make_float4(u0, v0, u1, v1));
+        }
+    } else {
+        for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < W; x += gridDim.x * blockDim.x) {
+            float u, v;
+            eval_pixel(m, x, y, sign, u, v);
+            row[(size_t)x * 2] = u;
+            row[(size_t)x * 2 + 1] = v;
+        }
+    }
+}
+
+}  // namespace ofk
+
+using namespace ofk;
+
+extern "C" int ofk_from_matrix(const double* mats, int mats_on_host, float sign, float* out, int N, int H, int W,
+                               ofk_stream_t stream) {
+    OFK_CHECK_ARG(mats && out, "ofk_from_matrix: NULL argument");
+    OFK_CHECK_ARG(N >= 0 && H > 0 && W > 0, "ofk_from_matrix: bad shape N=%d H=%d W=%d", N, H, W);
+    OFK_CHECK_ARG(sign == 1.0f || sign == -1.0f, "ofk_from_matrix: sign must be +1 or -1");
+    OFK_CHECK_ARG(H <= 65535, "ofk_from_matrix: H=%d exceeds 65535", H);
+    OFK_CHECK_ARG(!mats_on_host || N <= 64, "ofk_from_matrix: host matrices limited to N <= 64 (got %d)", N);
+    if (N == 0) return OFK_OK;
+    cudaStream_t st = as_stream(stream);
+    const int vec_ok = (W % 2 == 0) && aligned16(out);
+    const int per_thread = vec_ok ? 2 : 1;
+    int bx = (W + 256 * per_thread - 1) / (256 * per_thread);
+    if (bx < 1) bx = 1;
+    if (mats_on_host) {
+        for (int n0 = 0; n0 < N; n0 += 8) {
+            MatBatch mb;
+            const int cnt = (N - n0 < 8) ? (N - n0) : 8;
+            for (int i = 0; i < cnt; ++i)
+                for (int k = 0; k < 9; ++k) mb.mats[i].m[k] = mats[(size_t)(n0 + i) * 9 + k];
+            from_matrix_kernel<<<dim3(bx, H, cnt), 256, 0, st>>>(nullptr, mb, 1, n0, sign, out, H, W, vec_ok);
+            OFK_LAUNCHED();
+        }
+    } else {
+        OFK_CHECK_ARG(N <= 65535, "ofk_from_matrix: N=%d exceeds 65535", N);
+        MatBatch mb = {};
+        from_matrix_kernel<<<dim3(bx, H, N), 256, 0, st>>>(mats, mb, 0, 0, sign, out, H, W, vec_ok);
+        OFK_LAUNCHED();
+    }
+    return OFK_OK;
+}

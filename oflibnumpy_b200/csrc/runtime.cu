@@ -1,0 +1,357 @@
+// Runtime plumbing of oflib_b200: error reporting, device/stream/memory wrappers for the ctypes shim, and the
+// host-buffer entry points (ofh_*) that stream frames through a small ring of device buffers so host<->device copies
+// overlap the kernels.
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "ofk_common.cuh"
+
+namespace ofk {
+
+static thread_local char t_error[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_error, sizeof(t_error), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cached[dev] = v;
+    }
+    return cached[dev];
+}
+
+}  // namespace ofk
+
+using namespace ofk;
+
+extern "C" const char* ofk_last_error(void) { return t_error; }
+extern "C" int ofk_version(void) { return OFK_VERSION; }
+extern "C" unsigned long long ofk_rt_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------------------- runtime
+extern "C" int ofk_rt_device_count(int* count) {
+    OFK_CHECK_ARG(count, "ofk_rt_device_count: NULL");
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        set_error("cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return OFK_ECUDA;
+    }
+    return OFK_OK;
+}
+extern "C" int ofk_rt_set_device(int device) {
+    OFK_CUDA(cudaSetDevice(device));
+    return OFK_OK;
+}
+extern "C" int ofk_rt_get_device(int* device) {
+    OFK_CHECK_ARG(device, "ofk_rt_get_device: NULL");
+    OFK_CUDA(cudaGetDevice(device));
+    return OFK_OK;
+}
+extern "C" int ofk_rt_device_info(int device, int* sm, int* cc_major, int* cc_minor, size_t* l2_bytes,
+                                  size_t* total_mem) {
+    cudaDeviceProp p;
+    OFK_CUDA(cudaGetDeviceProperties(&p, device));
+    if (sm) *sm = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (l2_bytes) *l2_bytes = (size_t)p.l2CacheSize;
+    if (total_mem) *total_mem = p.totalGlobalMem;
+    return OFK_OK;
+}
+
+// stream-ordered pool allocation: freed blocks stay cached in the device's default mempool (release threshold
+// raised to "never"), so the per-call allocations of the Python shim cost microseconds, not cudaMalloc round trips.
+static int ensure_pool(int dev) {
+    static std::mutex mu;
+    static bool done[64] = {false};
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev < 0 || dev >= 64 || done[dev]) return OFK_OK;
+    cudaMemPool_t pool;
+    OFK_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    unsigned long long thr = ~0ull;
+    OFK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    done[dev] = true;
+    return OFK_OK;
+}
+extern "C" int ofk_rt_malloc(void** dptr, size_t bytes, ofk_stream_t stream) {
+    OFK_CHECK_ARG(dptr, "ofk_rt_malloc: NULL");
+    int dev = 0;
+    OFK_CUDA(cudaGetDevice(&dev));
+    int rc = ensure_pool(dev);
+    if (rc != OFK_OK) return rc;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMallocAsync(dptr, bytes, as_stream(stream));
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        set_error("device allocation of %zu bytes failed", bytes);
+        return OFK_ENOMEM;
+    }
+    OFK_CUDA(e);
+    return OFK_OK;
+}
+extern "C" int ofk_rt_free(void* dptr, ofk_stream_t stream) {
+    if (dptr == nullptr) return OFK_OK;
+    OFK_CUDA(cudaFreeAsync(dptr, as_stream(stream)));
+    return OFK_OK;
+}
+extern "C" int ofk_rt_host_alloc(void** hptr, size_t bytes) {
+    OFK_CHECK_ARG(hptr, "ofk_rt_host_alloc: NULL");
+    OFK_CUDA(cudaHostAlloc(hptr, bytes ? bytes : 16, cudaHostAllocPortable));
+    return OFK_OK;
+}
+extern "C" int ofk_rt_host_free(void* hptr) {
+    if (hptr) OFK_CUDA(cudaFreeHost(hptr));
+    return OFK_OK;
+}
+extern "C" int ofk_rt_host_register(void* hptr, size_t bytes) {
+    OFK_CUDA(cudaHostRegister(hptr, bytes, cudaHostRegisterPortable));
+    return OFK_OK;
+}
+extern "C" int ofk_rt_host_unregister(void* hptr) {
+    OFK_CUDA(cudaHostUnregister(hptr));
+    return OFK_OK;
+}
+extern "C" int ofk_rt_memcpy_h2d(void* dst, const void* src, size_t bytes, ofk_stream_t s) {
+    if (bytes) OFK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, as_stream(s)));
+    return OFK_OK;
+}
+extern "C" int ofk_rt_memcpy_d2h(void* dst, const void* src, size_t bytes, ofk_stream_t s) {
+    if (bytes) OFK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, as_stream(s)));
+    return OFK_OK;
+}
+extern "C" int ofk_rt_memcpy_d2d(void* dst, const void* src, size_t bytes, ofk_stream_t s) {
+    if (bytes) OFK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, as_stream(s)));
+    return OFK_OK;
+}
+extern "C" int ofk_rt_memset(void* dst, int value, size_t bytes, ofk_stream_t s) {
+    if (bytes) OFK_CUDA(cudaMemsetAsync(dst, value, bytes, as_stream(s)));
+    return OFK_OK;
+}
+extern "C" int ofk_rt_stream_create(ofk_stream_t* s) {
+    OFK_CHECK_ARG(s, "ofk_rt_stream_create: NULL");
+    cudaStream_t st;
+    OFK_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    *s = (ofk_stream_t)st;
+    return OFK_OK;
+}
+extern "C" int ofk_rt_stream_destroy(ofk_stream_t s) {
+    if (s) OFK_CUDA(cudaStreamDestroy(as_stream(s)));
+    return OFK_OK;
+}
+extern "C" int ofk_rt_stream_sync(ofk_stream_t s) {
+    OFK_CUDA(cudaStreamSynchronize(as_stream(s)));
+    return OFK_OK;
+}
+extern "C" int ofk_rt_device_sync(void) {
+    OFK_CUDA(cudaDeviceSynchronize());
+    return OFK_OK;
+}
+extern "C" int ofk_rt_event_create(void** ev) {
+    OFK_CHECK_ARG(ev, "ofk_rt_event_create: NULL");
+    cudaEvent_t e;
+    OFK_CUDA(cudaEventCreate(&e));
+    *ev = (void*)e;
+    return OFK_OK;
+}
+extern "C" int ofk_rt_event_destroy(void* ev) {
+    if (ev) OFK_CUDA(cudaEventDestroy((cudaEvent_t)ev));
+    return OFK_OK;
+}
+extern "C" int ofk_rt_event_record(void* ev, ofk_stream_t s) {
+    OFK_CUDA(cudaEventRecord((cudaEvent_t)ev, as_stream(s)));
+    return OFK_OK;
+}
+extern "C" int ofk_rt_event_sync(void* ev) {
+    OFK_CUDA(cudaEventSynchronize((cudaEvent_t)ev));
+    return OFK_OK;
+}
+extern "C" int ofk_rt_event_elapsed_ms(void* a, void* b, float* ms) {
+    OFK_CHECK_ARG(ms, "ofk_rt_event_elapsed_ms: NULL");
+    OFK_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b));
+    return OFK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ host-buffer API
+namespace {
+
+constexpr int kSlots = 3;
+constexpr size_t kChunkTarget = 48u << 20;  // ~48 MiB of traffic per chunk keeps PCIe busy without hoarding HBM
+
+struct Slot {
+    cudaStream_t st = nullptr;
+    char* dev = nullptr;
+    size_t cap = 0;
+    size_t used = 0;
+    void* take(size_t bytes) {
+        size_t off = (used + 255) & ~size_t(255);
+        used = off + bytes;
+        return dev + off;
+    }
+};
+struct Ring {
+    int device = -1;
+    Slot slot[kSlots];
+    std::mutex mu;
+};
+Ring g_ring;
+
+int ring_prepare(int device, size_t bytes_per_slot) {
+    if (g_ring.device != device) {
+        if (g_ring.device >= 0) {
+            cudaSetDevice(g_ring.device);
+            for (auto& s : g_ring.slot) {
+                if (s.dev) cudaFree(s.dev);
+                if (s.st) cudaStreamDestroy(s.st);
+                s = Slot();
+            }
+        }
+        g_ring.device = device;
+    }
+    OFK_CUDA(cudaSetDevice(device));
+    for (auto& s : g_ring.slot) {
+        if (!s.st) OFK_CUDA(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+        if (s.cap < bytes_per_slot) {
+            if (s.dev) {
+                OFK_CUDA(cudaStreamSynchronize(s.st));
+                OFK_CUDA(cudaFree(s.dev));
+                s.dev = nullptr;
+                s.cap = 0;
+            }
+            cudaError_t e = cudaMalloc((void**)&s.dev, bytes_per_slot);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                set_error("ring allocation of %zu bytes failed: %s", bytes_per_slot, cudaGetErrorString(e));
+                return OFK_ENOMEM;
+            }
+            s.cap = bytes_per_slot;
+        }
+    }
+    return OFK_OK;
+}
+
+size_t esize(int dtype) {
+    switch (dtype) {
+        case OFK_U8: return 1;
+        case OFK_I16:
+        case OFK_U16: return 2;
+        case OFK_F32: return 4;
+        default: return 8;
+    }
+}
+size_t pad256(size_t b) { return (b + 255) & ~size_t(255); }
+
+#define OFH_COPY_IN(dst, src, bytes) OFK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s.st))
+#define OFH_COPY_OUT(dst, src, bytes) OFK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s.st))
+
+}  // namespace
+
+extern "C" int ofh_warp_t(const void* payload, int dtype, int C, int arith, const float* flow, float flow_sign,
+                          const uint8_t* payload_mask, const uint8_t* flow_mask, void* out, uint8_t* out_mask,
+                          int mask_rule, int N, int H, int W, int device) {
+    OFK_CHECK_ARG(flow != nullptr && N >= 0 && H > 0 && W > 0 && C >= 0, "ofh_warp_t: bad arguments");
+    OFK_CHECK_ARG(dtype >= OFK_U8 && dtype <= OFK_F64, "ofh_warp_t: unknown dtype %d", dtype);
+    if (N == 0) return OFK_OK;
+    std::lock_guard<std::mutex> lk(g_ring.mu);
+    const size_t px = (size_t)H * W, es = esize(dtype);
+    const size_t b_flow = px * 8, b_pay = px * C * es, b_m = px;
+    const size_t per_frame = pad256(b_flow) + 2 * pad256(b_pay) + 3 * pad256(b_m);
+    int cf = (int)(kChunkTarget / per_frame);
+    if (cf < 1) cf = 1;
+    if (cf > N) cf = N;
+    int rc = ring_prepare(device, per_frame * cf + 4096);
+    if (rc != OFK_OK) return rc;
+    int chunk = 0;
+    for (int n0 = 0; n0 < N; n0 += cf, ++chunk) {
+        Slot& s = g_ring.slot[chunk % kSlots];
+        const int cn = (N - n0 < cf) ? (N - n0) : cf;
+        // a slot is reused only after everything queued on its stream has drained (keeps device buffers private)
+        OFK_CUDA(cudaStreamSynchronize(s.st));
+        s.used = 0;
+        float* d_flow = (float*)s.take(b_flow * cn);
+        void* d_pay = C ? s.take(b_pay * cn) : nullptr;
+        void* d_out = C ? s.take(b_pay * cn) : nullptr;
+        uint8_t* d_pm = payload_mask ? (uint8_t*)s.take(b_m * cn) : nullptr;
+        uint8_t* d_fm = flow_mask ? (uint8_t*)s.take(b_m * cn) : nullptr;
+        uint8_t* d_om = out_mask ? (uint8_t*)s.take(b_m * cn) : nullptr;
+        OFH_COPY_IN(d_flow, flow + (size_t)n0 * px * 2, b_flow * cn);
+        if (C) OFH_COPY_IN(d_pay, (const char*)payload + (size_t)n0 * b_pay, b_pay * cn);
+        if (d_pm) OFH_COPY_IN(d_pm, payload_mask + (size_t)n0 * px, b_m * cn);
+        if (d_fm) OFH_COPY_IN(d_fm, flow_mask + (size_t)n0 * px, b_m * cn);
+        rc = ofk_warp_t(d_pay, dtype, C, arith, d_flow, flow_sign, d_pm, d_fm, d_out, d_om, mask_rule, cn, H, W, H, W,
+                        0, 0, 1, (ofk_stream_t)s.st);
+        if (rc != OFK_OK) return rc;
+        if (C) OFH_COPY_OUT((char*)out + (size_t)n0 * b_pay, d_out, b_pay * cn);
+        if (d_om) OFH_COPY_OUT(out_mask + (size_t)n0 * px, d_om, b_m * cn);
+    }
+    for (auto& s : g_ring.slot) OFK_CUDA(cudaStreamSynchronize(s.st));
+    return OFK_OK;
+}
+
+extern "C" int ofh_combine3(const float* A, const uint8_t* Am, const float* B, const uint8_t* Bm, int ref, float thr,
+                            float* out, uint8_t* out_mask, int* flags, int N, int H, int W, int device) {
+    OFK_CHECK_ARG(A && B && out && out_mask && N >= 0 && H > 0 && W > 0, "ofh_combine3: bad arguments");
+    if (N == 0) return OFK_OK;
+    std::lock_guard<std::mutex> lk(g_ring.mu);
+    const size_t px = (size_t)H * W;
+    const size_t b_flow = px * 8, b_m = px;
+    const size_t per_frame = 3 * pad256(b_flow) + 3 * pad256(b_m) + 256;
+    int cf = (int)(kChunkTarget / per_frame);
+    if (cf < 1) cf = 1;
+    if (cf > N) cf = N;
+    int rc = ring_prepare(device, per_frame * cf + 4096);
+    if (rc != OFK_OK) return rc;
+    int chunk = 0;
+    for (int n0 = 0; n0 < N; n0 += cf, ++chunk) {
+        Slot& s = g_ring.slot[chunk % kSlots];
+        const int cn = (N - n0 < cf) ? (N - n0) : cf;
+        OFK_CUDA(cudaStreamSynchronize(s.st));
+        s.used = 0;
+        float* dA = (float*)s.take(b_flow * cn);
+        float* dB = (float*)s.take(b_flow * cn);
+        float* dO = (float*)s.take(b_flow * cn);
+        uint8_t* dAm = Am ? (uint8_t*)s.take(b_m * cn) : nullptr;
+        uint8_t* dBm = Bm ? (uint8_t*)s.take(b_m * cn) : nullptr;
+        uint8_t* dOm = (uint8_t*)s.take(b_m * cn);
+        int* dF = (int*)s.take(sizeof(int) * 2 * cn);
+        OFH_COPY_IN(dA, A + (size_t)n0 * px * 2, b_flow * cn);
+        OFH_COPY_IN(dB, B + (size_t)n0 * px * 2, b_flow * cn);
+        if (dAm) OFH_COPY_IN(dAm, Am + (size_t)n0 * px, b_m * cn);
+        if (dBm) OFH_COPY_IN(dBm, Bm + (size_t)n0 * px, b_m * cn);
+        rc = ofk_combine3(dA, dAm, dB, dBm, ref, thr, dO, dOm, dF, cn, H, W, (ofk_stream_t)s.st);
+        if (rc != OFK_OK) return rc;
+        OFH_COPY_OUT(out + (size_t)n0 * px * 2, dO, b_flow * cn);
+        OFH_COPY_OUT(out_mask + (size_t)n0 * px, dOm, b_m * cn);
+        if (flags) OFH_COPY_OUT(flags + (size_t)n0 * 2, dF, sizeof(int) * 2 * cn);
+    }
+    for (auto& s : g_ring.slot) OFK_CUDA(cudaStreamSynchronize(s.st));
+    return OFK_OK;
+}
+
+extern "C" int ofh_release(void) {
+    std::lock_guard<std::mutex> lk(g_ring.mu);
+    if (g_ring.device >= 0) {
+        cudaSetDevice(g_ring.device);
+        for (auto& s : g_ring.slot) {
+            if (s.st) cudaStreamSynchronize(s.st);
+            if (s.dev) cudaFree(s.dev);
+            if (s.st) cudaStreamDestroy(s.st);
+            s = Slot();
+        }
+        g_ring.device = -1;
+    }
+    return OFK_OK;
+}

@@ -1,0 +1,71 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library builds, loads, and exports every symbol that
+include/oflib_b200.h declares; the ctypes table matches the header; calls fail loudly without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, 'include', 'oflib_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(of[kh]_\w+)\s*\(', src)))
+
+
+@pytest.fixture(scope='module')
+def lib_path():
+    from oflibnumpy_b200 import build
+    return build.build()
+
+
+def test_header_declares_the_hot_path():
+    names = header_functions()
+    for must in ('ofk_warp_t', 'ofk_combine3', 'ofk_forward_s', 'ofk_from_matrix', 'ofk_valid_geom_t',
+                 'ofk_nonzero_flags', 'ofk_addsub', 'ofk_pad', 'ofh_warp_t', 'ofh_combine3', 'ofk_last_error'):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    lib = ctypes.CDLL(lib_path)
+    missing = [n for n in header_functions() if not hasattr(lib, n)]
+    assert not missing, "declared in the header but not exported: {}".format(missing)
+
+
+def test_ctypes_table_matches_header(lib_path):
+    from oflibnumpy_b200 import _lib
+    assert _lib.symbols() == header_functions()
+    lib = _lib.load()
+    assert lib.ofk_version() == 100
+
+
+def test_argument_errors_do_not_need_a_gpu(lib_path):
+    from oflibnumpy_b200 import _lib
+    with pytest.raises(_lib.OflibCudaError, match="flow is NULL"):
+        _lib.call('ofk_warp_t', None, 0, 0, 0, None, -1.0, None, None, None, None, 0, 1, 4, 4, 4, 4, 0, 0, 1, None)
+    with pytest.raises(_lib.OflibCudaError, match="ref must be"):
+        _lib.call('ofk_combine3', 16, None, 16, None, ord('x'), 0.0, 16, 16, None, 1, 4, 4, None)
+
+
+def test_no_cpu_fallback_without_gpu(lib_path):
+    import oflibnumpy_b200 as of
+    if of.device.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(of.OflibCudaError):
+        of.Flow(np.zeros((4, 4, 2), np.float32))
+    with pytest.raises(of.OflibCudaError):
+        of.apply_flow(np.ones((4, 4, 2), np.float32), np.zeros((4, 4), np.uint8), 't')
+
+
+def test_product_does_not_import_oracle():
+    """The package must never route through the CPU oracle."""
+    pkg = os.path.join(ROOT, 'oflibnumpy_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', text, flags=re.M), f
+                assert 'flowref' not in text and 'remap_q32' not in text, f

@@ -1,0 +1,378 @@
+"""GPU parity: the CUDA target-referenced path (through the Python shim -> ctypes -> C ABI) against outputs of the
+unmodified reference (tests/golden) and against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): valid masks bit-exact; flow / warped values within 1e-3 on valid pixels. The kernels
+restate cv2.remap's arithmetic operation by operation, so on this path the tests additionally demand bit-exact values.
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import golden_inputs as gi
+from conftest import load_golden
+from oracle import flowref as R
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3  # px / intensity, north_star tolerance
+
+
+@pytest.fixture(scope='module')
+def of():
+    import oflibnumpy_b200 as of
+    of.device.require_gpu()
+    return of
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def same(got, want):
+    assert got.dtype == want.dtype, (got.dtype, want.dtype)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    if np.issubdtype(want.dtype, np.floating):
+        assert np.abs(got.astype(np.float64) - want.astype(np.float64)).max() <= TOL
+    np.testing.assert_array_equal(got, want)
+
+
+def flow_same(g, prefix, f):
+    same(f.mask, g['out_' + prefix + '_mask'])
+    assert f.ref == str(g['out_' + prefix + '_ref'])
+    same(f.vecs, g['out_' + prefix + '_vecs'])
+
+
+def test_apply_flow_and_flow_apply_all_dtypes(of):
+    g = load_golden('warp_t')
+    flow, fmask = g['in_flow'], g['in_flow_mask']
+    f = of.Flow(flow, 't', fmask)
+    f_nomask = of.Flow(flow, 't')
+    for name in [k[3:] for k in g if k.startswith('in_img_')]:
+        img = g['in_' + name]
+        same(of.apply_flow(flow, img, 't'), g['out_applyflow_' + name])
+        same(f.apply(img), g['out_apply_' + name])
+        if 'err_applyva_' + name in g:
+            with pytest.raises(TypeError):
+                f.apply(img, return_valid_area=True)
+            continue
+        w, m = f.apply(img, return_valid_area=True)
+        same(w, g['out_applyva_' + name])
+        same(m, g['out_applyva_' + name + '_valid'])
+        if 'out_applyvatm_' + name in g:
+            w, m = f.apply(img, target_mask=g['in_target_mask'], return_valid_area=True)
+            same(w, g['out_applyvatm_' + name])
+            same(m, g['out_applyvatm_' + name + '_valid'])
+            w, m = f_nomask.apply(img, target_mask=g['in_target_mask'], return_valid_area=True)
+            same(w, g['out_applyvatm_nofm_' + name])
+            same(m, g['out_applyvatm_nofm_' + name + '_valid'])
+
+
+def test_flow_applied_to_flow_and_valid_areas(of):
+    g = load_golden('warp_t')
+    f = of.Flow(g['in_flow'], 't', g['in_flow_mask'])
+    flow_same(g, 'apply_flowobj', f.apply(of.Flow(g['in_flow2'], 't', g['in_flow2_mask'])))
+    flow_same(g, 'apply_flowobj_s', f.apply(of.Flow(g['in_flow2'], 's', g['in_flow2_mask'])))
+    same(f.valid_target(), g['out_valid_target'])
+    same(of.Flow(g['in_flow'], 's', g['in_flow_mask']).valid_source(), g['out_valid_source_of_s'])
+    assert f.get_padding() == list(g['out_get_padding_t'])
+    assert of.Flow(g['in_flow'], 's', g['in_flow_mask']).get_padding() == list(g['out_get_padding_s'])
+
+
+def test_vectorised_and_scalar_paths_agree(of):
+    """W % 4 == 0 takes the 4-pixel vector kernel, anything else the scalar kernel: both against the oracle."""
+    rng = np.random.default_rng(11)
+    for (h, w) in ((37, 64), (37, 66), (64, 128), (5, 4), (1, 1), (3, 257)):
+        flow = (rng.random((h, w, 2)).astype(np.float32) - np.float32(0.5)) * np.float32(12)
+        fmask = rng.random((h, w)) > 0.1
+        tmask = rng.random((h, w)) > 0.1
+        f, fr = of.Flow(flow, 't', fmask), R.make(flow, 't', fmask)
+        for dt, c in ((np.uint8, 3), (np.uint8, 1), (np.uint8, 4), (np.uint8, 2), (np.float32, 3), (np.float32, 2),
+                      (np.float32, 1), (np.float32, 4), (np.float32, 5), (np.int16, 3), (np.uint16, 1),
+                      (np.float64, 3)):
+            img = (rng.random((h, w, c)) * 255).astype(dt)
+            same(f.apply(img), R.apply(fr, img))
+            if dt != np.uint16:
+                w1, m1 = f.apply(img, return_valid_area=True)
+                w2, m2 = R.apply(fr, img, return_valid_area=True)
+                same(w1, w2)
+                same(m1, m2)
+            w1, m1 = f.apply(img, target_mask=tmask, return_valid_area=True)
+            w2, m2 = R.apply(fr, img, target_mask=tmask, return_valid_area=True)
+            same(w1, w2)
+            same(m1, m2)
+
+
+def test_padding_and_cut(of):
+    g = load_golden('warp_t_padded')
+    pad = [int(x) for x in g['in_padding']]
+    f = of.Flow(g['in_flow'], 't', g['in_flow_mask'])
+    for cut in (True, False):
+        tag = 'cut' if cut else 'nocut'
+        same(f.apply(g['in_img_u8c3'], padding=pad, cut=cut), g['out_apply_u8_' + tag])
+        w, m = f.apply(g['in_img_u8c3'], return_valid_area=True, padding=pad, cut=cut)
+        same(w, g['out_applyva_u8_' + tag])
+        same(m, g['out_applyva_u8_' + tag + '_valid'])
+        w, m = f.apply(g['in_img_f32c3'], target_mask=g['in_target_mask'], return_valid_area=True, padding=pad,
+                       cut=cut)
+        same(w, g['out_applyvatm_f32_' + tag])
+        same(m, g['out_applyvatm_f32_' + tag + '_valid'])
+        flow_same(g, 'apply_flowobj_' + tag, f.apply(of.Flow(g['in_big_flow'], 't', g['in_big_flow_mask']),
+                                                     padding=pad, cut=cut))
+    same(f.pad(pad).vecs, g['out_pad_constant_vecs'])
+    same(f.pad(pad).mask, g['out_pad_constant_mask'])
+    same(f.pad(pad, 'edge').vecs, g['out_pad_edge_vecs'])
+    same(f.pad(pad, 'symmetric').vecs, g['out_pad_symmetric_vecs'])
+
+
+def test_zero_and_tiny_flows_are_identity(of):
+    """The reference returns the target untouched for |v| < 1e-3 (utils.py:215-216); identity taps reproduce it."""
+    rng = np.random.default_rng(12)
+    h, w = 33, 48
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    imgf = rng.random((h, w, 3)).astype(np.float32)
+    tiny = (rng.random((h, w, 2)).astype(np.float32) - np.float32(0.5)) * np.float32(1.9e-3)
+    for flow in (np.zeros((h, w, 2), np.float32), tiny):
+        same(of.apply_flow(flow, img, 't'), img)
+        same(of.apply_flow(flow, imgf, 't'), imgf)
+        wv, m = of.Flow(flow).apply(img, return_valid_area=True)
+        same(wv, img)
+        assert m.all()
+        assert of.Flow(flow).valid_target().all()
+
+
+def test_combine_mode3_golden(of):
+    g = load_golden('combine3')
+    for r in ('t', 's'):
+        for pair in ('aff', 'smooth'):
+            a = of.Flow(g['in_' + pair + '_1'], r, g['in_mask_1'])
+            b = of.Flow(g['in_' + pair + '_2'], r, g['in_mask_2'])
+            flow_same(g, 'c3_{}_{}'.format(r, pair), a.combine_with(b, 3))
+            same(of.combine_flows(g['in_' + pair + '_1'], g['in_' + pair + '_2'], 3, r),
+                 g['out_cf3_{}_{}'.format(r, pair)])
+        a = of.Flow(g['in_zero_where_valid'], r, g['in_zero_mask'])
+        b = of.Flow(g['in_aff_2'], r, g['in_mask_2'])
+        res = a.combine_with(b, 3)
+        assert res is b                                   # the reference returns the operand itself
+        flow_same(g, 'c3_{}_Azero'.format(r), res)
+        res = b.combine_with(a, 3)
+        assert res is b
+        flow_same(g, 'c3_{}_Bzero'.format(r), res)
+        a = of.Flow(g['in_tiny'], r, g['in_mask_1'])
+        flow_same(g, 'c3_{}_tiny_thr'.format(r), a.combine_with(b, 3, thresholded=True))
+        flow_same(g, 'c3_{}_tiny_nothr'.format(r), a.combine_with(b, 3, thresholded=False))
+
+
+def test_combine_mode3_shapes_vs_oracle(of):
+    rng = np.random.default_rng(13)
+    for (h, w) in ((40, 64), (41, 67), (2, 4), (1, 1), (96, 160)):
+        a = (rng.random((h, w, 2)).astype(np.float32) - np.float32(0.5)) * np.float32(10)
+        b = (rng.random((h, w, 2)).astype(np.float32) - np.float32(0.5)) * np.float32(10)
+        am, bm = rng.random((h, w)) > 0.1, rng.random((h, w)) > 0.1
+        for r in ('t', 's'):
+            got = of.Flow(a, r, am).combine_with(of.Flow(b, r, bm), 3)
+            want = R.combine(R.make(a, r, am), R.make(b, r, bm), 3)
+            same(got.mask, want.mask)
+            same(got.vecs, want.vecs)
+
+
+def test_batched_equals_per_frame(of):
+    """FlowBatch (one launch for N frames, device-side early exits) == N single-frame calls == oracle."""
+    rng = np.random.default_rng(14)
+    n, h, w = 5, 36, 64
+    a = (rng.random((n, h, w, 2)).astype(np.float32) - np.float32(0.5)) * np.float32(8)
+    b = (rng.random((n, h, w, 2)).astype(np.float32) - np.float32(0.5)) * np.float32(8)
+    am, bm = rng.random((n, h, w)) > 0.05, rng.random((n, h, w)) > 0.05
+    a[1] = 0                         # frame 1: A zero            -> result is B
+    b[2][bm[2]] = 0                  # frame 2: B zero where valid -> result is A
+    a[3][am[3]] = 0                  # frame 3: both zero         -> result is B (A tested first)
+    b[3] = 0
+    imgs = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+    for r in ('t', 's'):
+        fa, fb = of.FlowBatch(a, r, am), of.FlowBatch(b, r, bm)
+        res, flags = fa.combine_with(fb, 3, return_flags=True)
+        v, m = res.numpy()
+        fl = flags.numpy()
+        assert fl[1, 0] == 0 and fl[2, 1] == 0 and fl[0].all() and fl[4].all()
+        for i in range(n):
+            want = R.combine(R.make(a[i], r, am[i]), R.make(b[i], r, bm[i]), 3)
+            same(m[i], want.mask)
+            same(v[i], want.vecs)
+            single = of.Flow(a[i], r, am[i]).combine_with(of.Flow(b[i], r, bm[i]), 3)
+            same(single.vecs, want.vecs)
+            same(res[i].vecs, want.vecs)
+    fa = of.FlowBatch(a, 't', am)
+    out, valid = fa.apply(imgs, return_valid_area=True)
+    out, valid = out.numpy(), valid.numpy().view(np.bool_)
+    for i in range(n):
+        w2, m2 = R.apply(R.make(a[i], 't', am[i]), imgs[i], return_valid_area=True)
+        same(out[i], w2)
+        same(valid[i], m2)
+    # host-buffer entry points (ofh_*): same results from numpy buffers
+    out_h, valid_h = of.batch.apply_flow_host(a, imgs, flow_masks=am, return_valid_area=True)
+    same(out_h, out)
+    same(valid_h, valid)
+    v_h, m_h = of.batch.combine_flows_host(a, b, 3, 't', am, bm)
+    v_d, m_d = of.FlowBatch(a, 't', am).combine_with(of.FlowBatch(b, 't', bm), 3).numpy()
+    same(v_h, v_d)
+    same(m_h, m_d)
+
+
+def test_generators_bit_exact(of):
+    g = load_golden('generators')
+    for i, (kind, arg, shape, r) in enumerate(gi.generator_specs()):
+        if kind == 'transforms':
+            got = of.from_transforms(arg, shape, r)
+            same(of.Flow.from_transforms(arg, shape, r).vecs, g['out_gen_%d' % i])
+        else:
+            got = of.from_matrix(np.array(arg, dtype=np.float64), shape, r)
+        same(got, g['out_gen_%d' % i])
+    fb = of.FlowBatch.from_transforms([gi.cfg4_transforms(i) for i in range(3)], (54, 96), 't')
+    v, _ = fb.numpy()
+    for i in range(3):
+        same(v[i], R.from_transforms(gi.cfg4_transforms(i), (54, 96), 't'))
+
+
+def test_reference_7x7_golden_masks_t_side(of):
+    """tests/test_flow_class.py:852-980 of the reference, the cases that sample in 't' direction."""
+    g = load_golden('small_masks')
+    ft = of.Flow(g['in_vecs_t'], 't')
+    fs = of.Flow(g['in_vecs_s'], 's')
+    ftm = of.Flow(g['in_vecs_t'], 't', g['in_mask_t'])
+    fsm = of.Flow(g['in_vecs_s'], 's', g['in_mask_s'])
+    same(ft.valid_target(), g['out_vt_t'])
+    same(fs.valid_source(), g['out_vs_s'])
+    same(ftm.valid_target(), g['out_vt_t_masked'])
+    same(fsm.valid_source(), g['out_vs_s_masked'])
+    same(of.Flow.from_transforms([['rotation', 0, 0, 45]], (7, 7), 't').vecs, g['in_vecs_t'])
+
+
+def test_arithmetic_and_reductions(of):
+    rng = np.random.default_rng(15)
+    h, w = 30, 52
+    a = rng.standard_normal((h, w, 2)).astype(np.float32) * 3
+    b = rng.standard_normal((h, w, 2)).astype(np.float32) * 3
+    am, bm = rng.random((h, w)) > 0.2, rng.random((h, w)) > 0.2
+    fa, fb = of.Flow(a, 't', am), of.Flow(b, 's', bm)
+    s = fa + fb
+    same(s.vecs, a + b)
+    same(s.mask, am & bm)
+    assert s.ref == 't'
+    d = fa - fb
+    same(d.vecs, a - b)
+    same((fa + b).vecs, a + b)
+    same((fa - b.astype(np.float64)).vecs, (a - b.astype(np.float64)).astype(np.float32))
+    same((-fa).vecs, -a)
+    same((fa * 2.5).vecs, a * np.float32(2.5))
+    same((fa / 3).vecs, a / np.float32(3))
+    same((fa * [2, -0.5]).vecs, (a * np.array([2, -0.5])).astype(np.float32))
+    same((fa * rng.random((h, w))).mask, am)
+    m2 = rng.random((h, w, 2))
+    same((fa * m2).vecs, (a * m2).astype(np.float32))
+    np.testing.assert_allclose((fa ** 2).vecs, a ** 2, rtol=1e-6)
+    with pytest.raises(ValueError):
+        fa / 0
+    # zero tests (reference: tests/test_flow_class.py:1006-1018, tests/test_utils.py:520-540)
+    mask = np.ones((10, 10), bool)
+    mask[0, 0] = False
+    v = np.zeros((10, 10, 2))
+    v[0, 0] = 10
+    fz = of.Flow(v, mask=mask)
+    assert fz.is_zero() is True and fz.is_zero(masked=True) is True and fz.is_zero(masked=False) is False
+    v = np.zeros((10, 10, 2), 'float32')
+    assert of.is_zero_flow(v, thresholded=True) and of.is_zero_flow(v, thresholded=False)
+    v[:3, :, 0] = 1e-4
+    assert of.is_zero_flow(v, thresholded=True) and not of.is_zero_flow(v, thresholded=False)
+    v[:3, :, 0] = 1e-2
+    assert not of.is_zero_flow(v)
+    # points_inside_area (tests/test_utils.py:305-319)
+    pts = np.array([[-1, -1], [-1, 0], [0, -1], [0, 0], [9, 20], [9, 19], [10, 19], [4.3, 7.6], [9.4, 19.4],
+                    [9.6, 19.4]])
+    assert of.points_inside_area(pts, (10, 20)).tolist() == R.points_inside_area(pts, (10, 20)).tolist()
+    # cross-reference inversion and slicing
+    inv = fa.invert('s')
+    same(inv.vecs, -a)
+    assert inv.ref == 's'
+    cut = fa[3:20, 5:40]
+    same(cut.vecs, a[3:20, 5:40])
+    same(cut.mask, am[3:20, 5:40])
+    same(fa[::2].vecs, a[::2])
+
+
+def test_host_views_are_live(of):
+    """`flow.mask[...] = False` edits the flow in the reference (its arrays are its storage); same here."""
+    f = of.Flow.from_transforms([['rotation', 0, 0, 30]], (32, 32), 't')
+    f.mask[:, 20:] = False
+    assert not f.valid_target()[:, 20:].any()
+    f.vecs[...] = 0
+    assert f.is_zero(thresholded=False)
+
+
+def test_constructor_errors(of):
+    with pytest.raises(TypeError):
+        of.Flow('test')
+    with pytest.raises(ValueError):
+        of.Flow(np.zeros((10, 10)))
+    with pytest.raises(ValueError):
+        of.Flow(np.zeros((10, 10, 3)))
+    bad = np.zeros((10, 10, 2), np.float32)
+    bad[2, 3, 1] = np.nan
+    with pytest.raises(ValueError):
+        of.Flow(bad)
+    with pytest.raises(ValueError):
+        of.Flow(bad.astype(np.float64))
+    with pytest.raises(ValueError):
+        of.Flow(np.zeros((10, 10, 2)), mask=np.ones((10, 11)))
+    with pytest.raises(ValueError):
+        of.Flow(np.zeros((10, 10, 2)), mask=np.full((10, 10), 2))
+    f = of.Flow(np.zeros((10, 10, 2)), 's', np.ones((10, 10)))
+    assert f.ref == 's' and f.mask.dtype == bool and f.vecs.dtype == np.float32 and f.shape == (10, 10)
+    f2 = of.Flow(np.ones((10, 10, 2)))
+    with pytest.raises(ValueError):
+        f.combine_with(f2, 3)                # different refs
+    with pytest.raises(ValueError):
+        f.combine_with(of.Flow(np.ones((10, 10, 2)), 's'), 4)
+    with pytest.raises(TypeError):
+        f.combine_with(np.ones((10, 10, 2)), 3)
+    with pytest.raises(TypeError):
+        f2.apply(np.zeros((10, 10)), return_valid_area='test')
+    with pytest.raises(ValueError):
+        f2.apply(np.zeros((11, 10)))
+    with pytest.raises(TypeError):
+        f2.apply(np.zeros((10, 10), np.int32))
+
+
+@pytest.mark.slow
+def test_full_size_digests(of):
+    """BASELINE.json configurations at full size against SHA-256 digests of the reference's own outputs."""
+    dg = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'digests.json')))
+    flow, img = gi.cfg1_full()
+    assert sha(of.Flow.from_transforms([['rotation', 621, 187.5, 10]], (375, 1242), 't').vecs) == dg['cfg1_flow_sha']
+    assert sha(of.apply_flow(flow, img, 't')) == dg['cfg1_apply_flow_u8c3']
+    w, m = of.Flow(flow, 't').apply(img, return_valid_area=True)
+    assert sha(w) == dg['cfg1_apply_va_u8c3'] and sha(m) == dg['cfg1_apply_va_valid']
+    a, am, b, bm = gi.cfg2_full()
+    for r in ('t', 's'):
+        res = of.Flow(a, r, am).combine_with(of.Flow(b, r, bm), 3)
+        assert sha(res.mask) == dg['cfg2_c3_%s_mask' % r]
+        assert sha(res.vecs) == dg['cfg2_c3_%s_vecs' % r]
+    for idx in (0, 5):
+        fa, fam, fb, fbm, img = gi.cfg4_frame(idx)
+        w, m = of.Flow(fa, 't', fam).apply(img, return_valid_area=True)
+        assert sha(w) == dg['cfg4_f%d_apply_va_u8c3' % idx] and sha(m) == dg['cfg4_f%d_apply_va_valid' % idx]
+        res = of.Flow(fa, 't', fam).combine_with(of.Flow(fb, 't', fbm), 3)
+        assert sha(res.vecs) == dg['cfg4_f%d_c3_t_vecs' % idx] and sha(res.mask) == dg['cfg4_f%d_c3_t_mask' % idx]
+    for r in ('t', 's'):
+        assert sha(of.from_transforms(gi.CFG5_TRANSFORMS, gi.CFG5_SHAPE, r)) == dg['cfg5_from_transforms_' + r]
+    # cfg 5 chain at 4K, entirely device-resident
+    f = of.Flow.from_transforms(gi.CFG5_TRANSFORMS, gi.CFG5_SHAPE, 't')
+    g_ = f.invert('s')
+    g_ = of.Flow(g_.vecs_device, 't', g_.mask_device)
+    acc = f
+    for i in range(4):
+        acc = acc.combine_with(g_ if i % 2 == 0 else f, 3)
+    w, m = acc.apply(gi.cfg5_image(), return_valid_area=True)
+    assert sha(acc.vecs) == dg['cfg5_chain_vecs'] and sha(acc.mask) == dg['cfg5_chain_mask']
+    assert sha(w) == dg['cfg5_chain_img'] and sha(m) == dg['cfg5_chain_valid']
