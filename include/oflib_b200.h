@@ -175,14 +175,16 @@ int ofk_points_inside_area(const double* pts, size_t n, int H, int W, uint8_t* o
 
 /* Source-referenced (forward) resampling: replaces `griddata(grid + flow, payload, grid, 'linear')` + nan_to_num in
  * apply_flow (utils.py:237-258) with a rasterisation of the displaced pixel grid (two triangles per cell, Delaunay
- * diagonal). payload is float32 [N,H,W,C] (C <= 8); the mask channel is resampled with the payload and thresholded
- * `== 1` within OFK_FWD_MASK_EPS. point_mask (consider_mask, or NULL) removes invalid source points: cells touching
- * a removed point are not rasterised (documented deviation from Qhull's gap bridging).
- * ws: workspace of ofk_forward_s_workspace(N,H,W) bytes (device). */
+ * diagonal, float64 geometry). payload is float32 [N,H,W,C]; payload_mask (or NULL = all valid) is resampled with it
+ * and turned into out_mask by mask_rule: OFK_RULE_STRICT (float payloads: interpolated mask == 1 after the float32
+ * cast) or OFK_RULE_GT_HALF (integer payloads: numpy.round(interpolated mask) == 1). point_mask (consider_mask, or
+ * NULL) removes invalid source points: cells touching a removed point are not rasterised (documented deviation from
+ * Qhull's gap bridging). Sample positions are p + flow_sign * flow[p].
+ * ws: device workspace of ofk_forward_s_workspace(N,H,W) bytes. payload/out may be NULL with C = 0 (mask only). */
 size_t ofk_forward_s_workspace(int N, int H, int W);
 int ofk_forward_s(const float* payload, int C, const float* flow, float flow_sign, const uint8_t* payload_mask,
-                  const uint8_t* point_mask, float* out, uint8_t* out_mask, int N, int H, int W, void* ws,
-                  size_t ws_bytes, ofk_stream_t stream);
+                  const uint8_t* point_mask, float* out, uint8_t* out_mask, int mask_rule, int N, int H, int W,
+                  void* ws, size_t ws_bytes, ofk_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------ host-buffer API */
 

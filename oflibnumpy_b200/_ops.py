@@ -174,7 +174,7 @@ def points_inside_area(pts, shape):
     return out.numpy().astype(bool)
 
 
-def forward_s(flow, sign, payload, payload_mask=None, point_mask=None, want_mask=True):
+def forward_s(flow, sign, payload, payload_mask=None, point_mask=None, want_mask=True, rule=_lib.RULE_STRICT):
     """Forward (source-referenced) resampling of a float32 payload [N,H,W,C] (ofk_forward_s)."""
     n, h, w = flow.shape[:3]
     c = payload.shape[3] if payload is not None else 0
@@ -183,5 +183,5 @@ def forward_s(flow, sign, payload, payload_mask=None, point_mask=None, want_mask
     ws_bytes = _lib.call('ofk_forward_s_workspace', n, h, w)
     ws = DeviceArray.empty((max(ws_bytes, 16),), np.uint8)
     _lib.call('ofk_forward_s', _p(payload), c, flow.ptr, float(sign), _p(payload_mask), _p(point_mask), _p(out),
-              _p(omask), n, h, w, ws.ptr, ws_bytes, dev.current_stream())
+              _p(omask), rule, n, h, w, ws.ptr, ws_bytes, dev.current_stream())
     return out, omask

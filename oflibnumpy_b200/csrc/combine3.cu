@@ -14,11 +14,12 @@ namespace ofk {
 // "P" is the operand read at p (pointwise), "G" the operand gathered at p + sign*P[p].
 struct SampleResult {
     float u, v;
-    bool strict;
+    int strict;
 };
 
-__device__ __forceinline__ SampleResult sample_flow(const float2* __restrict__ G, const uint8_t* __restrict__ Gm,
-                                                    int H, int W, float X, float Y) {
+// exact but slow: any coordinates, taps may leave the frame (out of line, by-value in / out: no stack traffic)
+__device__ __noinline__ SampleResult sample_flow_border(const float2* __restrict__ G, const uint8_t* __restrict__ Gm,
+                                                        int H, int W, float X, float Y) {
     const QCoord qx = quantise(X), qy = quantise(Y);
     const int ix = qx.i, iy = qy.i;
     const QWeights w = qweights(qx.f, qy.f);
@@ -30,20 +31,14 @@ __device__ __forceinline__ SampleResult sample_flow(const float2* __restrict__ G
     const float2 t01 = (x1 && y0) ? __ldg(G + o + 1) : z;
     const float2 t10 = (x0 && y1) ? __ldg(G + o + W) : z;
     const float2 t11 = (x1 && y1) ? __ldg(G + o + W + 1) : z;
-    int S;
-    if (Gm == nullptr) {
-        S = ((x0 && y0) ? w.w00 : 0) + ((x1 && y0) ? w.w01 : 0) + ((x0 && y1) ? w.w10 : 0) + ((x1 && y1) ? w.w11 : 0);
-    } else {
-        S = 0;
-        if (x0 && y0 && __ldg(Gm + o)) S += w.w00;
-        if (x1 && y0 && __ldg(Gm + o + 1)) S += w.w01;
-        if (x0 && y1 && __ldg(Gm + o + W)) S += w.w10;
-        if (x1 && y1 && __ldg(Gm + o + W + 1)) S += w.w11;
-    }
+    int S = 0;
+    if (x0 && y0 && (!Gm || __ldg(Gm + o))) S += w.w00;
+    if (x1 && y0 && (!Gm || __ldg(Gm + o + 1))) S += w.w01;
+    if (x0 && y1 && (!Gm || __ldg(Gm + o + W))) S += w.w10;
+    if (x1 && y1 && (!Gm || __ldg(Gm + o + W + 1))) S += w.w11;
     const float s = 1.0f / 1024.0f;
     const float f00 = float(w.w00) * s, f01 = float(w.w01) * s, f10 = float(w.w10) * s, f11 = float(w.w11) * s;
     SampleResult r;
-    // cv2.remap float32 accumulation order, no FMA contraction
     r.u = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t00.x, f00), __fmul_rn(t01.x, f01)), __fmul_rn(t10.x, f10)),
                     __fmul_rn(t11.x, f11));
     r.v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t00.y, f00), __fmul_rn(t01.y, f01)), __fmul_rn(t10.y, f10)),
@@ -52,78 +47,129 @@ __device__ __forceinline__ SampleResult sample_flow(const float2* __restrict__ G
     return r;
 }
 
+// cv2.remap float32 sample of the flow field G (and strict validity of its mask) at (X, Y). Interior pixels take the
+// branch-free path: 4 unconditional 64-bit loads, weights from the 5-bit fractions, sums left to right without FMA
+// contraction (bit-exact with OpenCV).
+template <bool MASKS>
+__device__ __forceinline__ SampleResult sample_flow(const float2* __restrict__ G, const uint8_t* __restrict__ Gm,
+                                                    int H, int W, float X, float Y) {
+    const QCoord qx = quantise_fast(X), qy = quantise_fast(Y);
+    const bool interior = (unsigned)qx.i < (unsigned)(W - 1) && (unsigned)qy.i < (unsigned)(H - 1) &&
+                          fabsf(X) < OFK_FAST_COORD_LIMIT && fabsf(Y) < OFK_FAST_COORD_LIMIT;
+    if (!interior) return sample_flow_border(G, MASKS ? Gm : nullptr, H, W, X, Y);
+    const unsigned o = (unsigned)(qy.i * W + qx.i);
+    const float2* g0 = G + o;
+    const float2* g1 = g0 + W;
+    const float2 t00 = __ldg(g0), t01 = __ldg(g0 + 1), t10 = __ldg(g1), t11 = __ldg(g1 + 1);
+    const int a = qx.f, b = qy.f;
+    int strict = 1;
+    if (MASKS) {
+        // a tap only matters when its weight is non-zero: (32-a)(32-b), a(32-b), (32-a)b, ab
+        const uint8_t* m0 = Gm + o;
+        const uint8_t* m1 = m0 + W;
+        const unsigned i00 = __ldg(m0) ^ 1u, i01 = __ldg(m0 + 1) ^ 1u, i10 = __ldg(m1) ^ 1u, i11 = __ldg(m1 + 1) ^ 1u;
+        const unsigned ha = a != 0, hb = b != 0;
+        strict = ((i00 | (i01 & ha) | (i10 & hb) | (i11 & ha & hb)) & 1u) ^ 1u;
+    }
+    const float fa = (float)a * (1.0f / 32.0f), fb = (float)b * (1.0f / 32.0f);
+    const float na = 1.0f - fa, nb = 1.0f - fb;                      // exact: multiples of 1/32
+    const float f00 = __fmul_rn(na, nb), f01 = __fmul_rn(fa, nb), f10 = __fmul_rn(na, fb), f11 = __fmul_rn(fa, fb);
+    SampleResult r;
+    r.u = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t00.x, f00), __fmul_rn(t01.x, f01)), __fmul_rn(t10.x, f10)),
+                    __fmul_rn(t11.x, f11));
+    r.v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t00.y, f00), __fmul_rn(t01.y, f01)), __fmul_rn(t10.y, f10)),
+                    __fmul_rn(t11.y, f11));
+    r.strict = strict;
+    return r;
+}
+
 __device__ __forceinline__ bool nonzero(float c, float thr) { return thr > 0.f ? !(c < thr && c > -thr) : (c != 0.f); }
 
-// flags[n*2 + 0] = A has a non-zero vector on a valid pixel, flags[n*2 + 1] = same for B (block-aggregated stores)
-__device__ __forceinline__ void publish_flags(bool nzA, bool nzB, int* __restrict__ flags, int n) {
-    const int a = __syncthreads_or(nzA);
-    const int b = __syncthreads_or(nzB);
-    if (threadIdx.x == 0) {
-        if (a) flags[n * 2 + 0] = 1;  // benign race: every writer stores the same value
-        if (b) flags[n * 2 + 1] = 1;
+// flags[n*2 + 0] = A has a non-zero vector on a valid pixel, flags[n*2 + 1] = same for B. Warps record what they saw
+// in shared memory; the last warp of the CTA to finish publishes (no CTA-wide barrier at the tail, so finished warps
+// release their slots immediately).
+struct FlagScratch {
+    int nzA, nzB, done;
+};
+__device__ __forceinline__ void publish_flags(bool nzA, bool nzB, int* __restrict__ flags, int n, FlagScratch* sc) {
+    const bool a = __any_sync(0xffffffffu, nzA), b = __any_sync(0xffffffffu, nzB);
+    if ((threadIdx.x & 31) == 0) {
+        if (a) sc->nzA = 1;   // benign race: every writer stores the same value
+        if (b) sc->nzB = 1;
+        __threadfence_block();
+        if (atomicAdd(&sc->done, 1) == (int)(blockDim.x >> 5) - 1) {
+            __threadfence_block();
+            if (*(volatile int*)&sc->nzA) flags[n * 2 + 0] = 1;
+            if (*(volatile int*)&sc->nzB) flags[n * 2 + 1] = 1;
+        }
     }
 }
 
-// 4 pixels per thread along x; 32x32 pixel tiles. REF_T: pointwise operand is B, gathered is A (sign -1);
-// otherwise pointwise is A, gathered is B (sign +1).
-template <bool REF_T>
-__global__ void __launch_bounds__(256) combine3_vec4(const float* __restrict__ A, const uint8_t* __restrict__ Am,
+// A warp owns 32 consecutive pixels of a row (lane = x) and walks 4 rows; a CTA owns a 32x32 tile. All accesses of a
+// warp instruction are contiguous along x: the pointwise operand, the zero-test read of the gathered operand and the
+// output are fully coalesced 256-byte requests, and each gather instruction touches the 2-3 cache lines of a rotated
+// row segment. Loads use clamped indices (no branches), only the stores are predicated.
+// REF_T: pointwise operand is B, gathered is A (sign -1); otherwise pointwise A, gathered B (sign +1).
+template <bool REF_T, bool MASKS>
+__global__ void __launch_bounds__(256) combine3_rows(const float* __restrict__ A, const uint8_t* __restrict__ Am,
                                                      const float* __restrict__ B, const uint8_t* __restrict__ Bm,
                                                      float thr, float* __restrict__ out, uint8_t* __restrict__ omask,
                                                      int* __restrict__ flags, int H, int W) {
-    constexpr int TXT = 8, ROWS = 32;
-    const int tx = threadIdx.x % TXT, ty = threadIdx.x / TXT;
-    const int x0 = (blockIdx.x * TXT + tx) * 4;
-    const int y = blockIdx.y * ROWS + ty;
-    const int n = blockIdx.z;
-    const bool active = (x0 < W && y < H);
-    const size_t frame = (size_t)H * W;
-    bool nzP = false, nzG = false;
-    if (active) {
-        const size_t pix0 = (size_t)n * frame + (size_t)y * W + x0;
-        const float* P = REF_T ? B : A;
-        const uint8_t* Pm = REF_T ? Bm : Am;
-        const float* G = REF_T ? A : B;
-        const uint8_t* Gm = REF_T ? Am : Bm;
-        const float sign = REF_T ? -1.0f : 1.0f;
-
-        const float4* p4 = reinterpret_cast<const float4*>(P + pix0 * 2);
-        const float4 pa = ld_stream_f4(p4), pb = ld_stream_f4(p4 + 1);
-        const float pu[4] = {pa.x, pa.z, pb.x, pb.z};
-        const float pv[4] = {pa.y, pa.w, pb.y, pb.w};
-        const uint32_t pm = Pm ? ld_stream_u32(reinterpret_cast<const uint32_t*>(Pm + pix0)) : 0x01010101u;
-
-        // zero test of the gathered operand needs its values AT p (not at the taps): these lines are the ones the
-        // neighbouring gathers pull into L1/L2 anyway, so this read costs no extra HBM traffic.
-        const float4* g4 = reinterpret_cast<const float4*>(G + pix0 * 2);
-        const float4 ga = __ldg(g4), gb = __ldg(g4 + 1);
-        const uint32_t gm = Gm ? __ldg(reinterpret_cast<const uint32_t*>(Gm + pix0)) : 0x01010101u;
-        const float gu[4] = {ga.x, ga.z, gb.x, gb.z};
-        const float gv[4] = {ga.y, ga.w, gb.y, gb.w};
-
-        const float2* Gf = reinterpret_cast<const float2*>(G) + (size_t)n * frame;
-        const uint8_t* Gmf = Gm ? Gm + (size_t)n * frame : nullptr;
-        const float Y0 = static_cast<float>(y);
-        float ou[4], ov[4];
-        uint32_t om = 0;
+    __shared__ FlagScratch sc;
+    if (threadIdx.x == 0) sc.nzA = sc.nzB = sc.done = 0;
+    __syncthreads();   // every warp is here at the start of the CTA anyway
+    const unsigned lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const unsigned x = blockIdx.x * 32 + lane, xc = min(x, (unsigned)W - 1);
+    const unsigned y0 = blockIdx.y * 32 + wrp * 4;
+    const size_t fbase = (size_t)blockIdx.z * ((size_t)H * W);
+    const float2* P = reinterpret_cast<const float2*>(REF_T ? B : A) + fbase;
+    const float2* G = reinterpret_cast<const float2*>(REF_T ? A : B) + fbase;
+    const uint8_t* Pm = MASKS ? (REF_T ? Bm : Am) + fbase : nullptr;
+    const uint8_t* Gm = MASKS ? (REF_T ? Am : Bm) + fbase : nullptr;
+    float2* O = reinterpret_cast<float2*>(out) + fbase;
+    uint8_t* Om = omask + fbase;
+    const float sign = REF_T ? -1.0f : 1.0f;
+    const float Xg = static_cast<float>(x);
+    // zero test as one compare per component: |c| >= t with t = thr, or the smallest denormal for the exact test
+    const float tz = thr > 0.f ? thr : 1.401298464e-45f;
+    float2 p[4], g[4];
+    unsigned pmv[4], gmv[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const bool pvalid = (pm >> (8 * j)) & 1u, gvalid = (gm >> (8 * j)) & 1u;
-            nzP |= pvalid && (nonzero(pu[j], thr) || nonzero(pv[j], thr));
-            nzG |= gvalid && (nonzero(gu[j], thr) || nonzero(gv[j], thr));
-            const float X = __fadd_rn(sign * pu[j], static_cast<float>(x0 + j));
-            const float Y = __fadd_rn(sign * pv[j], Y0);
-            const SampleResult r = sample_flow(Gf, Gmf, H, W, X, Y);
-            ou[j] = __fadd_rn(pu[j], r.u);
-            ov[j] = __fadd_rn(pv[j], r.v);
-            om |= ((pvalid && r.strict) ? 1u : 0u) << (8 * j);
-        }
-        float4* o4 = reinterpret_cast<float4*>(out + pix0 * 2);
-        st_stream_f4(o4, make_float4(ou[0], ov[0], ou[1], ov[1]));
-        st_stream_f4(o4 + 1, make_float4(ou[2], ov[2], ou[3], ov[3]));
-        st_stream_u32(reinterpret_cast<uint32_t*>(omask + pix0), om);
+    for (int j = 0; j < 4; ++j) {
+        const unsigned idx = min(y0 + j, (unsigned)H - 1) * (unsigned)W + xc;
+        p[j] = ld_stream_f2(P + idx);
+        g[j] = __ldg(G + idx);            // zero test of the gathered operand AT p; these lines are gathered anyway
+        pmv[j] = MASKS ? Pm[idx] : 1u;
+        gmv[j] = MASKS ? __ldg(Gm + idx) : 1u;
     }
-    if (flags != nullptr) publish_flags(REF_T ? nzG : nzP, REF_T ? nzP : nzG, flags, n);
+    unsigned nzP = 0, nzG = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const unsigned y = y0 + j;
+        nzP |= pmv[j] & (unsigned)(fabsf(p[j].x) >= tz || fabsf(p[j].y) >= tz);
+        nzG |= gmv[j] & (unsigned)(fabsf(g[j].x) >= tz || fabsf(g[j].y) >= tz);
+        const SampleResult r = sample_flow<MASKS>(G, Gm, H, W, __fmaf_rn(sign, p[j].x, Xg),
+                                                  __fmaf_rn(sign, p[j].y, static_cast<float>(y)));
+        if (x < (unsigned)W && y < (unsigned)H) {
+            const unsigned idx = y * (unsigned)W + x;
+            float2 o;
+            o.x = __fadd_rn(p[j].x, r.u);
+            o.y = __fadd_rn(p[j].y, r.v);
+            asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(O + idx), "f"(o.x), "f"(o.y) : "memory");
+            Om[idx] = (uint8_t)(pmv[j] & (unsigned)r.strict);
+        }
+    }
+    // clamped duplicates only repeat pixels of the same frame, so they cannot create false positives
+    if (flags != nullptr) publish_flags(REF_T ? nzG : nzP, REF_T ? nzP : nzG, flags, blockIdx.z, &sc);
+}
+
+__device__ __forceinline__ void publish_flags_barrier(bool nzA, bool nzB, int* __restrict__ flags, int n) {
+    const int a = __syncthreads_or(nzA);
+    const int b = __syncthreads_or(nzB);
+    if (threadIdx.x == 0) {
+        if (a) flags[n * 2 + 0] = 1;
+        if (b) flags[n * 2 + 1] = 1;
+    }
 }
 
 // scalar fallback: any W, any alignment
@@ -178,7 +224,7 @@ __global__ void __launch_bounds__(256) combine3_scalar(const float* __restrict__
         out[pix * 2 + 1] = __fadd_rn(pv, av);
         omask[pix] = (pvalid && S == 1024) ? 1 : 0;
     }
-    if (flags != nullptr) publish_flags(REF_T ? nzG : nzP, REF_T ? nzP : nzG, flags, n);
+    if (flags != nullptr) publish_flags_barrier(REF_T ? nzG : nzP, REF_T ? nzP : nzG, flags, n);
 }
 
 // Early exits of combine_with (flow_class.py:1338-1354), applied on the device: frame n becomes a copy of B when A
@@ -215,12 +261,18 @@ extern "C" int ofk_combine3(const float* A, const uint8_t* Am, const float* B, c
     OFK_CHECK_ARG(N <= 65535, "ofk_combine3: N=%d exceeds 65535 frames per call", N);
     cudaStream_t st = as_stream(stream);
     if (flags != nullptr) OFK_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 2 * (size_t)N, st));
-    const bool fast = (W % 4 == 0) && aligned16(A) && aligned16(B) && aligned16(out) && aligned16(out_mask) &&
-                      (Am == nullptr || aligned16(Am)) && (Bm == nullptr || aligned16(Bm));
+    const bool fast = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) |
+                        reinterpret_cast<uintptr_t>(out)) & 7) == 0 && (size_t)H * W < ((size_t)1 << 30) && H < 32768 &&
+                      W < 32768 && ((Am == nullptr) == (Bm == nullptr));
     if (fast) {
-        dim3 grid((W / 4 + 7) / 8, (H + 31) / 32, N);
-        if (ref == 't') combine3_vec4<true><<<grid, 256, 0, st>>>(A, Am, B, Bm, thr, out, out_mask, flags, H, W);
-        else combine3_vec4<false><<<grid, 256, 0, st>>>(A, Am, B, Bm, thr, out, out_mask, flags, H, W);
+        dim3 grid((W + 31) / 32, (H + 31) / 32, N);
+        if (Am && Bm) {
+            if (ref == 't') combine3_rows<true, true><<<grid, 256, 0, st>>>(A, Am, B, Bm, thr, out, out_mask, flags, H, W);
+            else combine3_rows<false, true><<<grid, 256, 0, st>>>(A, Am, B, Bm, thr, out, out_mask, flags, H, W);
+        } else {
+            if (ref == 't') combine3_rows<true, false><<<grid, 256, 0, st>>>(A, Am, B, Bm, thr, out, out_mask, flags, H, W);
+            else combine3_rows<false, false><<<grid, 256, 0, st>>>(A, Am, B, Bm, thr, out, out_mask, flags, H, W);
+        }
     } else {
         dim3 grid((W + 31) / 32, (H + 7) / 8, N);
         if (ref == 't') combine3_scalar<true><<<grid, 256, 0, st>>>(A, Am, B, Bm, thr, out, out_mask, flags, H, W);

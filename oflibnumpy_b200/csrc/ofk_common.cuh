@@ -65,6 +65,17 @@ __device__ __forceinline__ QCoord quantise(float X) {
     return q;
 }
 
+// Same quantisation without the XU-pipe conversion: adding 1.5*2^23 rounds X*32 to an integer (round-half-even, one
+// rounding because X*32 is exact) in the mantissa. Valid for |X| < 2^16; callers test that and fall back to quantise().
+#define OFK_FAST_COORD_LIMIT 65536.0f
+__device__ __forceinline__ QCoord quantise_fast(float X) {
+    const int bits = __float_as_int(__fmaf_rn(X, 32.0f, 12582912.0f)) - 0x4B400000;
+    QCoord q;
+    q.i = bits >> 5;
+    q.f = bits & 31;
+    return q;
+}
+
 // Absolute sampling coordinate: float32(sign*flow) + float32(grid), one rounding, as numpy's in-place
 // `field *= -1; field += arange` (utils.py:233-235).
 __device__ __forceinline__ float sample_coord(float flow_component, float sign, int grid) {

@@ -3,9 +3,10 @@
 // mask plumbing of Flow.apply (flow_class.py:631-680). HBM-bound gather: no tensor cores.
 //
 // Two kernels:
-//   warp_t_vec4    4 output pixels per thread along x, 128-bit flow loads, packed stores, 2-D CTA tiles so the
-//                  gathered neighbourhood of a tile stays in L1; interior pixels of uint8x3 images read both
-//                  horizontal taps of a row with one (two when straddling) aligned 64-bit load.
+//   warp_t_rows    a warp owns 32 consecutive pixels of a row and walks 4 rows (CTA = 32x32 tile): every access of a
+//                  warp instruction is contiguous along x, the gathered neighbourhood of a tile stays in L1.
+//   warp_t_u8x3    the image case: both horizontal taps of a row come from one aligned 64-bit load, the horizontal
+//                  blend runs on packed bytes (dp4a), rounding is integer, 96-byte rows are stored as 24 words.
 //   warp_t_generic 1 pixel per thread, any channel count / dtype / padding offsets / unaligned pointers.
 #include "ofk_common.cuh"
 
@@ -147,20 +148,22 @@ __global__ void __launch_bounds__(256) warp_t_generic(const T* __restrict__ payl
     }
 }
 
-// ----------------------------------------------------------------------------------------------- vec4 kernel
+// ----------------------------------------------------------------------------------------------- rows kernel
+// Thread mapping: a warp owns 32 consecutive pixels of a row (lane = x) and walks 4 rows, a CTA owns a 32x32 tile.
+// Every global access of a warp instruction is therefore contiguous along x: flow / mask / output are fully
+// coalesced and the gathers of a warp touch 2-3 cache lines (a rotated row segment) instead of 8.
+
 // Per-(T,C) tap fetch for one pixel: fills v[4][C] (tap order 00,01,10,11) with zero for out-of-bounds taps.
 template <typename T, int C>
 struct Fetch {
-    __device__ __forceinline__ static void run(const T* __restrict__ p, int Ws, const Taps& t, T (&v)[4][C],
-                                               const void* /*buf_end*/) {
-        const long long o = ((long long)t.iy * Ws + t.ix) * C;
-        const long long row = (long long)Ws * C;
+    __device__ __forceinline__ static void run(const T* __restrict__ p, int Ws, const Taps& t, T (&v)[4][C]) {
+        const int o = (t.iy * Ws + t.ix) * C, row = Ws * C;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            v[0][c] = t.in00 ? p[o + c] : T(0);
-            v[1][c] = t.in01 ? p[o + C + c] : T(0);
-            v[2][c] = t.in10 ? p[o + row + c] : T(0);
-            v[3][c] = t.in11 ? p[o + row + C + c] : T(0);
+            v[0][c] = t.in00 ? __ldg(p + o + c) : T(0);
+            v[1][c] = t.in01 ? __ldg(p + o + C + c) : T(0);
+            v[2][c] = t.in10 ? __ldg(p + o + row + c) : T(0);
+            v[3][c] = t.in11 ? __ldg(p + o + row + C + c) : T(0);
         }
     }
 };
@@ -168,15 +171,14 @@ struct Fetch {
 // float32 x2 (flow fields): one 64-bit load per tap
 template <>
 struct Fetch<float, 2> {
-    __device__ __forceinline__ static void run(const float* __restrict__ p, int Ws, const Taps& t, float (&v)[4][2],
-                                               const void*) {
+    __device__ __forceinline__ static void run(const float* __restrict__ p, int Ws, const Taps& t, float (&v)[4][2]) {
         const float2* q = reinterpret_cast<const float2*>(p);
-        const long long o = (long long)t.iy * Ws + t.ix;
+        const int o = t.iy * Ws + t.ix;
         const float2 z = make_float2(0.f, 0.f);
-        float2 a = t.in00 ? __ldg(q + o) : z;
-        float2 b = t.in01 ? __ldg(q + o + 1) : z;
-        float2 c = t.in10 ? __ldg(q + o + Ws) : z;
-        float2 d = t.in11 ? __ldg(q + o + Ws + 1) : z;
+        const float2 a = t.in00 ? __ldg(q + o) : z;
+        const float2 b = t.in01 ? __ldg(q + o + 1) : z;
+        const float2 c = t.in10 ? __ldg(q + o + Ws) : z;
+        const float2 d = t.in11 ? __ldg(q + o + Ws + 1) : z;
         v[0][0] = a.x; v[0][1] = a.y;
         v[1][0] = b.x; v[1][1] = b.y;
         v[2][0] = c.x; v[2][1] = c.y;
@@ -184,13 +186,29 @@ struct Fetch<float, 2> {
     }
 };
 
+// float32 x4: one 128-bit load per tap
+template <>
+struct Fetch<float, 4> {
+    __device__ __forceinline__ static void run(const float* __restrict__ p, int Ws, const Taps& t, float (&v)[4][4]) {
+        const float4* q = reinterpret_cast<const float4*>(p);
+        const int o = t.iy * Ws + t.ix;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 r[4] = {t.in00 ? __ldg(q + o) : z, t.in01 ? __ldg(q + o + 1) : z, t.in10 ? __ldg(q + o + Ws) : z,
+                             t.in11 ? __ldg(q + o + Ws + 1) : z};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[k][0] = r[k].x; v[k][1] = r[k].y; v[k][2] = r[k].z; v[k][3] = r[k].w;
+        }
+    }
+};
+
 // uint8 x4: one 32-bit load per tap
 template <>
 struct Fetch<uint8_t, 4> {
     __device__ __forceinline__ static void run(const uint8_t* __restrict__ p, int Ws, const Taps& t,
-                                               uint8_t (&v)[4][4], const void*) {
+                                               uint8_t (&v)[4][4]) {
         const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
-        const long long o = (long long)t.iy * Ws + t.ix;
+        const int o = t.iy * Ws + t.ix;
         uint32_t w[4];
         w[0] = t.in00 ? __ldg(q + o) : 0u;
         w[1] = t.in01 ? __ldg(q + o + 1) : 0u;
@@ -206,134 +224,260 @@ struct Fetch<uint8_t, 4> {
     }
 };
 
-// 6-byte window [b0..b5] starting at address a: the two horizontal taps of a uint8x3 row.
-// One aligned 64-bit load, a second one only when the window straddles the 8-byte boundary.
-__device__ __forceinline__ uint64_t window6(const uint8_t* __restrict__ a) {
-    const uintptr_t addr = reinterpret_cast<uintptr_t>(a);
-    const unsigned long long* q = reinterpret_cast<const unsigned long long*>(addr & ~uintptr_t(7));
-    const unsigned sh = (unsigned)(addr & 7) * 8;
-    uint64_t lo = __ldg(q);
-    if (sh > 16) {  // bytes 0..5 of the window cross into the next word
-        uint64_t hi = __ldg(q + 1);
-        lo = (lo >> sh) | (hi << (64 - sh));
-    } else {
-        lo >>= sh;
-    }
-    return lo;
-}
-
-template <>
-struct Fetch<uint8_t, 3> {
-    __device__ __forceinline__ static void run(const uint8_t* __restrict__ p, int Ws, const Taps& t,
-                                               uint8_t (&v)[4][3], const void* buf_end) {
-        const long long o = ((long long)t.iy * Ws + t.ix) * 3;
-        const long long row = (long long)Ws * 3;
-        // fast path: all four taps inside, and the aligned word covering the end of the lower window inside the buffer
-        if (t.interior &&
-            ((reinterpret_cast<uintptr_t>(p + o + row + 6) + 7) & ~uintptr_t(7)) <= reinterpret_cast<uintptr_t>(buf_end)) {
-            uint64_t r0 = window6(p + o);
-            uint64_t r1 = window6(p + o + row);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                v[0][c] = (uint8_t)(r0 >> (8 * c));
-                v[1][c] = (uint8_t)(r0 >> (8 * (c + 3)));
-                v[2][c] = (uint8_t)(r1 >> (8 * c));
-                v[3][c] = (uint8_t)(r1 >> (8 * (c + 3)));
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                v[0][c] = t.in00 ? p[o + c] : 0;
-                v[1][c] = t.in01 ? p[o + 3 + c] : 0;
-                v[2][c] = t.in10 ? p[o + row + c] : 0;
-                v[3][c] = t.in11 ? p[o + row + 3 + c] : 0;
-            }
-        }
-    }
-};
-
-// Packed store of 4 pixels x C elements of T (contiguous, 4*C*sizeof(T) bytes, a multiple of 4 bytes; the address is
-// 4-byte aligned because W % 4 == 0 and x0 % 4 == 0).
+// Store C elements of one pixel (contiguous across the warp).
 template <typename T, int C>
-__device__ __forceinline__ void store4(T* __restrict__ dst, const T (&r)[4][C]) {
-    constexpr int BYTES = 4 * C * sizeof(T);
-    union {
-        T e[4 * C];
-        uint32_t w[BYTES / 4];
-        uint4 q[(BYTES + 15) / 16];
-    } u;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int c = 0; c < C; ++c) u.e[j * C + c] = r[j][c];
-    if constexpr (BYTES % 16 == 0) {
-        // 16-byte aligned when the per-4-pixel footprint is a multiple of 16 bytes
-        uint4* d = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-        for (int k = 0; k < BYTES / 16; ++k) d[k] = u.q[k];
+__device__ __forceinline__ void store_px(T* __restrict__ dst, const T (&r)[C]) {
+    if constexpr (sizeof(T) * C == 8) {
+        uint2 u;
+        memcpy(&u, r, 8);
+        *reinterpret_cast<uint2*>(dst) = u;
+    } else if constexpr (sizeof(T) * C == 16) {
+        uint4 u;
+        memcpy(&u, r, 16);
+        *reinterpret_cast<uint4*>(dst) = u;
+    } else if constexpr (sizeof(T) * C == 4) {
+        uint32_t u;
+        memcpy(&u, r, 4);
+        *reinterpret_cast<uint32_t*>(dst) = u;
     } else {
-        uint32_t* d = reinterpret_cast<uint32_t*>(dst);
 #pragma unroll
-        for (int k = 0; k < BYTES / 4; ++k) d[k] = u.w[k];
+        for (int c = 0; c < C; ++c) dst[c] = r[c];
     }
-}
-
-// TXT x-threads per tile row (tile width = 4*TXT pixels), 256/TXT rows per tile.
-template <typename T, int C, int AR, int TXT>
-__global__ void __launch_bounds__(256) warp_t_vec4(const T* __restrict__ payload, const float* __restrict__ flow,
-                                                   float sign, const uint8_t* __restrict__ pmask,
-                                                   const uint8_t* __restrict__ fmask, T* __restrict__ out,
-                                                   uint8_t* __restrict__ omask, int rule, int H, int W) {
-    constexpr int ROWS = 256 / TXT;
-    const int tx = threadIdx.x % TXT, ty = threadIdx.x / TXT;
-    const int x0 = (blockIdx.x * TXT + tx) * 4;
-    const int y = blockIdx.y * ROWS + ty;
-    const int n = blockIdx.z;
-    if (x0 >= W || y >= H) return;
-    const size_t pix0 = ((size_t)n * H + y) * W + x0;
-
-    const float4* f4 = reinterpret_cast<const float4*>(flow + pix0 * 2);
-    const float4 fa = ld_stream_f4(f4), fb = ld_stream_f4(f4 + 1);
-    const float u[4] = {fa.x, fa.z, fb.x, fb.z};
-    const float v[4] = {fa.y, fa.w, fb.y, fb.w};
-    uint32_t fm = 0x01010101u;
-    if (omask != nullptr && fmask != nullptr) fm = ld_stream_u32(reinterpret_cast<const uint32_t*>(fmask + pix0));
-
-    const size_t frame_elems = (size_t)H * W * C;
-    const T* p = payload + (size_t)n * frame_elems;
-    const uint8_t* pm = pmask ? pmask + (size_t)n * H * W : nullptr;
-    const float Y0 = static_cast<float>(y);
-
-    const void* buf_end = payload + (size_t)gridDim.z * frame_elems;
-    T res[4][C > 0 ? C : 1];
-    uint32_t om = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float X = __fadd_rn(sign * u[j], static_cast<float>(x0 + j));
-        const float Y = __fadd_rn(sign * v[j], Y0);
-        const Taps t = make_taps(X, Y, H, W);
-        if constexpr (C > 0) {
-            T taps[4][C];
-            Fetch<T, C>::run(p, W, t, taps, buf_end);
-#pragma unroll
-            for (int c = 0; c < C; ++c) res[j][c] = blend<T, AR>(taps[0][c], taps[1][c], taps[2][c], taps[3][c], t.w);
-        }
-        if (omask != nullptr) {
-            const bool ok = mask_rule_pass(valid_weight_sum(t, pm, W), rule) && ((fm >> (8 * j)) & 1u);
-            om |= (ok ? 1u : 0u) << (8 * j);
-        }
-    }
-    if constexpr (C > 0) store4<T, C>(out + pix0 * C, res);
-    if (omask != nullptr) *reinterpret_cast<uint32_t*>(omask + pix0) = om;
 }
 
 template <typename T, int C, int AR>
-static int launch_vec4(const void* payload, const float* flow, float sign, const uint8_t* pmask, const uint8_t* fmask,
+__global__ void __launch_bounds__(256) warp_t_rows(const T* __restrict__ payload, const float* __restrict__ flow,
+                                                   float sign, const uint8_t* __restrict__ pmask,
+                                                   const uint8_t* __restrict__ fmask, T* __restrict__ out,
+                                                   uint8_t* __restrict__ omask, int rule, int H, int W) {
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int x = blockIdx.x * 32 + lane;
+    const int y0 = blockIdx.y * 32 + wrp * 4;
+    const size_t frame = (size_t)H * W, fbase = (size_t)blockIdx.z * frame;
+    if (x >= W) return;
+    const float2* fl = reinterpret_cast<const float2*>(flow) + fbase;
+    const uint8_t* fm = fmask ? fmask + fbase : nullptr;
+    const uint8_t* pm = pmask ? pmask + fbase : nullptr;
+    const T* p = C > 0 ? payload + fbase * C : nullptr;
+    const float Xg = static_cast<float>(x);
+    float2 f[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (y0 + j < H) f[j] = ld_stream_f2(fl + (y0 + j) * W + x);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int y = y0 + j;
+        if (y >= H) break;
+        const int pix = y * W + x;
+        const Taps t = make_taps(__fadd_rn(sign * f[j].x, Xg), __fadd_rn(sign * f[j].y, static_cast<float>(y)), H, W);
+        if constexpr (C > 0) {
+            T taps[4][C], res[C];
+            Fetch<T, C>::run(p, W, t, taps);
+#pragma unroll
+            for (int c = 0; c < C; ++c) res[c] = blend<T, AR>(taps[0][c], taps[1][c], taps[2][c], taps[3][c], t.w);
+            store_px<T, C>(out + (fbase + pix) * C, res);
+        }
+        if (omask != nullptr) {
+            const int S = (pm == nullptr && t.interior) ? 1024 : valid_weight_sum(t, pm, W);
+            const bool ok = mask_rule_pass(S, rule) && (fm == nullptr || fm[pix] != 0);
+            omask[fbase + pix] = ok ? 1 : 0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------- uint8 x3 (images), specialised
+// Both arithmetic modes are pure integer for 8-bit taps: with weights k/1024 the float32 products and partial sums of
+// cv2.remap's int16 path are exact (< 2^18 in units of 1/1024), so cvRound(sum) == round-half-even(acc / 1024) where
+// acc = sum t*w is the same integer the fixed-point path rounds half-up.
+__device__ __forceinline__ uint32_t round_acc(int acc, bool half_even) {
+    return half_even ? (uint32_t)(acc + 511 + ((acc >> 10) & 1)) >> 10 : (uint32_t)(acc + 512) >> 10;
+}
+
+// bytes [b0..b5] at byte offset `off` from the 4-byte aligned base pa (the two horizontal taps of a row):
+// lo = b0..b3, hi = b4,b5 (upper half undefined). Three aligned 32-bit loads off one address, two funnel shifts.
+__device__ __forceinline__ void window6(const uint8_t* __restrict__ pa, int off, uint32_t& lo, uint32_t& hi) {
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(pa + (off & ~3));
+    const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+    const unsigned t = (unsigned)off << 3;          // funnel shift uses t & 31 = 8 * (off & 3)
+    lo = __funnelshift_r(w0, w1, t);
+    hi = __funnelshift_r(w1, w2, t);
+}
+
+// Pixels whose taps touch the border (or whose coordinates leave the fast-quantisation range): exact but slow, out
+// of line, by-value in / out (no stack traffic). Returns the 3 result bytes in bits 0..23 and the validity in bit 24.
+__device__ __noinline__ uint32_t border_px_u8x3(const uint8_t* __restrict__ p, const uint8_t* __restrict__ pm, float X,
+                                                float Y, int H, int W, int half_even, int rule) {
+    const QCoord qx = quantise(X), qy = quantise(Y);
+    const int ix = qx.i, iy = qy.i;
+    const QWeights w = qweights(qx.f, qy.f);
+    const bool in[4] = {(unsigned)ix < (unsigned)W && (unsigned)iy < (unsigned)H,
+                        (unsigned)(ix + 1) < (unsigned)W && (unsigned)iy < (unsigned)H,
+                        (unsigned)ix < (unsigned)W && (unsigned)(iy + 1) < (unsigned)H,
+                        (unsigned)(ix + 1) < (unsigned)W && (unsigned)(iy + 1) < (unsigned)H};
+    const long long o = (long long)iy * W + ix;
+    const long long off[4] = {o, o + 1, o + W, o + W + 1};
+    const int wi[4] = {w.w00, w.w01, w.w10, w.w11};
+    int acc[3] = {0, 0, 0}, S = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (!in[k]) continue;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[c] += (int)p[off[k] * 3 + c] * wi[k];
+        if (pm == nullptr || pm[off[k]]) S += wi[k];
+    }
+    uint32_t v = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int a = acc[c];
+        const uint32_t r = half_even ? (uint32_t)(a + 511 + ((a >> 10) & 1)) >> 10 : (uint32_t)(a + 512) >> 10;
+        v |= r << (8 * c);
+    }
+    return v | (mask_rule_pass(S, rule) ? (1u << 24) : 0u);
+}
+
+// bytes [b0..b5] at byte offset `off` from the 4-byte aligned base pa (the two horizontal taps of a row):
+// lo = b0..b3, hi = b4,b5 (upper half undefined). Three aligned 32-bit loads off one address, two funnel shifts.
+__device__ __forceinline__ void window6(const uint8_t* __restrict__ pa, unsigned off, uint32_t& lo, uint32_t& hi) {
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(pa + (off & ~3u));
+    const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+    const unsigned t = off << 3;                    // funnel shift uses t & 31 = 8 * (off & 3)
+    lo = __funnelshift_r(w0, w1, t);
+    hi = __funnelshift_r(w1, w2, t);
+}
+
+// HALF_EVEN: cv2.remap's int16 path (cvRound) instead of the uint8 fixed-point path; PM: a payload mask is resampled.
+// Loads use clamped indices (no branches), only the stores are predicated.
+template <bool HALF_EVEN, bool PM>
+__global__ void __launch_bounds__(256) warp_t_u8x3(const uint8_t* __restrict__ payload,
+                                                   const float* __restrict__ flow, float sign,
+                                                   const uint8_t* __restrict__ pmask,
+                                                   const uint8_t* __restrict__ fmask, uint8_t* __restrict__ out,
+                                                   uint8_t* __restrict__ omask, int rule, int H, int W,
+                                                   int packed_store) {
+    const unsigned lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const unsigned x = blockIdx.x * 32 + lane, xc = min(x, (unsigned)W - 1);
+    const unsigned y0 = blockIdx.y * 32 + wrp * 4;
+    const size_t frame = (size_t)H * W, fbase = (size_t)blockIdx.z * frame;
+    const bool full_row = packed_store && (blockIdx.x * 32 + 32 <= (unsigned)W);   // warp-uniform
+    const float2* fl = reinterpret_cast<const float2*>(flow) + fbase;
+    const uint8_t* fm = fmask ? fmask + fbase : nullptr;
+    const uint8_t* pm = PM ? pmask + fbase : nullptr;
+    const uint8_t* p = payload + fbase * 3;
+    // 4-byte aligned view of the frame for the word loads of the interior path
+    const unsigned r0 = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3);
+    const uint8_t* pa = p - r0;
+    const size_t avail = (size_t)(payload + (size_t)gridDim.z * frame * 3 - pa);
+    const unsigned limit = avail > 0x7fffffffu ? 0x7fffffffu : (unsigned)avail;
+    uint8_t* o = out + fbase * 3;
+    uint8_t* om = omask ? omask + fbase : nullptr;
+    const float Xg = static_cast<float>(x);
+    const unsigned row3 = (unsigned)W * 3;
+    float2 f[4];
+    unsigned fmv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const unsigned idx = min(y0 + j, (unsigned)H - 1) * (unsigned)W + xc;
+        f[j] = ld_stream_f2(fl + idx);
+        fmv[j] = (om != nullptr && fm != nullptr) ? fm[idx] : 1u;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const unsigned y = y0 + j;
+        if (y >= (unsigned)H) break;                                     // warp-uniform
+        const float X = __fmaf_rn(sign, f[j].x, Xg), Y = __fmaf_rn(sign, f[j].y, static_cast<float>(y));
+        const QCoord qx = quantise_fast(X), qy = quantise_fast(Y);
+        const unsigned off = (unsigned)(qy.i * W + qx.i) * 3 + r0;
+        const bool interior = (unsigned)qx.i < (unsigned)(W - 1) && (unsigned)qy.i < (unsigned)(H - 1) &&
+                              fabsf(X) < OFK_FAST_COORD_LIMIT && fabsf(Y) < OFK_FAST_COORD_LIMIT &&
+                              off + row3 + 12 <= limit;
+        uint32_t v;
+        unsigned ok;
+        if (interior) {
+            uint32_t lo0, hi0, lo1, hi1;
+            window6(pa, off, lo0, hi0);
+            window6(pa, off + row3, lo1, hi1);
+            const uint32_t a = qx.f, na = 32 - a;
+            const int b = qy.f;
+            ok = 1;
+            if (PM) {
+                const uint8_t* m0 = pm + (unsigned)(qy.i * W + qx.i);
+                const uint8_t* m1 = m0 + W;
+                const QWeights w = qweights((int)a, b);
+                const int S = (m0[0] ? w.w00 : 0) + (m0[1] ? w.w01 : 0) + (m1[0] ? w.w10 : 0) + (m1[1] ? w.w11 : 0);
+                ok = mask_rule_pass(S, rule);
+            }
+            // horizontal pass with 8-bit weights on packed bytes (dp4a); vertical pass in 32 bits with the weights
+            // scaled by 64 so the rounded result lands in byte 2: t = acc * 64 + 512 * 64
+            const uint32_t w0 = na | (a << 24);                     // ch0: lo byte0 (tap 0) and lo byte3 (tap 1)
+            const uint32_t w1l = na << 8, w1h = a;                  // ch1: lo byte1, hi byte0
+            const uint32_t w2l = na << 16, w2h = a << 8;            // ch2: lo byte2, hi byte1
+            const uint32_t vb = (uint32_t)b << 6, vnb = 2048u - vb;
+            const uint32_t t0 = __dp4a(lo0, w0, 0u) * vnb + (__dp4a(lo1, w0, 0u) * vb + 32768u);
+            const uint32_t t1 = __dp4a(lo0, w1l, __dp4a(hi0, w1h, 0u)) * vnb +
+                                (__dp4a(lo1, w1l, __dp4a(hi1, w1h, 0u)) * vb + 32768u);
+            const uint32_t t2 = __dp4a(lo0, w2l, __dp4a(hi0, w2h, 0u)) * vnb +
+                                (__dp4a(lo1, w2l, __dp4a(hi1, w2h, 0u)) * vb + 32768u);
+            // round half up = byte 2 of t; bytes: v = [t0.b2, t1.b2, t2.b2, 0]
+            v = __byte_perm(__byte_perm(t0, t1, 0x0062), t2, 0x4610) & 0x00ffffffu;
+            if (HALF_EVEN) {
+                // cvRound sends exact ties to the even neighbour: a tie that rounded up to an odd value shows as
+                // (t & 0x1ffff) == 0x10000. Rare, so test all three at once and fix up out of the main flow.
+                const uint32_t m0 = (t0 & 0x1ffffu) ^ 0x10000u, m1 = (t1 & 0x1ffffu) ^ 0x10000u,
+                               m2 = (t2 & 0x1ffffu) ^ 0x10000u;
+                if (min(m0, min(m1, m2)) == 0u) {
+                    if (m0 == 0u) v -= 1u;
+                    if (m1 == 0u) v -= 1u << 8;
+                    if (m2 == 0u) v -= 1u << 16;
+                }
+            }
+        } else {
+            const uint32_t r = border_px_u8x3(p, pm, X, Y, H, W, HALF_EVEN, rule);
+            v = r & 0x00ffffffu;
+            ok = r >> 24;
+        }
+        const bool xin = x < (unsigned)W;
+        if (om != nullptr && xin) om[y * (unsigned)W + x] = (uint8_t)(ok & fmv[j]);
+        if (full_row) {
+            // 32 pixels x 3 bytes = 24 words: lane L < 24 assembles word L from pixels L + L/3 and the next one
+            const unsigned p0 = lane + lane / 3;
+            const uint32_t v0 = __shfl_sync(0xffffffffu, v, p0 & 31), v1 = __shfl_sync(0xffffffffu, v, (p0 + 1) & 31);
+            const uint32_t word = __funnelshift_r(v0 | (v1 << 24), v1 >> 8, 8 * (lane % 3));
+            if (lane < 24)
+                st_stream_u32(reinterpret_cast<uint32_t*>(o + ((size_t)y * W + blockIdx.x * 32) * 3) + lane, word);
+        } else if (xin) {
+            uint8_t* d = o + ((size_t)y * W + x) * 3;
+            d[0] = (uint8_t)v;
+            d[1] = (uint8_t)(v >> 8);
+            d[2] = (uint8_t)(v >> 16);
+        }
+    }
+}
+
+template <typename T, int C, int AR>
+static int launch_rows(const void* payload, const float* flow, float sign, const uint8_t* pmask, const uint8_t* fmask,
                        void* out, uint8_t* omask, int rule, int N, int H, int W, cudaStream_t st) {
-    constexpr int TXT = 8;  // 32 x 32 pixel tiles
-    dim3 grid((W / 4 + TXT - 1) / TXT, (H + (256 / TXT) - 1) / (256 / TXT), N);
-    warp_t_vec4<T, C, AR, TXT><<<grid, 256, 0, st>>>(static_cast<const T*>(payload), flow, sign, pmask, fmask,
-                                                     static_cast<T*>(out), omask, rule, H, W);
+    dim3 grid((W + 31) / 32, (H + 31) / 32, N);
+    warp_t_rows<T, C, AR><<<grid, 256, 0, st>>>(static_cast<const T*>(payload), flow, sign, pmask, fmask,
+                                                static_cast<T*>(out), omask, rule, H, W);
+    OFK_LAUNCHED();
+    return OFK_OK;
+}
+
+static int launch_u8x3(bool half_even, const void* payload, const float* flow, float sign, const uint8_t* pmask,
+                       const uint8_t* fmask, void* out, uint8_t* omask, int rule, int N, int H, int W,
+                       cudaStream_t st) {
+    dim3 grid((W + 31) / 32, (H + 31) / 32, N);
+    // word stores need every row start 4-byte aligned: W % 4 == 0 and a 4-byte aligned base
+    const int packed = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 3) == 0);
+#define OFK_U8X3(HE, PMK)                                                                                    \
+    warp_t_u8x3<HE, PMK><<<grid, 256, 0, st>>>((const uint8_t*)payload, flow, sign, pmask, fmask, (uint8_t*)out, \
+                                               omask, rule, H, W, packed)
+    const bool pmk = pmask != nullptr && omask != nullptr;
+    if (half_even && pmk) OFK_U8X3(true, true);
+    else if (half_even) OFK_U8X3(true, false);
+    else if (pmk) OFK_U8X3(false, true);
+    else OFK_U8X3(false, false);
+#undef OFK_U8X3
     OFK_LAUNCHED();
     return OFK_OK;
 }
@@ -384,29 +528,30 @@ extern "C" int ofk_warp_t(const void* payload, int dtype, int C, int arith, cons
         case OFK_F32: ar = AR_F32; break;
         default: ar = AR_F64; break;
     }
-    const bool fast = same_frame && (W % 4 == 0) && aligned16(flow) && (C == 0 || (aligned16(payload) && aligned16(out))) &&
-                      (payload_mask == nullptr || aligned16(payload_mask)) &&
-                      (flow_mask == nullptr || aligned16(flow_mask)) && (out_mask == nullptr || aligned16(out_mask));
+    // rows kernels: same frame for flow and payload, natural alignment, frame-local 32-bit offsets
+    const bool fast = same_frame && H < 32768 && W < 32768 && ((size_t)H * W * (C > 0 ? C : 1) < (size_t)1 << 30) &&
+                      ((reinterpret_cast<uintptr_t>(flow) & 7) == 0) &&
+                      (C == 0 || (aligned16(payload) && aligned16(out)));
     if (fast) {
-#define OFK_V4(T, CC, AR)                                                                                         \
-    return launch_vec4<T, CC, AR>(payload, flow, flow_sign, payload_mask, flow_mask, out, out_mask, mask_rule, N, H, \
-                                  W, st)
-        if (C == 0) OFK_V4(uint8_t, 0, AR_U8_FIXED);
+#define OFK_ROWS(T, CC, AR) \
+    return launch_rows<T, CC, AR>(payload, flow, flow_sign, payload_mask, flow_mask, out, out_mask, mask_rule, N, H, W, st)
+        if (C == 0) OFK_ROWS(uint8_t, 0, AR_U8_FIXED);
+        if (dtype == OFK_U8 && C == 3)
+            return launch_u8x3(ar == AR_RINT, payload, flow, flow_sign, payload_mask, flow_mask, out, out_mask,
+                               mask_rule, N, H, W, st);
         if (dtype == OFK_U8 && ar == AR_U8_FIXED) {
-            if (C == 3) OFK_V4(uint8_t, 3, AR_U8_FIXED);
-            if (C == 1) OFK_V4(uint8_t, 1, AR_U8_FIXED);
-            if (C == 4) OFK_V4(uint8_t, 4, AR_U8_FIXED);
+            if (C == 1) OFK_ROWS(uint8_t, 1, AR_U8_FIXED);
+            if (C == 4) OFK_ROWS(uint8_t, 4, AR_U8_FIXED);
         } else if (dtype == OFK_U8 && ar == AR_RINT) {
-            if (C == 3) OFK_V4(uint8_t, 3, AR_RINT);
-            if (C == 1) OFK_V4(uint8_t, 1, AR_RINT);
-            if (C == 4) OFK_V4(uint8_t, 4, AR_RINT);
+            if (C == 1) OFK_ROWS(uint8_t, 1, AR_RINT);
+            if (C == 4) OFK_ROWS(uint8_t, 4, AR_RINT);
         } else if (dtype == OFK_F32) {
-            if (C == 2) OFK_V4(float, 2, AR_F32);
-            if (C == 3) OFK_V4(float, 3, AR_F32);
-            if (C == 1) OFK_V4(float, 1, AR_F32);
-            if (C == 4) OFK_V4(float, 4, AR_F32);
+            if (C == 2) OFK_ROWS(float, 2, AR_F32);
+            if (C == 3) OFK_ROWS(float, 3, AR_F32);
+            if (C == 1) OFK_ROWS(float, 1, AR_F32);
+            if (C == 4) OFK_ROWS(float, 4, AR_F32);
         }
-#undef OFK_V4
+#undef OFK_ROWS
     }
     // generic path: output frame is the flow frame (cut) or the payload frame (no cut)
     const int Ho = cut ? H : Hs, Wo = cut ? W : Ws;

@@ -388,6 +388,7 @@ class Flow(object):
                            rule, placement, cut)
 
     def _apply_s(self, payload, pmask, host_tmask, return_flow, want_mask, consider_mask, padding, cut):
+        out_is_float = return_flow or np.issubdtype(payload.dtype, np.floating)
         if not return_flow:
             payload = DeviceArray.from_numpy(payload[None], np.float32)
             pmask = None if host_tmask is None else DeviceArray.from_numpy(host_tmask[None].view(np.uint8))
@@ -400,7 +401,10 @@ class Flow(object):
             if padding is not None and host_tmask is not None:
                 # the reference overwrites the caller's target_mask in place here (flow_class.py:639-641)
                 host_tmask[...] = res_mask.numpy()[0].view(np.bool_)
-        warped, wmask = _ops.forward_s(flow_v, 1.0, payload, res_mask, flow_m if consider_mask else None, want_mask)
+        # integer payloads: the reference rounds the interpolated payload||mask array before `== 1` (utils.py:256-258)
+        rule = _lib.RULE_STRICT if (return_flow or out_is_float) else _lib.RULE_GT_HALF
+        warped, wmask = _ops.forward_s(flow_v, 1.0, payload, res_mask, flow_m if consider_mask else None, want_mask,
+                                       rule)
         if padding is not None and cut:
             fh, fw = self.shape
             warped = _ops.crop(warped, padding[0], padding[2], fh, fw)
