@@ -168,6 +168,21 @@ int ofk_crop(const void* in, void* out, int elem_bytes, int N, int H, int W, int
 int ofk_extent(const float* flow, const uint8_t* mask, float sign, float thr, float* out4, int N, int H, int W,
                ofk_stream_t stream);
 
+/* Flow.resize / resize_flow (flow_class.py:491-506, utils.py:493-524): cv2.resize(INTER_LINEAR) of vectors and float
+ * mask to [N,Ho,Wo], vectors multiplied by (fx, fy) per channel, mask = round-half-even(resized mask) == 1.
+ * Ho = cvRound(H*fy), Wo = cvRound(W*fx) are computed by the caller. Either pair of pointers may be NULL. */
+int ofk_resize_flow(const float* vecs, const uint8_t* mask, float* out_vecs, uint8_t* out_mask, int N, int H, int W,
+                    int Ho, int Wo, double fy, double fx, ofk_stream_t stream);
+
+/* out[i] = v[i] > thr (the `> .99` mask test of combine_with mode 2 / ref 't', flow_class.py:1410). */
+int ofk_greater(const float* v, float thr, uint8_t* out, size_t n, ofk_stream_t stream);
+
+/* Point tracking through an 's' flow with float points: replaces bilinear_interpolation + `pts + flow_vecs`
+ * (utils.py:161-196,605,608). flow [H,W,2] (one frame), pts float64 [n][2] (row, col); out float64 [n][2];
+ * bad (int32, device) is set to 1 if any point lies outside the flow area (the reference raises IndexError). */
+int ofk_track_bilinear(const float* flow, const double* pts, size_t n, int H, int W, double* out, int* bad,
+                       ofk_stream_t stream);
+
 /* points_inside_area (utils.py:283-295): pts float64 [n][2] (row, col) rounded half-even like numpy.round. */
 int ofk_points_inside_area(const double* pts, size_t n, int H, int W, uint8_t* out, ofk_stream_t stream);
 
@@ -185,6 +200,19 @@ size_t ofk_forward_s_workspace(int N, int H, int W);
 int ofk_forward_s(const float* payload, int C, const float* flow, float flow_sign, const uint8_t* payload_mask,
                   const uint8_t* point_mask, float* out, uint8_t* out_mask, int mask_rule, int N, int H, int W,
                   void* ws, size_t ws_bytes, ofk_stream_t stream);
+
+/* Scattered-to-scattered barycentric interpolation on the displaced-grid mesh: replaces the direct
+ * `griddata(grid - A, A||mask, grid - B, 'linear', fill_value=0)` of combine_with mode 2 / ref 't'
+ * (flow_class.py:1398-1410) and the griddata calls of track_pts (utils.py:603,614).
+ *   mesh vertices: p + mesh_sign * mesh_flow[p] carrying payload[p] (float32, C channels) and payload_mask[p]
+ *   queries: either one per pixel at p + query_sign * query_flow[p] (Q = H*W), or Q explicit float64 (row, col)
+ *   points per frame (query_pts [N,Q,2]); exactly one of the two is non-NULL.
+ *   pos_f32 != 0: coordinates are rounded to float32 before use, as the reference's in-place float32 adds do.
+ *   out [N,Q,C] float32 (0 outside the mesh), out_maskval [N,Q] float32 interpolated mask (may be NULL),
+ *   found [N,Q] uint8: 1 where a containing triangle exists (griddata returns NaN elsewhere; may be NULL). */
+int ofk_mesh_sample(const float* mesh_flow, float mesh_sign, int pos_f32, const float* payload, int C,
+                    const uint8_t* payload_mask, const float* query_flow, float query_sign, const double* query_pts,
+                    int Q, float* out, float* out_maskval, uint8_t* found, int N, int H, int W, ofk_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------ host-buffer API */
 

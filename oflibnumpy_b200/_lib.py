@@ -36,9 +36,13 @@ _SIGNATURES = {
     'ofk_mask_and': (_i, [_vp, _vp, _vp, _sz, _vp]),
     'ofk_crop': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'ofk_extent': (_i, [_vp, _vp, _f, _f, _vp, _i, _i, _i, _vp]),
+    'ofk_resize_flow': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _d, _vp]),
+    'ofk_greater': (_i, [_vp, _f, _vp, _sz, _vp]),
+    'ofk_track_bilinear': (_i, [_vp, _vp, _sz, _i, _i, _vp, _vp, _vp]),
     'ofk_points_inside_area': (_i, [_vp, _sz, _i, _i, _vp, _vp]),
     'ofk_forward_s_workspace': (_sz, [_i, _i, _i]),
     'ofk_forward_s': (_i, [_vp, _i, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    'ofk_mesh_sample': (_i, [_vp, _f, _i, _vp, _i, _vp, _vp, _f, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'ofh_warp_t': (_i, [_vp, _i, _i, _i, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i]),
     'ofh_combine3': (_i, [_vp, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _i, _i, _i, _i]),
     'ofh_release': (_i, []),

@@ -185,3 +185,52 @@ def forward_s(flow, sign, payload, payload_mask=None, point_mask=None, want_mask
     _lib.call('ofk_forward_s', _p(payload), c, flow.ptr, float(sign), _p(payload_mask), _p(point_mask), _p(out),
               _p(omask), rule, n, h, w, ws.ptr, ws_bytes, dev.current_stream())
     return out, omask
+
+
+def mesh_sample(mesh_flow, mesh_sign, payload, payload_mask, query_flow=None, query_sign=1.0, query_pts=None,
+                pos_f32=False, want_mask=True, want_found=False):
+    """Scattered-to-scattered interpolation on the displaced-grid mesh (ofk_mesh_sample)."""
+    n, h, w = mesh_flow.shape[:3]
+    c = payload.shape[3] if payload is not None else 0
+    if query_pts is not None:
+        q = query_pts.shape[1]
+        oshape = (n, q)
+    else:
+        q = h * w
+        oshape = (n, h, w)
+    out = DeviceArray.empty(oshape + (c,), np.float32) if c else None
+    mval = DeviceArray.empty(oshape, np.float32) if want_mask else None
+    found = DeviceArray.empty(oshape, np.uint8) if want_found else None
+    _lib.call('ofk_mesh_sample', mesh_flow.ptr, float(mesh_sign), 1 if pos_f32 else 0, _p(payload), c,
+              _p(payload_mask), _p(query_flow), float(query_sign), _p(query_pts), q, _p(out), _p(mval), _p(found), n, h,
+              w, dev.current_stream())
+    return out, mval, found
+
+
+def greater(values, thr):
+    out = DeviceArray.empty(values.shape, np.uint8)
+    _lib.call('ofk_greater', values.ptr, float(thr), out.ptr, values.size, dev.current_stream())
+    return out
+
+
+def track_bilinear(flow, pts):
+    """flow: DeviceArray [1,H,W,2]; pts: numpy float64 (n,2). Returns (numpy (n,2) float64, outside flag)."""
+    h, w = flow.shape[1:3]
+    p = DeviceArray.from_numpy(np.ascontiguousarray(pts, dtype=np.float64))
+    out = DeviceArray.empty(p.shape, np.float64)
+    bad = DeviceArray.empty((1,), np.int32)
+    _lib.call('ofk_track_bilinear', flow.ptr, p.ptr, p.shape[0], h, w, out.ptr, bad.ptr, dev.current_stream())
+    return out.numpy(), bool(bad.numpy()[0])
+
+
+def resize_flow(vecs, mask, fy, fx):
+    """cv2.resize semantics: output size = round-half-even(size * scale) (ofk_resize_flow)."""
+    n, h, w = (vecs if vecs is not None else mask).shape[:3]
+    ho, wo = int(np.rint(h * float(fy))), int(np.rint(w * float(fx)))
+    if ho < 1 or wo < 1:
+        raise ValueError("Error resizing flow: Scale values result in an empty flow field")
+    ov = DeviceArray.empty((n, ho, wo, 2), np.float32) if vecs is not None else None
+    om = DeviceArray.empty((n, ho, wo), np.uint8) if mask is not None else None
+    _lib.call('ofk_resize_flow', _p(vecs), _p(mask), _p(ov), _p(om), n, h, w, ho, wo, float(fy), float(fx),
+              dev.current_stream())
+    return ov, om

@@ -236,6 +236,95 @@ __global__ void __launch_bounds__(256) crop_kernel(const uint8_t* __restrict__ i
         dst[i] = src[i];
 }
 
+// cv2.resize(INTER_LINEAR) of a flow field and its mask (utils.py:493-524, flow_class.py:491-506): half-pixel-centre
+// mapping, edge clamp, float32 coefficients; horizontal pass then vertical pass like OpenCV's separable kernel.
+// Vectors are scaled per axis afterwards; the mask is the resized float mask rounded half-even (0.5 -> 0).
+__device__ __forceinline__ void resize_coord(int d, double scale, int n, int& s0, int& s1, float& f) {
+    float fx = (float)((d + 0.5) * scale - 0.5);
+    int sx = (int)floorf(fx);
+    fx -= sx;
+    if (sx < 0) { fx = 0.f; sx = 0; }
+    if (sx >= n - 1) { fx = 0.f; sx = n - 1; }
+    s0 = sx;
+    s1 = min(sx + 1, n - 1);
+    f = fx;
+}
+
+__global__ void __launch_bounds__(256) resize_kernel(const float* __restrict__ vecs, const uint8_t* __restrict__ mask,
+                                                     float* __restrict__ ov, uint8_t* __restrict__ om, int H, int W,
+                                                     int Ho, int Wo, double scale_x, double scale_y, float mul_u,
+                                                     float mul_v) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int n = blockIdx.z;
+    if (x >= Wo || y >= Ho) return;
+    int x0, x1, y0, y1;
+    float fx, fy;
+    resize_coord(x, scale_x, W, x0, x1, fx);
+    resize_coord(y, scale_y, H, y0, y1, fy);
+    const float a0 = 1.f - fx, a1 = fx, b0 = 1.f - fy, b1 = fy;
+    const size_t fb = (size_t)n * H * W, ob = ((size_t)n * Ho + y) * Wo + x;
+    if (ov != nullptr) {
+        const float2* f = reinterpret_cast<const float2*>(vecs) + fb;
+        const float2 s00 = f[(size_t)y0 * W + x0], s01 = f[(size_t)y0 * W + x1], s10 = f[(size_t)y1 * W + x0],
+                     s11 = f[(size_t)y1 * W + x1];
+        const float r0u = __fadd_rn(__fmul_rn(s00.x, a0), __fmul_rn(s01.x, a1));
+        const float r1u = __fadd_rn(__fmul_rn(s10.x, a0), __fmul_rn(s11.x, a1));
+        const float r0v = __fadd_rn(__fmul_rn(s00.y, a0), __fmul_rn(s01.y, a1));
+        const float r1v = __fadd_rn(__fmul_rn(s10.y, a0), __fmul_rn(s11.y, a1));
+        float2 o;
+        o.x = __fmul_rn(__fadd_rn(__fmul_rn(r0u, b0), __fmul_rn(r1u, b1)), mul_u);
+        o.y = __fmul_rn(__fadd_rn(__fmul_rn(r0v, b0), __fmul_rn(r1v, b1)), mul_v);
+        reinterpret_cast<float2*>(ov)[ob] = o;
+    }
+    if (om != nullptr) {
+        const uint8_t* m = mask + fb;
+        const float m00 = m[(size_t)y0 * W + x0], m01 = m[(size_t)y0 * W + x1], m10 = m[(size_t)y1 * W + x0],
+                    m11 = m[(size_t)y1 * W + x1];
+        const float r0 = __fadd_rn(__fmul_rn(m00, a0), __fmul_rn(m01, a1));
+        const float r1 = __fadd_rn(__fmul_rn(m10, a0), __fmul_rn(m11, a1));
+        const float v = __fadd_rn(__fmul_rn(r0, b0), __fmul_rn(r1, b1));
+        om[ob] = rintf(v) == 1.0f ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) greater_kernel(const float* __restrict__ v, float thr, uint8_t* __restrict__ out,
+                                                      size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = v[i] > thr ? 1 : 0;
+}
+
+// Flow vectors at float64 points (row, col) by exact bilinear interpolation with clipped neighbours, float64
+// arithmetic in the reference's operation order (utils.py:161-196); out = pts + (v, u). bad[0] is set when a point
+// lies outside [0,H-1]x[0,W-1] (the reference raises IndexError).
+__global__ void __launch_bounds__(128) track_bilinear_kernel(const float* __restrict__ flow, const double* __restrict__ pts,
+                                                             size_t n, int H, int W, double* __restrict__ out,
+                                                             int* __restrict__ bad) {
+    const float2* f = reinterpret_cast<const float2*>(flow);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double r = pts[i * 2], c = pts[i * 2 + 1];
+        if (!(0 <= r && r <= H - 1) || !(0 <= c && c <= W - 1)) {
+            *bad = 1;
+            out[i * 2] = out[i * 2 + 1] = 0.0;
+            continue;
+        }
+        const int r0 = (int)floor(r), c0 = (int)floor(c);
+        const int r0c = min(max(r0, 0), H - 1), c0c = min(max(c0, 0), W - 1);
+        const int r1c = min(max(r0 + 1, 0), H - 1), c1c = min(max(c0 + 1, 0), W - 1);
+        const double wa = __dmul_rn((double)r1c - r, (double)c1c - c), wb = __dmul_rn((double)r1c - r, c - (double)c0c);
+        const double wc = __dmul_rn(r - (double)r0c, (double)c1c - c), wd = __dmul_rn(r - (double)r0c, c - (double)c0c);
+        const float2 a = f[(size_t)r0c * W + c0c], b = f[(size_t)r1c * W + c0c], cc = f[(size_t)r0c * W + c1c],
+                     d = f[(size_t)r1c * W + c1c];
+        // result = wa*data_a + wb*data_b + wc*data_c + wd*data_d, data in (v, u) order, no FMA contraction
+        const double dv = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(wa, (double)a.y), __dmul_rn(wb, (double)b.y)),
+                                              __dmul_rn(wc, (double)cc.y)), __dmul_rn(wd, (double)d.y));
+        const double du = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(wa, (double)a.x), __dmul_rn(wb, (double)b.x)),
+                                              __dmul_rn(wc, (double)cc.x)), __dmul_rn(wd, (double)d.x));
+        out[i * 2] = __dadd_rn(r, dv);
+        out[i * 2 + 1] = __dadd_rn(c, du);
+    }
+}
+
 __global__ void __launch_bounds__(256) inside_kernel(const double* __restrict__ pts, size_t n, int H, int W,
                                                      uint8_t* __restrict__ out) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -372,6 +461,40 @@ extern "C" int ofk_crop(const void* in, void* out, int elem_bytes, int N, int H,
     if (bx > 8) bx = 8;
     crop_kernel<<<dim3(bx, h, N), 256, 0, as_stream(stream)>>>((const uint8_t*)in, (uint8_t*)out, elem_bytes, H, W, y0,
                                                               x0, h, w);
+    OFK_LAUNCHED();
+    return OFK_OK;
+}
+
+extern "C" int ofk_resize_flow(const float* vecs, const uint8_t* mask, float* out_vecs, uint8_t* out_mask, int N, int H,
+                               int W, int Ho, int Wo, double fy, double fx, ofk_stream_t stream) {
+    OFK_CHECK_ARG((vecs && out_vecs) || (mask && out_mask), "ofk_resize_flow: nothing to do");
+    OFK_CHECK_ARG(N >= 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0 && fx > 0 && fy > 0, "ofk_resize_flow: bad shape / scale");
+    OFK_CHECK_ARG(!out_vecs || ((((uintptr_t)vecs | (uintptr_t)out_vecs) & 7) == 0), "ofk_resize_flow: vecs must be 8-byte aligned");
+    if (N == 0) return OFK_OK;
+    OFK_CHECK_ARG(N <= 65535, "ofk_resize_flow: N too large");
+    dim3 grid((Wo + 31) / 32, (Ho + 7) / 8, N);
+    resize_kernel<<<grid, 256, 0, as_stream(stream)>>>(out_vecs ? vecs : nullptr, out_mask ? mask : nullptr, out_vecs,
+                                                      out_mask, H, W, Ho, Wo, 1.0 / fx, 1.0 / fy, (float)fx, (float)fy);
+    OFK_LAUNCHED();
+    return OFK_OK;
+}
+
+extern "C" int ofk_greater(const float* v, float thr, uint8_t* out, size_t n, ofk_stream_t stream) {
+    OFK_CHECK_ARG(v && out, "ofk_greater: NULL argument");
+    if (n == 0) return OFK_OK;
+    greater_kernel<<<stream_grid(n, 256), 256, 0, as_stream(stream)>>>(v, thr, out, n);
+    OFK_LAUNCHED();
+    return OFK_OK;
+}
+
+extern "C" int ofk_track_bilinear(const float* flow, const double* pts, size_t n, int H, int W, double* out, int* bad,
+                                  ofk_stream_t stream) {
+    OFK_CHECK_ARG(flow && pts && out && bad, "ofk_track_bilinear: NULL argument");
+    OFK_CHECK_ARG(H > 0 && W > 0, "ofk_track_bilinear: bad shape");
+    cudaStream_t st = as_stream(stream);
+    OFK_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), st));
+    if (n == 0) return OFK_OK;
+    track_bilinear_kernel<<<stream_grid(n, 128), 128, 0, st>>>(flow, pts, n, H, W, out, bad);
     OFK_LAUNCHED();
     return OFK_OK;
 }

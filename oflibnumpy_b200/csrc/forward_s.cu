@@ -216,3 +216,160 @@ extern "C" int ofk_forward_s(const float* payload, int C, const float* flow, flo
     OFK_LAUNCHED();
     return OFK_OK;
 }
+
+// ------------------------------------------------------------------------------------------- scattered -> scattered
+// Barycentric interpolation of values attached to the displaced grid at arbitrary query points: replaces the direct
+// `griddata(grid - A, A||mask, grid - B, 'linear', fill_value=0)` of combine_with mode 2 / ref 't'
+// (flow_class.py:1398-1410) and the griddata calls of track_pts (utils.py:603,614). Same mesh as above (cells split
+// along their Delaunay diagonal); the containing triangle of a query is found by a fixed-point walk
+// p <- q - sign*flow(p) towards the source cell followed by an exact containment search around it.
+namespace ofk {
+
+__device__ __forceinline__ P2 mesh_vertex(const float2* __restrict__ fl, int W, int row, int col, float sign,
+                                          int pos_f32) {
+    const float2 f = __ldg(fl + row * W + col);
+    P2 p;
+    if (pos_f32) {  // the reference builds these coordinates in float32 (in-place adds on a float32 array)
+        p.x = static_cast<double>(__fadd_rn(sign * f.x, static_cast<float>(col)));
+        p.y = static_cast<double>(__fadd_rn(sign * f.y, static_cast<float>(row)));
+    } else {
+        p.x = static_cast<double>(col) + static_cast<double>(sign * f.x);
+        p.y = static_cast<double>(row) + static_cast<double>(sign * f.y);
+    }
+    return p;
+}
+
+// tests cell (i, j); on success fills the three vertex indices and barycentric weights
+__device__ bool locate_in_cell(const float2* __restrict__ fl, int H, int W, float sign, int pos_f32, int i, int j,
+                               double qx, double qy, int (&vidx)[3], double (&w)[3]) {
+    if (i < 0 || j < 0 || i >= H - 1 || j >= W - 1) return false;
+    P2 v[4];
+    v[0] = mesh_vertex(fl, W, i, j, sign, pos_f32);
+    v[1] = mesh_vertex(fl, W, i, j + 1, sign, pos_f32);
+    v[2] = mesh_vertex(fl, W, i + 1, j, sign, pos_f32);
+    v[3] = mesh_vertex(fl, W, i + 1, j + 1, sign, pos_f32);
+    const int vid[4] = {i * W + j, i * W + j + 1, (i + 1) * W + j, (i + 1) * W + j + 1};
+    const int diag = choose_diagonal(v[0], v[1], v[2], v[3]);
+    for (int tri = 0; tri < 2; ++tri) {
+        const int c0 = corner_of(diag, tri, 0), c1 = corner_of(diag, tri, 1), c2 = corner_of(diag, tri, 2);
+        const double area2 = orient(v[c0], v[c1], v[c2]);
+        if (area2 == 0.0) continue;
+        const double sgn = area2 > 0 ? 1.0 : -1.0;
+        const double e0 = edge_fn(v[c1], vid[c1], v[c2], vid[c2], qx, qy);
+        const double e1 = edge_fn(v[c2], vid[c2], v[c0], vid[c0], qx, qy);
+        const double e2 = edge_fn(v[c0], vid[c0], v[c1], vid[c1], qx, qy);
+        if (sgn * e0 >= 0.0 && sgn * e1 >= 0.0 && sgn * e2 >= 0.0) {
+            vidx[0] = vid[c0];
+            vidx[1] = vid[c1];
+            vidx[2] = vid[c2];
+            w[0] = e0 / area2;
+            w[1] = e1 / area2;
+            w[2] = 1.0 - w[0] - w[1];
+            return true;
+        }
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(128) mesh_sample_kernel(const float* __restrict__ mesh_flow, float mesh_sign,
+                                                          int pos_f32, const float* __restrict__ payload, int C,
+                                                          const uint8_t* __restrict__ payload_mask,
+                                                          const float* __restrict__ query_flow, float query_sign,
+                                                          const double* __restrict__ query_pts, int Q,
+                                                          float* __restrict__ out, float* __restrict__ out_maskval,
+                                                          uint8_t* __restrict__ found, int H, int W) {
+    const int n = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= Q) return;
+    const size_t fbase = (size_t)n * H * W;
+    const float2* fl = reinterpret_cast<const float2*>(mesh_flow) + fbase;
+    double qx, qy;
+    if (query_pts != nullptr) {  // (row, col) pairs
+        qy = query_pts[((size_t)n * Q + k) * 2];
+        qx = query_pts[((size_t)n * Q + k) * 2 + 1];
+    } else {                     // one query per pixel: p + query_sign * query_flow[p]
+        const int row = k / W, col = k - row * W;
+        const float2 f = __ldg(reinterpret_cast<const float2*>(query_flow) + fbase + k);
+        if (pos_f32) {
+            qx = static_cast<double>(__fadd_rn(query_sign * f.x, static_cast<float>(col)));
+            qy = static_cast<double>(__fadd_rn(query_sign * f.y, static_cast<float>(row)));
+        } else {
+            qx = static_cast<double>(col) + static_cast<double>(query_sign * f.x);
+            qy = static_cast<double>(row) + static_cast<double>(query_sign * f.y);
+        }
+    }
+    // fixed-point walk towards the source position p with p + sign*flow(p) = q (bilinear flow lookup, clamped)
+    double px = qx, py = qy;
+    for (int it = 0; it < 12; ++it) {
+        const double cx = fmin(fmax(px, 0.0), (double)(W - 1)), cy = fmin(fmax(py, 0.0), (double)(H - 1));
+        const int j0 = min((int)cx, W - 2 < 0 ? 0 : W - 2), i0 = min((int)cy, H - 2 < 0 ? 0 : H - 2);
+        const double a = cx - j0, b = cy - i0;
+        const int j1 = min(j0 + 1, W - 1), i1 = min(i0 + 1, H - 1);
+        const float2 f00 = __ldg(fl + i0 * W + j0), f01 = __ldg(fl + i0 * W + j1), f10 = __ldg(fl + i1 * W + j0),
+                     f11 = __ldg(fl + i1 * W + j1);
+        const double u = (1 - b) * ((1 - a) * f00.x + a * f01.x) + b * ((1 - a) * f10.x + a * f11.x);
+        const double v = (1 - b) * ((1 - a) * f00.y + a * f01.y) + b * ((1 - a) * f10.y + a * f11.y);
+        const double nx = qx - mesh_sign * u, ny = qy - mesh_sign * v;
+        const bool done = fabs(nx - px) < 1e-3 && fabs(ny - py) < 1e-3;
+        px = nx;
+        py = ny;
+        if (done) break;
+    }
+    int vidx[3];
+    double w[3];
+    bool hit = false;
+    const int ci = (int)floor(py), cj = (int)floor(px);
+    for (int ring = 0; ring <= 2 && !hit; ++ring) {
+        for (int di = -ring; di <= ring && !hit; ++di)
+            for (int dj = -ring; dj <= ring && !hit; ++dj) {
+                if (max(abs(di), abs(dj)) != ring) continue;
+                hit = locate_in_cell(fl, H, W, mesh_sign, pos_f32, ci + di, cj + dj, qx, qy, vidx, w);
+            }
+    }
+    const size_t o = (size_t)n * Q + k;
+    if (found) found[o] = hit ? 1 : 0;
+    if (!hit) {
+        for (int c = 0; c < C; ++c) out[o * C + c] = 0.f;
+        if (out_maskval) out_maskval[o] = 0.f;
+        return;
+    }
+    const float* pay = payload + fbase * C;
+    for (int c = 0; c < C; ++c) {
+        const double val = w[0] * (double)__ldg(pay + (size_t)vidx[0] * C + c) +
+                           w[1] * (double)__ldg(pay + (size_t)vidx[1] * C + c) +
+                           w[2] * (double)__ldg(pay + (size_t)vidx[2] * C + c);
+        out[o * C + c] = (float)val;
+    }
+    if (out_maskval) {
+        double m = w[0] + w[1] + w[2];
+        if (payload_mask) {
+            const uint8_t* pm = payload_mask + fbase;
+            m = (pm[vidx[0]] ? w[0] : 0.0) + (pm[vidx[1]] ? w[1] : 0.0) + (pm[vidx[2]] ? w[2] : 0.0);
+        }
+        out_maskval[o] = (float)m;
+    }
+}
+
+}  // namespace ofk
+
+extern "C" int ofk_mesh_sample(const float* mesh_flow, float mesh_sign, int pos_f32, const float* payload, int C,
+                               const uint8_t* payload_mask, const float* query_flow, float query_sign,
+                               const double* query_pts, int Q, float* out, float* out_maskval, uint8_t* found, int N,
+                               int H, int W, ofk_stream_t stream) {
+    OFK_CHECK_ARG(mesh_flow != nullptr, "ofk_mesh_sample: mesh_flow is NULL");
+    OFK_CHECK_ARG((query_flow != nullptr) != (query_pts != nullptr),
+                  "ofk_mesh_sample: exactly one of query_flow / query_pts must be given");
+    OFK_CHECK_ARG(N >= 0 && H > 1 && W > 1 && C >= 0, "ofk_mesh_sample: bad shape N=%d H=%d W=%d C=%d", N, H, W, C);
+    OFK_CHECK_ARG(C == 0 || (payload != nullptr && out != nullptr), "ofk_mesh_sample: payload/out NULL");
+    OFK_CHECK_ARG((size_t)H * W < ((size_t)1 << 30), "ofk_mesh_sample: frame too large");
+    if (query_flow != nullptr) Q = H * W;
+    OFK_CHECK_ARG(Q >= 0, "ofk_mesh_sample: negative query count");
+    if (N == 0 || Q == 0) return OFK_OK;
+    OFK_CHECK_ARG(N <= 65535, "ofk_mesh_sample: N too large");
+    dim3 grid((Q + 127) / 128, N);
+    ofk::mesh_sample_kernel<<<grid, 128, 0, ofk::as_stream(stream)>>>(mesh_flow, mesh_sign, pos_f32, payload, C,
+                                                                     payload_mask, query_flow, query_sign, query_pts,
+                                                                     Q, out, out_maskval, found, H, W);
+    OFK_LAUNCHED();
+    return OFK_OK;
+}

@@ -170,21 +170,88 @@ def points_inside_area(pts, shape):
 
 
 # ------------------------------------------------------------------------------------------------- "next" rows
+def _valid_scale(scale):
+    if isinstance(scale, (float, int)):
+        scale = [scale, scale]
+    elif isinstance(scale, (tuple, list)):
+        if len(scale) != 2:
+            raise ValueError("Error resizing flow: Scale {} must have a length of 2".format(type(scale)))
+        if not all(isinstance(item, (float, int)) for item in scale):
+            raise ValueError("Error resizing flow: Scale {} items must be integers or floats".format(type(scale)))
+    else:
+        raise TypeError("Error resizing flow: "
+                        "Scale must be an integer, float, or list or tuple of integers or floats")
+    if any(s <= 0 for s in scale):
+        raise ValueError("Error resizing flow: Scale values must be larger than 0")
+    return scale
+
+
 def _resize_device(vecs, mask, scale):
-    raise NotImplementedError("Flow.resize / resize_flow: not built yet (SURVEY section 8f-2, after the hot path)")
+    scale = _valid_scale(scale)
+    return _ops.resize_flow(vecs, mask, scale[0], scale[1])
 
 
 def resize_flow(flow, scale):
-    raise NotImplementedError("resize_flow: not built yet (SURVEY section 8f-2, after the hot path)")
+    """Resize a flow field array, scaling the vector values accordingly (utils.py:493-524)."""
+    flow = validate_flow_array(flow, "Error resizing flow: ")
+    scale = _valid_scale(scale)
+    out, _ = _ops.resize_flow(DeviceArray.from_numpy(flow[None]), None, scale[0], scale[1])
+    return out.numpy()[0]
 
 
 def _track_device(flow, pts, int_out, s_exact_mode):
-    raise NotImplementedError("Flow.track / track_pts: not built yet (SURVEY section 8f-1, after the hot path)")
+    """Point tracking (utils.py:547-622) on the device. `flow` is a Flow object."""
+    if not isinstance(pts, np.ndarray):
+        raise TypeError("Error tracking points: Pts needs to be a numpy array")
+    if pts.ndim != 2:
+        raise ValueError("Error tracking points: Pts needs to have shape N-2")
+    if pts.shape[1] != 2:
+        raise ValueError("Error tracking points: Pts needs to have shape N-2")
+    int_out = False if int_out is None else int_out
+    s_exact_mode = False if s_exact_mode is None else s_exact_mode
+    if not isinstance(int_out, bool):
+        raise TypeError("Error tracking points: Int_out needs to be a boolean")
+    if not isinstance(s_exact_mode, bool):
+        raise TypeError("Error tracking points: S_exact_mode needs to be a boolean")
+    vecs = flow._vd()
+    if int(_ops.nonzero_flags(vecs, None, DEFAULT_THRESHOLD)[0]) == 0:      # thresholded-zero flow: points unchanged
+        warped = pts
+    else:
+        if flow.ref == 's' and np.issubdtype(pts.dtype, np.integer):
+            # direct lookup of the vectors at integer positions: a gather through the same mesh sampler would be
+            # overkill; the points are few, so index a (lazy) host view like the reference does
+            d = vecs.numpy()[0][pts[:, 0], pts[:, 1], ::-1]
+            warped = pts + d
+        elif flow.ref == 's' and not np.issubdtype(pts.dtype, np.floating):
+            raise TypeError("Error tracking points: Pts numpy array needs to have a float or int dtype")
+        elif flow.ref == 's' and not s_exact_mode:
+            warped, outside = _ops.track_bilinear(vecs, pts)
+            if outside:
+                raise IndexError("Some points are outside of the data area.")
+        else:
+            # 's' exact mode: interpolate the flow on the undisplaced grid; 't': on the grid displaced by -flow
+            zero = DeviceArray.zeros(vecs.shape, np.float32) if flow.ref == 's' else None
+            mesh = zero if flow.ref == 's' else vecs
+            q = DeviceArray.from_numpy(np.ascontiguousarray(pts, dtype=np.float64)[None])
+            vals, _, found = _ops.mesh_sample(mesh, -1.0, vecs, None, query_pts=q, want_mask=False, want_found=True)
+            d = vals.numpy()[0].astype(np.float64)[:, ::-1]
+            warped = pts + d
+            warped[found.numpy()[0] == 0] = 0                               # NaN rows of griddata -> 0 (utils.py:616-618)
+    if int_out:
+        warped = np.round(warped).astype('i')
+    return warped
 
 
 def track_pts(flow, ref, pts, int_out=None, s_exact_mode=None):
-    raise NotImplementedError("track_pts: not built yet (SURVEY section 8f-1, after the hot path)")
+    """Warp points (N,2) given as (row, col) with a flow field (utils.py:547-622)."""
+    flow = validate_flow_array(flow, "Error tracking points: ")
+    return _track_device(Flow(flow, ref), pts, int_out, s_exact_mode)
 
 
 def _combine2_t_device(a, b):
-    raise NotImplementedError("combine_with(mode=2) for ref 't': scattered-to-scattered resampling not built yet")
+    """combine_with(mode=2) for ref 't' (flow_class.py:1398-1410): A, resampled from its source positions
+    grid - A to the source positions grid - B of B, is subtracted from B."""
+    vals, mval, _ = _ops.mesh_sample(a._vd(), -1.0, a._vd(), a._md(), query_flow=b._vd(), query_sign=-1.0,
+                                     pos_f32=True)
+    resampled = Flow._wrap(vals, 't', _ops.greater(mval, 0.99))
+    return b - resampled
