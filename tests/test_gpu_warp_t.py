@@ -166,10 +166,13 @@ def test_combine_mode3_golden(of):
 
 
 def test_combine_mode3_shapes_vs_oracle(of):
+    """Widths that are multiples of 16 take the TMA-staged kernel (box fits: small flows; box does not fit: large
+    flows, CTA-uniform fallback), other widths the plain gather kernel; all against the oracle."""
     rng = np.random.default_rng(13)
-    for (h, w) in ((40, 64), (41, 67), (2, 4), (1, 1), (96, 160)):
-        a = (rng.random((h, w, 2)).astype(np.float32) - np.float32(0.5)) * np.float32(10)
-        b = (rng.random((h, w, 2)).astype(np.float32) - np.float32(0.5)) * np.float32(10)
+    for (h, w, amp) in ((40, 64, 10), (41, 67, 10), (2, 4, 10), (1, 1, 10), (96, 160, 10), (96, 160, 60), (64, 48, 3),
+                        (33, 16, 200), (70, 130, 25)):
+        a = (rng.random((h, w, 2)).astype(np.float32) - np.float32(0.5)) * np.float32(amp)
+        b = (rng.random((h, w, 2)).astype(np.float32) - np.float32(0.5)) * np.float32(amp)
         am, bm = rng.random((h, w)) > 0.1, rng.random((h, w)) > 0.1
         for r in ('t', 's'):
             got = of.Flow(a, r, am).combine_with(of.Flow(b, r, bm), 3)
