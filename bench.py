@@ -156,6 +156,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--gather', action='store_true', help='also time the optional NCCL gather of the outputs')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3
@@ -249,10 +250,20 @@ def main():
     comb_ms = float(np.mean([e[1].elapsed_ms(e[2]) for e in ev]))
 
     if dist is not None:
+        from oflibnumpy_b200 import dist as ofd
+        total_ms, warp_ms, comb_ms = ofd.max_over_ranks([total_ms, warp_ms, comb_ms])
+    gather_ms = None
+    if args.gather and dist is not None:
+        # optional: collect the combined flows of all ranks on rank 0 over NCCL / NVLink (outside the headline timing)
         import torch
-        t = torch.tensor([total_ms, warp_ms, comb_ms], device='cuda', dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, warp_ms, comb_ms = (float(x) for x in t.tolist())
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        full = ofd.gather_frames(out_vecs, world * B, dst=0)
+        g1.record()
+        torch.cuda.synchronize()
+        gather_ms = ofd.max_over_ranks([g0.elapsed_time(g1)])[0]
+        del full
     ms_per_step = total_ms / args.steps
     px_step = world * B * H * W
     value = px_step / (ms_per_step * 1e-3) / 1e6
@@ -290,10 +301,7 @@ def main():
         barrier()
         dt = (time.perf_counter() - t0) / args.e2e_steps
         if dist is not None:
-            import torch
-            t = torch.tensor([dt], device='cuda', dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+            dt = ofd.max_over_ranks([dt])[0]
         px = EB * H * W
         h2d = px * (8 + 1 + 3) + px * (8 + 8 + 1 + 1)     # call 1: flow, flow mask, image; call 2: A, B, masks
         d2h = px * (3 + 1) + px * (8 + 1) + EB * 8
@@ -322,14 +330,14 @@ def main():
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get('combine3_vec4_bytes_per_px')
+            traffic = json.load(open(tpath)).get('combine3_rows_dram_bytes_per_px')
             traffic = traffic * px_rank if traffic else None
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "combine3_vec4<ref t>", "achieved": comb_gbs, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "combine3_rows<ref t, masks>", "achieved": comb_gbs, "peak": peak,
                 "unit": "GB/s", "frac": comb_gbs / peak, "traffic": traffic, "peak_source": peak_src,
                 "bytes_per_px": BYTES_COMBINE, "ms_per_launch": comb_ms,
-                "other_kernels": {"warp_t_vec4<u8,3,rint>": {"achieved": warp_gbs, "frac": warp_gbs / peak,
+                "other_kernels": {"warp_t_u8x3<half_even>": {"achieved": warp_gbs, "frac": warp_gbs / peak,
                                                             "bytes_per_px": BYTES_WARP, "ms_per_launch": warp_ms}},
                 "frac_of_nominal_8TBs": comb_gbs / 8000.0}
     cpu = None
@@ -351,6 +359,9 @@ def main():
                        "l2": "inputs (%.1f GB per GPU) exceed L2; no flush needed" %
                              (px_rank * (8 + 8 + 1 + 1 + 3) / 1e9)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+    if gather_ms is not None:
+        line["gather"] = {"ms": gather_ms, "bytes": world * px_rank * 8, "what": "combined flows of all ranks -> rank 0 "
+                          "(isend/irecv over NCCL), outside the timed region"}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

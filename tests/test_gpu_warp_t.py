@@ -379,3 +379,42 @@ def test_full_size_digests(of):
     w, m = acc.apply(gi.cfg5_image(), return_valid_area=True)
     assert sha(acc.vecs) == dg['cfg5_chain_vecs'] and sha(acc.mask) == dg['cfg5_chain_mask']
     assert sha(w) == dg['cfg5_chain_img'] and sha(m) == dg['cfg5_chain_valid']
+
+
+def test_tma_pipelined_variant_parity():
+    """The opt-in TMA-pipelined composition kernel (OFK_TMA=1, read once per process) against the oracle."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import oflibnumpy_b200 as of
+from oracle import flowref as R
+rng = np.random.default_rng(21)
+for (h, w, amp) in ((40, 64, 10), (96, 160, 10), (96, 160, 60), (64, 48, 3), (33, 16, 200), (70, 128, 25), (130, 96, 6)):
+    a = (rng.random((h, w, 2)).astype(np.float32) - np.float32(0.5)) * np.float32(amp)
+    b = (rng.random((h, w, 2)).astype(np.float32) - np.float32(0.5)) * np.float32(amp)
+    am, bm = rng.random((h, w)) > 0.1, rng.random((h, w)) > 0.1
+    for r in ('t', 's'):
+        got = of.Flow(a, r, am).combine_with(of.Flow(b, r, bm), 3)
+        want = R.combine(R.make(a, r, am), R.make(b, r, bm), 3)
+        assert np.array_equal(got.mask, want.mask), (h, w, amp, r)
+        assert np.array_equal(got.vecs, want.vecs), (h, w, amp, r)
+        got = of.combine_flows(a, b, 3, r)
+        assert np.array_equal(got, R.combine(R.make(a, r), R.make(b, r), 3).vecs), (h, w, amp, r, 'nomask')
+n = 6
+a = (rng.random((n, 64, 96, 2)).astype(np.float32) - np.float32(0.5)) * np.float32(8)
+b = (rng.random((n, 64, 96, 2)).astype(np.float32) - np.float32(0.5)) * np.float32(8)
+am, bm = rng.random((n, 64, 96)) > 0.05, rng.random((n, 64, 96)) > 0.05
+a[1] = 0
+b[2][bm[2]] = 0
+v, m = of.FlowBatch(a, 't', am).combine_with(of.FlowBatch(b, 't', bm), 3).numpy()
+for i in range(n):
+    want = R.combine(R.make(a[i], 't', am[i]), R.make(b[i], 't', bm[i]), 3)
+    assert np.array_equal(m[i], want.mask) and np.array_equal(v[i], want.vecs), i
+print("tma parity ok")
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OFK_TMA='1')
+    res = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert 'tma parity ok' in res.stdout

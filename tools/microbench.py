@@ -29,3 +29,9 @@ timeit('d2d copy flows (16 B/px)', lambda: _lib.call('ofk_rt_memcpy_d2d', o.ptr,
 timeit('valid_geom_t (10 B/px)', lambda: _lib.call('ofk_valid_geom_t', a.ptr, -1.0, am.ptr, om.ptr, N, H, W, st.handle), 10)
 flags = DeviceArray.empty((N, 2), np.int32)
 timeit('combine3 zero flows (27)', lambda: _lib.call('ofk_combine3', a.ptr, am.ptr, b.ptr, bm.ptr, ord('t'), 0.0, o.ptr, om.ptr, None, N, H, W, st.handle), 27)
+timeit('combine3 no masks zero (25)', lambda: _lib.call('ofk_combine3', a.ptr, None, b.ptr, None, ord('t'), 0.0, o.ptr, om.ptr, None, N, H, W, st.handle), 25)
+img = DeviceArray.zeros((N, H, W, 3), np.uint8); oimg = DeviceArray.empty((N, H, W, 3), np.uint8)
+timeit('warp u8x3 rint+valid (16)', lambda: _lib.call('ofk_warp_t', img.ptr, _lib.U8, 3, _lib.ARITH_RINT, a.ptr, -1.0, None, am.ptr, oimg.ptr, om.ptr, _lib.RULE_GT_HALF, N, H, W, H, W, 0, 0, 1, st.handle), 16)
+timeit('warp u8x3 fixed novalid (14)', lambda: _lib.call('ofk_warp_t', img.ptr, _lib.U8, 3, _lib.ARITH_NATIVE, a.ptr, -1.0, None, None, oimg.ptr, None, _lib.RULE_STRICT, N, H, W, H, W, 0, 0, 1, st.handle), 14)
+timeit('warp flow f32x2 + masks (27)', lambda: _lib.call('ofk_warp_t', b.ptr, _lib.F32, 2, _lib.ARITH_NATIVE, a.ptr, -1.0, bm.ptr, am.ptr, o.ptr, om.ptr, _lib.RULE_STRICT, N, H, W, H, W, 0, 0, 1, st.handle), 27)
+timeit('from_matrix (8)', lambda: _ops.from_matrix(np.tile(np.eye(3)[None], (N, 1, 1)), (H, W), -1.0), 8, reps=3)
