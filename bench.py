@@ -256,6 +256,8 @@ def main():
     if args.gather and dist is not None:
         # optional: collect the combined flows of all ranks on rank 0 over NCCL / NVLink (outside the headline timing)
         import torch
+        full = ofd.gather_frames(out_vecs, world * B, dst=0)      # warm-up: NCCL connects lazily
+        del full
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()

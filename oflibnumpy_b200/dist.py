@@ -55,16 +55,17 @@ def gather_frames(local, total_frames, dst=0):
     out = None
     if rank == dst:
         out = torch.empty((total_frames,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-    # point-to-point sends keep ragged shards simple and let the copies overlap each other on the NVSwitch
-    reqs = []
+    # point-to-point copies keep ragged shards simple; batched so NCCL runs them as one group over the NVSwitch
+    ops = []
     if rank == dst:
         for r, (a, b) in enumerate(sizes):
             if r == dst:
                 out[a:b].copy_(t)
             elif b > a:
-                reqs.append(dist.irecv(out[a:b], src=r))
+                ops.append(dist.P2POp(dist.irecv, out[a:b], r))
     elif t.shape[0] > 0:
-        reqs.append(dist.isend(t.contiguous(), dst=dst))
-    for q in reqs:
-        q.wait()
+        ops.append(dist.P2POp(dist.isend, t.contiguous(), dst))
+    if ops:
+        for q in dist.batch_isend_irecv(ops):
+            q.wait()
     return out
