@@ -336,7 +336,7 @@ def main():
             traffic = traffic * px_rank if traffic else None
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "combine3_rows<ref t, masks>", "achieved": comb_gbs, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "c3_ws_kernel<masks> (ofk_combine3, ref t)", "achieved": comb_gbs, "peak": peak,
                 "unit": "GB/s", "frac": comb_gbs / peak, "traffic": traffic, "peak_source": peak_src,
                 "bytes_per_px": BYTES_COMBINE, "ms_per_launch": comb_ms,
                 "other_kernels": {"warp_t_u8x3<half_even>": {"achieved": warp_gbs, "frac": warp_gbs / peak,

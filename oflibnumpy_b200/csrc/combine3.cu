@@ -322,10 +322,12 @@ __global__ void __launch_bounds__(256) combine3_fixup(const float* __restrict__ 
 
 }  // namespace ofk
 
-namespace ofk {
-int launch_combine3_tma(const float* A, const uint8_t* Am, const float* B, const uint8_t* Bm, int ref, float thr,
-                        float* out, uint8_t* out_mask, int* flags, int N, int H, int W, cudaStream_t st);
-bool tma_enabled();
+namespace ofk {   // combine3_ws.cu
+int launch_combine3_ws(const float* P, const uint8_t* Pm, const float* G, const uint8_t* Gm, float sign, float* out,
+                       uint8_t* omask, int N, int H, int W, cudaStream_t st);
+int launch_c3_zero_flags(const float* A, const uint8_t* Am, const float* B, const uint8_t* Bm, float thr, int* flags,
+                         int N, int H, int W, cudaStream_t st);
+bool c3_ws_enabled();
 }
 
 using namespace ofk;
@@ -341,16 +343,25 @@ extern "C" int ofk_combine3(const float* A, const uint8_t* Am, const float* B, c
     OFK_CHECK_ARG(N <= 65535, "ofk_combine3: N=%d exceeds 65535 frames per call", N);
     OFK_CHECK_ARG((double)N * ((H + 31) / 32) * ((W + 31) / 32) < 2.0e9, "ofk_combine3: too many tiles");
     cudaStream_t st = as_stream(stream);
-    if (flags != nullptr) OFK_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 2 * (size_t)N, st));
     const bool fast = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) |
                         reinterpret_cast<uintptr_t>(out)) & 7) == 0 && (size_t)H * W < ((size_t)1 << 30) && H < 32768 &&
                       W < 32768 && ((Am == nullptr) == (Bm == nullptr));
-    int tma = 0;
-    if (fast && tma_enabled()) {
-        tma = launch_combine3_tma(A, Am, B, Bm, ref, thr, out, out_mask, flags, N, H, W, st);
-        if (tma < 0) return tma;
+    // default: the warp-specialised TMA kernel (16-byte aligned frames, W % 16 == 0); its zero tests are separate
+    // launches. Everything else: the register-pipelined gather kernel, which tests for zero on the fly.
+    int ws = 0;
+    if (fast && c3_ws_enabled() && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) |
+                                     reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(out_mask) |
+                                     reinterpret_cast<uintptr_t>(Am) | reinterpret_cast<uintptr_t>(Bm)) & 15) == 0) {
+        if (ref == 't') ws = launch_combine3_ws(B, Bm, A, Am, -1.0f, out, out_mask, N, H, W, st);
+        else ws = launch_combine3_ws(A, Am, B, Bm, 1.0f, out, out_mask, N, H, W, st);
+        if (ws < 0) return ws;
+        if (ws == 1 && flags != nullptr) {
+            const int rc = launch_c3_zero_flags(A, Am, B, Bm, thr, flags, N, H, W, st);
+            if (rc != OFK_OK) return rc;
+        }
     }
-    if (tma == 1) {
+    if (ws != 1 && flags != nullptr) OFK_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 2 * (size_t)N, st));
+    if (ws == 1) {
         // launched
     } else if (fast) {
         static int variant = -1;
@@ -390,7 +401,7 @@ extern "C" int ofk_combine3(const float* A, const uint8_t* Am, const float* B, c
         if (ref == 't') combine3_scalar<true><<<grid, 256, 0, st>>>(A, Am, B, Bm, thr, out, out_mask, flags, H, W);
         else combine3_scalar<false><<<grid, 256, 0, st>>>(A, Am, B, Bm, thr, out, out_mask, flags, H, W);
     }
-    if (tma != 1) OFK_LAUNCHED();
+    if (ws != 1) OFK_LAUNCHED();
     if (flags != nullptr) {
         const size_t frame = (size_t)H * W;
         int bx = (int)((frame + 256 * 8 - 1) / (256 * 8));

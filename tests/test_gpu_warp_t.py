@@ -181,6 +181,39 @@ def test_combine_mode3_shapes_vs_oracle(of):
             same(got.vecs, want.vecs)
 
 
+def test_zero_test_probe_and_scan(of):
+    """The zero tests of the TMA composition path: a sparse probe decides almost every frame, a full scan the rest.
+    Frames that are zero except on pixels the probe does not visit must still count as non-zero; frames that are
+    non-zero only on invalid pixels must count as zero (the reference tests vecs[mask])."""
+    rng = np.random.default_rng(15)
+    n, h, w = 6, 64, 96                                     # 6144 px per frame: the probe looks at every 3rd pixel
+    a = np.zeros((n, h, w, 2), np.float32)
+    b = (rng.random((n, h, w, 2)).astype(np.float32) - np.float32(0.5)) * np.float32(6)
+    am, bm = rng.random((n, h, w)) > 0.05, rng.random((n, h, w)) > 0.05
+    a[0].reshape(-1, 2)[1] = (0.5, 0)                        # frame 0: one non-zero vector on an unprobed pixel
+    am[0].reshape(-1)[1] = True
+    a[1].reshape(-1, 2)[4] = (0, -2)                         # frame 1: the only non-zero vector is invalid -> zero
+    am[1].reshape(-1)[4] = False
+    a[2].reshape(-1, 2)[-1] = (1e-4, 0)                      # frame 2: last pixel, below the threshold
+    am[2].reshape(-1)[-1] = True
+    a[3] = (rng.random((h, w, 2)).astype(np.float32) - np.float32(0.5)) * np.float32(6)
+    b[4] = 0                                                 # frame 4: B zero, A zero -> B returned
+    a[5].reshape(-1, 2)[5000] = (3, 3)
+    am[5].reshape(-1)[5000] = True
+    for thr, expect_a in ((False, [1, 0, 1, 1, 0, 1]), (True, [1, 0, 0, 1, 0, 1])):
+        for r in ('t', 's'):
+            res, flags = of.FlowBatch(a, r, am).combine_with(of.FlowBatch(b, r, bm), 3, thresholded=thr,
+                                                              return_flags=True)
+            fl = flags.numpy()
+            assert fl[:, 0].tolist() == expect_a, (thr, r, fl.tolist())
+            assert fl[:, 1].tolist() == [1, 1, 1, 1, 0, 1], (thr, r, fl.tolist())
+            v, m = res.numpy()
+            for i in range(n):
+                want = R.combine(R.make(a[i], r, am[i]), R.make(b[i], r, bm[i]), 3, thresholded=thr)
+                same(m[i], want.mask)
+                same(v[i], want.vecs)
+
+
 def test_batched_equals_per_frame(of):
     """FlowBatch (one launch for N frames, device-side early exits) == N single-frame calls == oracle."""
     rng = np.random.default_rng(14)
@@ -381,8 +414,9 @@ def test_full_size_digests(of):
     assert sha(w) == dg['cfg5_chain_img'] and sha(m) == dg['cfg5_chain_valid']
 
 
-def test_tma_pipelined_variant_parity():
-    """The opt-in TMA-pipelined composition kernel (OFK_TMA=1, read once per process) against the oracle."""
+def test_gather_kernel_fallback_parity():
+    """The register-pipelined gather kernel behind ofk_combine3 (what runs for widths that are not multiples of 16)
+    forced for every shape with OFK_C3_WS=0 (read once per process), against the oracle."""
     import subprocess
     import sys
     code = r'''
@@ -412,9 +446,9 @@ v, m = of.FlowBatch(a, 't', am).combine_with(of.FlowBatch(b, 't', bm), 3).numpy(
 for i in range(n):
     want = R.combine(R.make(a[i], 't', am[i]), R.make(b[i], 't', bm[i]), 3)
     assert np.array_equal(m[i], want.mask) and np.array_equal(v[i], want.vecs), i
-print("tma parity ok")
+print("fallback parity ok")
 ''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, OFK_TMA='1')
+    env = dict(os.environ, OFK_C3_WS='0')
     res = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout + res.stderr
-    assert 'tma parity ok' in res.stdout
+    assert 'fallback parity ok' in res.stdout
