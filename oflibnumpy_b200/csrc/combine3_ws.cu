@@ -21,13 +21,13 @@
 // The zero tests gating the reference's early exits (flow_class.py:1338-1354) are not part of the hot loop: a probe
 // kernel looks at a sparse sample of every operand (almost always enough to prove "not zero"), a scan kernel reads the
 // operands completely only for frames the probe could not decide, and combine3_fixup (combine3.cu) applies the exits.
-#include <cuda.h>
 #include <stdlib.h>
 
-#include "ofk_common.cuh"
+#include "ws_common.cuh"
 
 namespace ofk {
 namespace c3ws {
+using namespace ws;
 
 constexpr int TS = 32;
 constexpr int BW = 48, BH = 48;   // vector box (pixels)
@@ -53,39 +53,6 @@ struct Smem {
 struct Maps {
     CUtensorMap p, pm, gb, gmb, ov, om;
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// arrive once `dep` has been computed: ties the release of a buffer to the registers loaded from it
-__device__ __forceinline__ void mbar_arrive_after(uint64_t* bar, unsigned dep) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];  // after %1" ::"r"(smem_u32(bar)), "r"(dep) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(phase)
-            : "memory");
-    }
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
 
 // packed f32x2 arithmetic (sm_100): both halves are IEEE round-to-nearest, no contraction
 __device__ __forceinline__ uint64_t pack2(float lo, float hi) {
@@ -152,43 +119,6 @@ __device__ __noinline__ float4 slow_sample(const float2* __restrict__ G, const u
     r.w = 0.f;
     return r;
 }
-
-// Linear tile index -> (frame, tile row, tile column), advanced by the grid stride without divisions.
-struct TileIter {
-    int n, ty, tx, dn, dy, dx;
-    __device__ __forceinline__ void init(unsigned t, unsigned stride, int tiles_x, int tiles_y) {
-        const unsigned per_frame = (unsigned)tiles_x * tiles_y;
-        n = t / per_frame;
-        unsigned r = t - n * per_frame;
-        ty = r / tiles_x;
-        tx = r - ty * tiles_x;
-        dn = stride / per_frame;
-        r = stride - dn * per_frame;
-        dy = r / tiles_x;
-        dx = r - dy * tiles_x;
-    }
-    __device__ __forceinline__ void advance(int tiles_x, int tiles_y) {
-        tx += dx;
-        if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
-        ty += dy;
-        if (ty >= tiles_y) { ty -= tiles_y; ++n; }
-        n += dn;
-    }
-};
-
-// bulk tensor store shared -> global (clipped at the tensor bounds), tracked by the issuing thread's bulk groups
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
-                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() {
-    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <bool MASKS, int NP, int NB, int LA>
 __global__ void __launch_bounds__((NCW + 1) * 32) c3_ws_kernel(const __grid_constant__ Maps maps,
@@ -291,7 +221,6 @@ __global__ void __launch_bounds__((NCW + 1) * 32) c3_ws_kernel(const __grid_cons
 
     // ---------------------------------------------------------------------------------------------- consumer warps
     const uint64_t one2 = pack2(1.0f, 1.0f);
-    const float lim = 60000.f;
     unsigned s = 0, s_ph = 0, b = 0, b_ph = 0;
     int prev_s = -1;
     for (unsigned i = 0; i < T; ++i) {
@@ -320,9 +249,10 @@ __global__ void __launch_bounds__((NCW + 1) * 32) c3_ws_kernel(const __grid_cons
             quant(Y, iy, fb[j]);
             dx[j] = ix - info.x;
             dy[j] = iy - info.z;
-            // covered by the box and inside the range of the fast quantiser; everything else is decided per pixel
-            ok = ok && (unsigned)dx[j] < (unsigned)(BW - 1) && (unsigned)dy[j] < (unsigned)(BH - 1) &&
-                 fabsf(X) < lim && fabsf(Y) < lim;
+            // Covered by the box? Everything else is decided per pixel. No range test is needed for the fast quantiser:
+            // it is exact for |X| < 2^17, and beyond that (or for NaN / Inf) the integer it produces is far outside
+            // [-2^16, 2^16], so such a pixel can never pass the box test (frames are smaller than 32768).
+            ok = ok && (unsigned)dx[j] < (unsigned)(BW - 1) && (unsigned)dy[j] < (unsigned)(BH - 1);
         }
         if (__all_sync(0xffffffffu, ok)) {
             uint64_t t[4][4];
@@ -374,8 +304,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32) c3_ws_kernel(const __grid_cons
             for (int j = 0; j < 4; ++j) {
                 const float2 pv = unpack2(p[j]);
                 const float X = __fmaf_rn(sign, pv.x, xg), Y = __fmaf_rn(sign, pv.y, (float)(ty0 + (int)wrp * 4 + j));
-                const bool inbox = (unsigned)dx[j] < (unsigned)(BW - 1) && (unsigned)dy[j] < (unsigned)(BH - 1) &&
-                                   fabsf(X) < lim && fabsf(Y) < lim;
+                const bool inbox = (unsigned)dx[j] < (unsigned)(BW - 1) && (unsigned)dy[j] < (unsigned)(BH - 1);
                 float su, sv;
                 unsigned strict;
                 if (inbox) {
@@ -485,40 +414,6 @@ __global__ void __launch_bounds__(256) c3_scan_nonzero(const float2* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-        else
-            cudaGetLastError();
-    }
-    return fn;
-}
-// rank-3 map over [N][H][row_elems] of esize-byte elements, box [1][box_h][box_w]
-static bool make_map3(CUtensorMap* map, const void* base, int esize, size_t row_elems, size_t H, size_t N, int box_w,
-                      int box_h) {
-    EncodeTiledFn fn = encode_fn();
-    if (fn == nullptr) return false;
-    CUtensorMapDataType dt = esize == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
-    cuuint64_t dims[3] = {row_elems, H, N};
-    cuuint64_t strides[2] = {row_elems * esize, row_elems * esize * H};
-    cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    if ((reinterpret_cast<uintptr_t>(base) & 15) || (strides[0] & 15) || (strides[1] & 15)) return false;
-    return fn(map, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 constexpr int WS_NP = 6, WS_NB = 2, WS_LA = 3;   // measured best on B200 (profiles/): 6 P stages, 2 boxes, P 3 tiles ahead
 
 }  // namespace c3ws

@@ -9,6 +9,7 @@
 //                  blend runs on packed bytes (dp4a), rounding is integer, 96-byte rows are stored as 24 words.
 //   warp_t_generic 1 pixel per thread, any channel count / dtype / padding offsets / unaligned pointers.
 #include "ofk_common.cuh"
+#include "warp_t_device.cuh"
 
 namespace ofk {
 
@@ -303,38 +304,6 @@ __device__ __forceinline__ void window6(const uint8_t* __restrict__ pa, int off,
     hi = __funnelshift_r(w1, w2, t);
 }
 
-// Pixels whose taps touch the border (or whose coordinates leave the fast-quantisation range): exact but slow, out
-// of line, by-value in / out (no stack traffic). Returns the 3 result bytes in bits 0..23 and the validity in bit 24.
-__device__ __noinline__ uint32_t border_px_u8x3(const uint8_t* __restrict__ p, const uint8_t* __restrict__ pm, float X,
-                                                float Y, int H, int W, int half_even, int rule) {
-    const QCoord qx = quantise(X), qy = quantise(Y);
-    const int ix = qx.i, iy = qy.i;
-    const QWeights w = qweights(qx.f, qy.f);
-    const bool in[4] = {(unsigned)ix < (unsigned)W && (unsigned)iy < (unsigned)H,
-                        (unsigned)(ix + 1) < (unsigned)W && (unsigned)iy < (unsigned)H,
-                        (unsigned)ix < (unsigned)W && (unsigned)(iy + 1) < (unsigned)H,
-                        (unsigned)(ix + 1) < (unsigned)W && (unsigned)(iy + 1) < (unsigned)H};
-    const long long o = (long long)iy * W + ix;
-    const long long off[4] = {o, o + 1, o + W, o + W + 1};
-    const int wi[4] = {w.w00, w.w01, w.w10, w.w11};
-    int acc[3] = {0, 0, 0}, S = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (!in[k]) continue;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) acc[c] += (int)p[off[k] * 3 + c] * wi[k];
-        if (pm == nullptr || pm[off[k]]) S += wi[k];
-    }
-    uint32_t v = 0;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const int a = acc[c];
-        const uint32_t r = half_even ? (uint32_t)(a + 511 + ((a >> 10) & 1)) >> 10 : (uint32_t)(a + 512) >> 10;
-        v |= r << (8 * c);
-    }
-    return v | (mask_rule_pass(S, rule) ? (1u << 24) : 0u);
-}
-
 // bytes [b0..b5] at byte offset `off` from the 4-byte aligned base pa (the two horizontal taps of a row):
 // lo = b0..b3, hi = b4,b5 (upper half undefined). Three aligned 32-bit loads off one address, two funnel shifts.
 __device__ __forceinline__ void window6(const uint8_t* __restrict__ pa, unsigned off, uint32_t& lo, uint32_t& hi) {
@@ -494,6 +463,11 @@ static int launch_generic(const void* payload, int C, const float* flow, float s
     return OFK_OK;
 }
 
+// warp_t_ws.cu
+int launch_warp_u8x3_ws(bool half_even, const void* payload, const float* flow, float sign, const uint8_t* pmask,
+                        const uint8_t* fmask, void* out, uint8_t* omask, int rule, int N, int H, int W, cudaStream_t st);
+bool warp_ws_enabled();
+
 }  // namespace ofk
 
 using namespace ofk;
@@ -536,6 +510,11 @@ extern "C" int ofk_warp_t(const void* payload, int dtype, int C, int arith, cons
 #define OFK_ROWS(T, CC, AR) \
     return launch_rows<T, CC, AR>(payload, flow, flow_sign, payload_mask, flow_mask, out, out_mask, mask_rule, N, H, W, st)
         if (C == 0) OFK_ROWS(uint8_t, 0, AR_U8_FIXED);
+        if (dtype == OFK_U8 && C == 3 && warp_ws_enabled()) {
+            const int ws = launch_warp_u8x3_ws(ar == AR_RINT, payload, flow, flow_sign, payload_mask, flow_mask, out,
+                                               out_mask, mask_rule, N, H, W, st);
+            if (ws != 0) return ws < 0 ? ws : OFK_OK;
+        }
         if (dtype == OFK_U8 && C == 3)
             return launch_u8x3(ar == AR_RINT, payload, flow, flow_sign, payload_mask, flow_mask, out, out_mask,
                                mask_rule, N, H, W, st);

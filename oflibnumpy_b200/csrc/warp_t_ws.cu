@@ -1,0 +1,420 @@
+// Target-referenced (backward) warp of uint8 x3 images for sm_100a: warp-specialised, TMA-staged kernel (the default
+// path of ofk_warp_t for images). Replaces cv2.remap at utils.py:236 of the reference plus the mask plumbing of
+// Flow.apply (flow_class.py:631-680).
+//
+// Same pipeline as combine3_ws.cu: CTA = 1 producer warp + 8 consumer warps, persistent over 32x32 output tiles.
+//   producer : TMA-loads the flow tile (and the flow-mask tile) ahead of time, estimates the bounding box of the
+//              tile's sample positions from the tile perimeter and TMA-loads that box of the image -- as rows of
+//              3*W bytes, 160 bytes x 48 rows, start aligned down to 16 bytes -- and, if a target mask is resampled, the
+//              matching box of the mask. Hardware zero fill outside the frame == cv2.remap's BORDER_CONSTANT(0).
+//   consumers: both horizontal taps of a row (6 bytes at an arbitrary byte offset) come out of three aligned shared-
+//              memory words; the blend is pure integer (cv2.remap's uint8 fixed-point path and its int16 path are both
+//              exact integers for 8-bit taps, see warp_t.cu): two 16-bit x 8-bit dot products (dp2a) per channel against
+//              the packed weights {(32-a)(32-b), a(32-b)} and {(32-a)b, ab}. The three result bytes and the validity
+//              byte are written over the flow tile in place; the warp's four rows leave through TMA stores (clipped at
+//              the frame border by the hardware).
+// Pixels whose taps are not covered by the box take the exact global-memory path of warp_t.cu individually.
+// HBM traffic is the algorithmic 8 (flow) + 3 + 3 (image in / out) + 1 + 1 (flow mask, validity) bytes per pixel.
+#include <stdlib.h>
+
+#include "warp_t_device.cuh"
+#include "ws_common.cuh"
+
+namespace ofk {
+namespace wtws {
+using namespace ws;
+
+constexpr int TS = 32;
+constexpr int BH = 48;            // box rows
+constexpr int BWB = 160;          // image box width in bytes: 48 pixels x 3 + up to 15 bytes of alignment slack
+constexpr int BMW = 64;           // mask box width (bytes): start is aligned down to 16
+constexpr int NCW = 8;            // consumer warps
+constexpr int IMG_STAGE = 7808;   // BH * BWB = 7680 rounded up to 128 (word loads may run 6 bytes past the last tap)
+
+enum : int { MM_NONE = 0, MM_GEOM = 1, MM_PMASK = 2 };
+
+template <int NP, int NB, bool PMBOX>
+struct Smem {
+    struct PStage {
+        float2 f[TS * TS];        // flow tile; rows [4w, 4w+4) double as warp w's output staging (4 x 96 bytes)
+        uint8_t fm[TS * TS];      // flow-mask tile; overwritten by the validity bytes
+    };
+    struct BStage {
+        uint8_t img[IMG_STAGE];
+        uint8_t m[PMBOX ? BH * BMW : 128];
+    };
+    alignas(128) PStage ps[NP];
+    alignas(128) BStage bs[NB];
+    alignas(16) int4 binfo[NB][2];   // {bx0 (bytes), mx0 (pixels), by0, -}, {tx0, ty0, n, -}
+    uint64_t pfull[NP], pempty[NP], bfull[NB], bempty[NB];
+};
+
+struct Maps {
+    CUtensorMap f, fm, ib, pmb, oi, om;
+};
+
+// the three result bytes of one pixel (v0, v1, v2: values 0..255) from the two 12-byte windows around its taps
+template <bool HALF_EVEN>
+__device__ __forceinline__ void blend_u8x3(uint32_t r0w0, uint32_t r0w1, uint32_t r0w2, uint32_t r1w0, uint32_t r1w1,
+                                           uint32_t r1w2, unsigned sh8, unsigned a, unsigned b, uint32_t& W0,
+                                           uint32_t& W1, uint32_t& v0, uint32_t& v1, uint32_t& v2) {
+    const uint32_t lo0 = __funnelshift_r(r0w0, r0w1, sh8), hi0 = __funnelshift_r(r0w1, r0w2, sh8);
+    const uint32_t lo1 = __funnelshift_r(r1w0, r1w1, sh8), hi1 = __funnelshift_r(r1w1, r1w2, sh8);
+    // lo = [c0t0 c1t0 c2t0 c0t1], hi = [c1t1 c2t1 . .]  ->  X = [c0t0 c0t1 c1t0 c1t1], Y = [c2t0 c2t1 . .]
+    const uint32_t X0 = __byte_perm(lo0, hi0, 0x4130), Y0 = __byte_perm(lo0, hi0, 0x0052);
+    const uint32_t X1 = __byte_perm(lo1, hi1, 0x4130), Y1 = __byte_perm(lo1, hi1, 0x0052);
+    const uint32_t pa = a * 65535u + 32u;              // (32 - a) | a << 16
+    W0 = pa * (32u - b);                               // {(32-a)(32-b), a(32-b)}: exact, no carry between the halves
+    W1 = pa * b;                                       // {(32-a)b, ab}
+    const uint32_t acc0 = __dp2a_lo(W1, X1, __dp2a_lo(W0, X0, 512u));
+    const uint32_t acc1 = __dp2a_hi(W1, X1, __dp2a_hi(W0, X0, 512u));
+    const uint32_t acc2 = __dp2a_lo(W1, Y1, __dp2a_lo(W0, Y0, 512u));
+    v0 = acc0 >> 10; v1 = acc1 >> 10; v2 = acc2 >> 10;               // round half up
+    if (HALF_EVEN) {
+        // cvRound sends exact ties (acc % 1024 == 0 after the +512) to the even neighbour; rare, so one test for all
+        const uint32_t t0 = acc0 & 1023u, t1 = acc1 & 1023u, t2 = acc2 & 1023u;
+        if (min(t0, min(t1, t2)) == 0u) {
+            if (t0 == 0u) v0 &= ~1u;
+            if (t1 == 0u) v1 &= ~1u;
+            if (t2 == 0u) v2 &= ~1u;
+        }
+    }
+}
+
+// which taps of (ix, iy) lie inside the frame, one byte each (tap order 00, 01, 10, 11)
+__device__ __forceinline__ uint32_t taps_in_frame(int ix, int iy, int H, int W) {
+    const bool x0 = (unsigned)ix < (unsigned)W, x1 = (unsigned)(ix + 1) < (unsigned)W;
+    const bool y0 = (unsigned)iy < (unsigned)H, y1 = (unsigned)(iy + 1) < (unsigned)H;
+    return (x0 && y0 ? 1u : 0u) | (x1 && y0 ? 1u << 8 : 0u) | (x0 && y1 ? 1u << 16 : 0u) | (x1 && y1 ? 1u << 24 : 0u);
+}
+
+template <bool HALF_EVEN, int MM, bool FM, int NP, int NB, int LA>
+__global__ void __launch_bounds__((NCW + 1) * 32) warp_u8x3_ws_kernel(const __grid_constant__ Maps maps,
+                                                                      const uint8_t* __restrict__ img,
+                                                                      const uint8_t* __restrict__ pmask, float sign,
+                                                                      int rule, int H, int W, unsigned tiles_x,
+                                                                      unsigned tiles_per_frame, unsigned total_tiles) {
+    static_assert(NP >= NB + LA + 1, "P stages must outlive the box pipeline and the output store");
+    using SM = Smem<NP, NB, MM == MM_PMASK>;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    SM& sm = *reinterpret_cast<SM*>(smem_raw);   // no static shared memory in this kernel: the window starts aligned
+    if (smem_u32(smem_raw) & 127u) __trap();
+    const unsigned tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const unsigned first = blockIdx.x, stride = gridDim.x;
+    if (first >= total_tiles) return;
+    const unsigned T = (total_tiles - first + stride - 1) / stride;
+    constexpr uint32_t P_BYTES = TS * TS * 8 + (FM ? TS * TS : 0);
+    constexpr uint32_t B_BYTES = BH * BWB + (MM == MM_PMASK ? BH * BMW : 0);
+
+    if (tid == 0) {
+        for (int k = 0; k < NP; ++k) { mbar_init(&sm.pfull[k], 1); mbar_init(&sm.pempty[k], NCW); }
+        for (int k = 0; k < NB; ++k) { mbar_init(&sm.bfull[k], 1); mbar_init(&sm.bempty[k], NCW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (wrp == NCW) {
+        // ------------------------------------------------------------------------------------------ producer warp
+        const int tiles_y = (int)(tiles_per_frame / tiles_x);
+        TileIter pit, bit;   // cursors of the flow-tile loads and of the box preparation
+        pit.init(first, stride, (int)tiles_x, tiles_y);
+        bit = pit;
+        unsigned ps_i = 0, ps_ph = 0;
+        auto issue_p = [&](bool wait_empty) {   // lane 0 only; tiles are issued in order
+            const int tx0 = pit.tx * TS, ty0 = pit.ty * TS, n = pit.n;
+            pit.advance((int)tiles_x, tiles_y);
+            if (wait_empty) mbar_wait(&sm.pempty[ps_i], ps_ph ^ 1);
+            mbar_expect_tx(&sm.pfull[ps_i], P_BYTES);
+            tma_load_3d(sm.ps[ps_i].f, &maps.f, &sm.pfull[ps_i], tx0, ty0, n);
+            if (FM) tma_load_3d(sm.ps[ps_i].fm, &maps.fm, &sm.pfull[ps_i], tx0, ty0, n);
+            if (++ps_i == NP) { ps_i = 0; ps_ph ^= 1; }
+        };
+        if (lane == 0)
+            for (unsigned k = 0; k < (unsigned)LA && k < T; ++k) issue_p(false);
+        unsigned s = 0, s_ph = 0, b = 0, b_ph = 0;
+        for (unsigned i = 0; i < T; ++i) {
+            const int tx0 = bit.tx * TS, ty0 = bit.ty * TS, n = bit.n;
+            bit.advance((int)tiles_x, tiles_y);
+            mbar_wait(&sm.pfull[s], s_ph);
+            // sample positions along the tile perimeter and two interior rows (lane = column for the rows, lane = row
+            // for the two columns): exact for affine fields, an estimate otherwise (consumers verify per pixel)
+            const float2* p = sm.ps[s].f;
+            float mnx = 1e30f, mxx = -1e30f, mny = 1e30f, mxy = -1e30f;
+            auto acc = [&](int r, int c) {
+                const int x = tx0 + c, y = ty0 + r;
+                if (x < W && y < H) {
+                    const float2 v = p[r * TS + c];
+                    const float X = __fmaf_rn(sign, v.x, (float)x), Y = __fmaf_rn(sign, v.y, (float)y);
+                    mnx = fminf(mnx, X); mxx = fmaxf(mxx, X);
+                    mny = fminf(mny, Y); mxy = fmaxf(mxy, Y);
+                }
+            };
+            acc(0, lane); acc(10, lane); acc(21, lane); acc(31, lane);
+            acc(lane, 0); acc(lane, 31);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+                mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+                mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+                mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+            }
+            if (lane == 0) {
+                // integer tap range, clamped to the taps that can contribute: ix in [-1, W-1], iy in [-1, H-1]
+                const float lim = 60000.f;
+                int x0 = (int)floorf(fminf(fmaxf(mnx, -lim), lim)), x1 = (int)floorf(fminf(fmaxf(mxx, -lim), lim));
+                int y0 = (int)floorf(fminf(fmaxf(mny, -lim), lim)), y1 = (int)floorf(fminf(fmaxf(mxy, -lim), lim));
+                x0 = max(-1, min(W - 1, x0)); x1 = max(-1, min(W - 1, x1));
+                y0 = max(-1, min(H - 1, y0)); y1 = max(-1, min(H - 1, y1));
+                // centre the needed range [x0, x1 + 1] in the box (spare margin on both sides for curved flows)
+                const int needw = x1 + 2 - x0, needh = y1 + 2 - y0;
+                const int vx0 = x0 - max(0, (48 - needw) / 2);
+                const int bx0 = (3 * vx0) & ~15;             // 16-byte aligned box start, in bytes of the 3*W-byte row
+                const int mx0 = vx0 & ~15;
+                const int by0 = y0 - max(0, (BH - needh) / 2);
+                if (i >= NB) mbar_wait(&sm.bempty[b], b_ph ^ 1);
+                // every tap of a pixel covered by a box that lies inside the frame is inside the frame
+                const int inframe = (bx0 >= 0 && bx0 + BWB <= 3 * W && by0 >= 0 && by0 + BH <= H) ? 1 : 0;
+                sm.binfo[b][0] = make_int4(bx0, mx0, by0, inframe);
+                sm.binfo[b][1] = make_int4(tx0, ty0, n, 0);
+                mbar_expect_tx(&sm.bfull[b], B_BYTES);
+                tma_load_3d(sm.bs[b].img, &maps.ib, &sm.bfull[b], bx0, by0, n);
+                if (MM == MM_PMASK) tma_load_3d(sm.bs[b].m, &maps.pmb, &sm.bfull[b], mx0, by0, n);
+                if (i + LA < T) issue_p(i + LA >= NP);
+            }
+            __syncwarp();
+            if (++s == NP) { s = 0; s_ph ^= 1; }
+            if (++b == NB) { b = 0; b_ph ^= 1; }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------------------------------- consumer warps
+    const unsigned s_pass = rule == OFK_RULE_STRICT ? 1024u : (rule == OFK_RULE_GT_HALF ? 513u : 512u);   // S >= s_pass
+    const unsigned own = wrp * 4 * TS + lane;          // this thread's pixel in row 4w of a tile (+ j * TS)
+    const unsigned own3 = wrp * 4 * TS * 8 + lane * 3; // byte offset of its first output byte in the flow tile (+ j * 96)
+    unsigned s = 0, s_ph = 0, b = 0, b_ph = 0;
+    int prev_s = -1;
+    for (unsigned i = 0; i < T; ++i) {
+        mbar_wait(&sm.bfull[b], b_ph);
+        mbar_wait(&sm.pfull[s], s_ph);
+        const int4 info = sm.binfo[b][0], tile = sm.binfo[b][1];
+        typename SM::PStage& ps = sm.ps[s];
+        const typename SM::BStage& bs = sm.bs[b];
+        const int tx0 = tile.x, ty0 = tile.y, n = tile.z;
+        const float xg = (float)(tx0 + (int)lane), yg = (float)(ty0 + (int)wrp * 4);
+        const float2* frow = ps.f + own;
+        uint8_t* mrow = ps.fm + own;                                        // validity bytes, in place
+        uint8_t* orow = reinterpret_cast<uint8_t*>(ps.f) + own3;            // image bytes, in place
+
+        float2 f[4];
+        unsigned fmv[4];
+        int dxb[4], dy[4], ixs[4], iys[4];
+        unsigned fa[4], fb[4];
+        bool ok = true;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            f[j] = frow[j * TS];
+            fmv[j] = (FM && MM != MM_NONE) ? mrow[j * TS] : 1u;
+            const float X = __fmaf_rn(sign, f[j].x, xg), Y = __fmaf_rn(sign, f[j].y, yg + (float)j);
+            const QCoord qx = quantise_fast(X), qy = quantise_fast(Y);
+            ixs[j] = qx.i; iys[j] = qy.i;
+            fa[j] = (unsigned)qx.f; fb[j] = (unsigned)qy.f;
+            dxb[j] = 3 * qx.i - info.x;
+            dy[j] = qy.i - info.z;
+            // Covered by the box? Everything else is decided per pixel. No range test is needed for the fast quantiser:
+            // it is exact for |X| < 2^17, and beyond that (or for NaN / Inf) the integer it produces is far outside
+            // [-2^16, 2^16], so such a pixel can never pass the box test (frames are smaller than 32768).
+            ok = ok && (unsigned)dxb[j] <= (unsigned)(BWB - 6) && (unsigned)dy[j] <= (unsigned)(BH - 2);
+        }
+        if (__all_sync(0xffffffffu, ok)) {
+            uint32_t w[4][6];
+            uint32_t mt[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned o = (unsigned)(dy[j] * BWB + dxb[j]);
+                const uint32_t* q = reinterpret_cast<const uint32_t*>(bs.img + (o & ~3u));
+                w[j][0] = q[0]; w[j][1] = q[1]; w[j][2] = q[2];
+                w[j][3] = q[BWB / 4]; w[j][4] = q[BWB / 4 + 1]; w[j][5] = q[BWB / 4 + 2];
+                if (MM == MM_PMASK) {
+                    const uint8_t* mm = bs.m + (dy[j] * BMW + (ixs[j] - info.y));
+                    mt[j] = (uint32_t)mm[0] | ((uint32_t)mm[1] << 8) | ((uint32_t)mm[BMW] << 16) |
+                            ((uint32_t)mm[BMW + 1] << 24);
+                }
+            }
+            // everything loaded from the box is consumed by the reduction below before the stage is handed back
+            unsigned dep = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dep |= w[j][5] | (MM == MM_PMASK ? mt[j] : 0u);
+            dep = __reduce_or_sync(0xffffffffu, dep);
+            if (lane == 0) mbar_arrive_after(&sm.bempty[b], dep);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned o = (unsigned)(dy[j] * BWB + dxb[j]);
+                uint32_t W0, W1, v0, v1, v2;
+                blend_u8x3<HALF_EVEN>(w[j][0], w[j][1], w[j][2], w[j][3], w[j][4], w[j][5], o << 3, fa[j], fb[j], W0, W1,
+                                      v0, v1, v2);
+                orow[j * 96 + 0] = (uint8_t)v0;
+                orow[j * 96 + 1] = (uint8_t)v1;
+                orow[j * 96 + 2] = (uint8_t)v2;
+                if (MM == MM_PMASK) {
+                    const unsigned valid = __dp2a_hi(W1, mt[j], __dp2a_lo(W0, mt[j], 0u)) >= s_pass;
+                    mrow[j * TS] = (uint8_t)(valid & fmv[j]);
+                } else if (MM == MM_GEOM) {
+                    unsigned valid = 1u;
+                    if (!info.w) {                      // tile-uniform: the box reaches over the frame border
+                        const uint32_t in = taps_in_frame(ixs[j], iys[j], H, W);
+                        valid = __dp2a_hi(W1, in, __dp2a_lo(W0, in, 0u)) >= s_pass;
+                    }
+                    mrow[j * TS] = (uint8_t)(valid & fmv[j]);
+                }
+            }
+        } else {
+            // some pixel of this warp is not covered by the box: per-pixel decision
+            const size_t fbase = (size_t)n * ((size_t)H * W);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float X = __fmaf_rn(sign, f[j].x, xg), Y = __fmaf_rn(sign, f[j].y, yg + (float)j);
+                const bool inbox = (unsigned)dxb[j] <= (unsigned)(BWB - 6) && (unsigned)dy[j] <= (unsigned)(BH - 2);
+                uint32_t v0, v1, v2;
+                unsigned valid;
+                if (inbox) {
+                    const unsigned o = (unsigned)(dy[j] * BWB + dxb[j]);
+                    const uint32_t* q = reinterpret_cast<const uint32_t*>(bs.img + (o & ~3u));
+                    uint32_t W0, W1;
+                    blend_u8x3<HALF_EVEN>(q[0], q[1], q[2], q[BWB / 4], q[BWB / 4 + 1], q[BWB / 4 + 2], o << 3, fa[j], fb[j],
+                                          W0, W1, v0, v1, v2);
+                    uint32_t in;
+                    if (MM == MM_PMASK) {
+                        const uint8_t* mm = bs.m + (dy[j] * BMW + (ixs[j] - info.y));
+                        in = (uint32_t)mm[0] | ((uint32_t)mm[1] << 8) | ((uint32_t)mm[BMW] << 16) |
+                             ((uint32_t)mm[BMW + 1] << 24);
+                    } else {
+                        in = taps_in_frame(ixs[j], iys[j], H, W);
+                    }
+                    valid = __dp2a_hi(W1, in, __dp2a_lo(W0, in, 0u)) >= s_pass;
+                } else if (X <= -1.0f || Y <= -1.0f || X >= (float)W || Y >= (float)H) {
+                    v0 = v1 = v2 = 0u; valid = 0u;       // every tap lies outside the frame
+                } else {
+                    const uint32_t r = border_px_u8x3(img + fbase * 3, MM == MM_PMASK ? pmask + fbase : nullptr, X, Y, H,
+                                                      W, HALF_EVEN, rule);
+                    v0 = r & 0xffu; v1 = (r >> 8) & 0xffu; v2 = (r >> 16) & 0xffu;
+                    valid = r >> 24;
+                }
+                orow[j * 96 + 0] = (uint8_t)v0;
+                orow[j * 96 + 1] = (uint8_t)v1;
+                orow[j * 96 + 2] = (uint8_t)v2;
+                if (MM != MM_NONE) mrow[j * TS] = (uint8_t)(valid & fmv[j] & 1u);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.bempty[b]);
+        }
+        // the warp's 4 result rows go out as bulk tensor stores (clipped at the frame border by the hardware)
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_3d(&maps.oi, ps.f + (int)wrp * 4 * TS, 3 * tx0, ty0 + (int)wrp * 4, n);
+            if (MM != MM_NONE) tma_store_3d(&maps.om, ps.fm + (int)wrp * 4 * TS, tx0, ty0 + (int)wrp * 4, n);
+            bulk_commit();
+            if (prev_s >= 0) {
+                bulk_wait_read<1>();                 // the previous tile's rows have been read out of shared memory
+                mbar_arrive(&sm.pempty[prev_s]);
+            }
+        }
+        prev_s = (int)s;
+        if (++s == NP) { s = 0; s_ph ^= 1; }
+        if (++b == NB) { b = 0; b_ph ^= 1; }
+    }
+    if (lane == 0) bulk_wait_all();
+}
+
+constexpr int WS_NP = 6, WS_NB = 2, WS_LA = 3;
+
+template <bool HALF_EVEN, int MM, bool FM>
+static int launch_variant(const Maps& maps, const uint8_t* img, const uint8_t* pmask, float sign, int rule, int H, int W,
+                          unsigned tx, unsigned ty, unsigned total, int ctas_per_sm, cudaStream_t st) {
+    using SM = Smem<WS_NP, WS_NB, MM == MM_PMASK>;
+    static bool attr_done_dev[64] = {false};   // the attribute is per device
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+    auto kernel = warp_u8x3_ws_kernel<HALF_EVEN, MM, FM, WS_NP, WS_NB, WS_LA>;
+    if (!attr_done_dev[dev]) {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM)) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        attr_done_dev[dev] = true;
+    }
+    static int resident[64] = {0};              // co-resident CTAs per SM (shared memory / registers), per device
+    if (resident[dev] == 0) {
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, (NCW + 1) * 32, sizeof(SM)) != cudaSuccess || nb < 1) {
+            cudaGetLastError();
+            nb = 1;
+        }
+        resident[dev] = nb;
+    }
+    unsigned grid = (unsigned)(sm_count() * (ctas_per_sm < resident[dev] ? ctas_per_sm : resident[dev]));
+    if (grid > total) grid = total;
+    kernel<<<grid, (NCW + 1) * 32, sizeof(SM), st>>>(maps, img, pmask, sign, rule, H, W, tx, tx * ty, total);
+    return 1;
+}
+
+}  // namespace wtws
+
+bool warp_ws_enabled() {
+    static int state = -1;
+    if (state < 0) {
+        const char* e = getenv("OFK_WARP_WS");
+        state = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return state == 1;
+}
+
+// Returns 1 if the kernel was launched, 0 if the configuration is not eligible (caller uses the gather kernel),
+// negative OFK_E* on error.
+int launch_warp_u8x3_ws(bool half_even, const void* payload, const float* flow, float sign, const uint8_t* pmask,
+                        const uint8_t* fmask, void* out, uint8_t* omask, int rule, int N, int H, int W,
+                        cudaStream_t st) {
+    using namespace wtws;
+    if (W % 16 != 0 || H >= 32768 || W >= 32768) return 0;    // 16-byte row pitch of the uint8 tensors
+    const uintptr_t align = reinterpret_cast<uintptr_t>(payload) | reinterpret_cast<uintptr_t>(flow) |
+                            reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(omask) |
+                            reinterpret_cast<uintptr_t>(pmask) | reinterpret_cast<uintptr_t>(fmask);
+    if (align & 15) return 0;
+    const int mm = omask == nullptr ? MM_NONE : (pmask != nullptr ? MM_PMASK : MM_GEOM);
+    const bool fm = omask != nullptr && fmask != nullptr;
+    Maps maps;
+    if (!make_map3(&maps.f, flow, 8, W, H, N, TS, TS) || !make_map3(&maps.ib, payload, 1, (size_t)W * 3, H, N, BWB, BH) ||
+        !make_map3(&maps.oi, out, 1, (size_t)W * 3, H, N, 96, 4))
+        return 0;
+    maps.fm = maps.pmb = maps.om = maps.f;
+    if (fm && !make_map3(&maps.fm, fmask, 1, W, H, N, TS, TS)) return 0;
+    if (mm == MM_PMASK && !make_map3(&maps.pmb, pmask, 1, W, H, N, BMW, BH)) return 0;
+    if (mm != MM_NONE && !make_map3(&maps.om, omask, 1, W, H, N, TS, 4)) return 0;
+    const unsigned tx = (W + TS - 1) / TS, ty = (H + TS - 1) / TS;
+    if ((double)tx * ty * N >= 4.0e9) return 0;
+    const unsigned total = tx * ty * (unsigned)N;
+    static int cps = -1;
+    if (cps < 0) {
+        const char* e = getenv("OFK_WARP_WS_CPS");
+        cps = e ? atoi(e) : 3;
+        if (cps < 1 || cps > 4) cps = 3;
+    }
+    int rc;
+#define OFK_WV(HE, MMV, FMV) rc = launch_variant<HE, MMV, FMV>(maps, (const uint8_t*)payload, pmask, sign, rule, H, W, tx, ty, total, cps, st)
+#define OFK_WV_HE(MMV, FMV)            \
+    do {                               \
+        if (half_even) OFK_WV(true, MMV, FMV);  \
+        else OFK_WV(false, MMV, FMV);  \
+    } while (0)
+    if (mm == MM_NONE) OFK_WV_HE(MM_NONE, false);
+    else if (mm == MM_GEOM) { if (fm) OFK_WV_HE(MM_GEOM, true); else OFK_WV_HE(MM_GEOM, false); }
+    else { if (fm) OFK_WV_HE(MM_PMASK, true); else OFK_WV_HE(MM_PMASK, false); }
+#undef OFK_WV_HE
+#undef OFK_WV
+    if (rc != 1) return rc;
+    OFK_LAUNCHED();
+    return 1;
+}
+
+}  // namespace ofk
