@@ -332,8 +332,8 @@ def main():
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get('combine3_rows_dram_bytes_per_px')
-            traffic = traffic * px_rank if traffic else None
+            traffic = json.load(open(tpath)).get('combine3_ws_dram_bytes_per_px')
+            traffic = traffic * px_rank if traffic else None       # bytes per launch, like `achieved`
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": "c3_ws_kernel<masks> (ofk_combine3, ref t)", "achieved": comb_gbs, "peak": peak,

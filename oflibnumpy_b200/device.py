@@ -4,6 +4,7 @@
 It implements ``__cuda_array_interface__`` (so ``torch.as_tensor(arr, device='cuda')`` is zero-copy) and
 :func:`as_device` wraps any object exposing that interface (torch / cupy tensors) without copying.
 """
+import atexit
 import ctypes as C
 
 import numpy as np
@@ -11,6 +12,16 @@ import numpy as np
 from . import _lib
 
 _current_stream = None  # cudaStream_t as int, None = legacy default stream
+_closing = False        # set at interpreter exit: objects die in arbitrary order then, and the process teardown frees
+                        # every device resource anyway, so finalisers stop calling into the library
+
+
+def _mark_closing():
+    global _closing
+    _closing = True
+
+
+atexit.register(_mark_closing)
 
 
 def device_count():
@@ -77,8 +88,11 @@ class Stream:
         _lib.call('ofk_rt_stream_sync', self.handle)
 
     def __del__(self):
+        global _current_stream
         try:
-            if self.handle:
+            if self.handle and not _closing:
+                if _current_stream == self.handle:      # later frees must not be ordered on a destroyed stream
+                    _current_stream = None
                 _lib.call('ofk_rt_stream_destroy', self.handle)
         except Exception:
             pass
@@ -104,7 +118,7 @@ class Event:
 
     def __del__(self):
         try:
-            if self.handle:
+            if self.handle and not _closing:
                 _lib.call('ofk_rt_event_destroy', self.handle)
         except Exception:
             pass
@@ -187,7 +201,7 @@ class DeviceArray:
                 'strides': None}
 
     def __del__(self):
-        if self._owned and self.ptr:
+        if self._owned and self.ptr and not _closing:
             try:
                 _lib.call('ofk_rt_free', self.ptr, _current_stream)
             except Exception:
@@ -236,7 +250,7 @@ class PinnedArray:
 
     def __del__(self):
         try:
-            if self._ptr:
+            if self._ptr and not _closing:
                 self.array = None
                 _lib.call('ofk_rt_host_free', self._ptr)
                 self._ptr = None
