@@ -323,8 +323,8 @@ __global__ void __launch_bounds__(256) combine3_fixup(const float* __restrict__ 
 }  // namespace ofk
 
 namespace ofk {   // combine3_ws.cu
-int launch_combine3_ws(const float* P, const uint8_t* Pm, const float* G, const uint8_t* Gm, float sign, float* out,
-                       uint8_t* omask, int N, int H, int W, cudaStream_t st);
+int launch_combine3_ws(const float* P, const uint8_t* Pm, const float* G, const uint8_t* Gm, float sign, bool add,
+                       float* out, uint8_t* omask, int N, int H, int W, cudaStream_t st);
 int launch_c3_zero_flags(const float* A, const uint8_t* Am, const float* B, const uint8_t* Bm, float thr, int* flags,
                          int N, int H, int W, cudaStream_t st);
 bool c3_ws_enabled();
@@ -352,8 +352,8 @@ extern "C" int ofk_combine3(const float* A, const uint8_t* Am, const float* B, c
     if (fast && c3_ws_enabled() && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) |
                                      reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(out_mask) |
                                      reinterpret_cast<uintptr_t>(Am) | reinterpret_cast<uintptr_t>(Bm)) & 15) == 0) {
-        if (ref == 't') ws = launch_combine3_ws(B, Bm, A, Am, -1.0f, out, out_mask, N, H, W, st);
-        else ws = launch_combine3_ws(A, Am, B, Bm, 1.0f, out, out_mask, N, H, W, st);
+        if (ref == 't') ws = launch_combine3_ws(B, Bm, A, Am, -1.0f, true, out, out_mask, N, H, W, st);
+        else ws = launch_combine3_ws(A, Am, B, Bm, 1.0f, true, out, out_mask, N, H, W, st);
         if (ws < 0) return ws;
         if (ws == 1 && flags != nullptr) {
             const int rc = launch_c3_zero_flags(A, Am, B, Bm, thr, flags, N, H, W, st);

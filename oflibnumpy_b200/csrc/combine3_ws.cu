@@ -120,7 +120,8 @@ __device__ __noinline__ float4 slow_sample(const float2* __restrict__ G, const u
     return r;
 }
 
-template <bool MASKS, int NP, int NB, int LA>
+// ADD: out = P + Q(G, ...) (composition); otherwise out = Q(G, ...) alone (Flow.apply of a flow: ofk_warp_t, float32 x2)
+template <bool MASKS, bool ADD, int NP, int NB, int LA>
 __global__ void __launch_bounds__((NCW + 1) * 32) c3_ws_kernel(const __grid_constant__ Maps maps,
                                                                const float2* __restrict__ G,
                                                                const uint8_t* __restrict__ Gm, float sign,
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32) c3_ws_kernel(const __grid_cons
                 accv = add2(accv, mul2_nofuse(t[j][1], mul2(fa2, nb2), negzero2));
                 accv = add2(accv, mul2_nofuse(t[j][2], mul2(na2, fb2), negzero2));
                 accv = add2(accv, mul2_nofuse(t[j][3], mul2(fa2, fb2), negzero2));
-                *reinterpret_cast<uint64_t*>(prow + j * TS) = add2(p[j], accv);
+                *reinterpret_cast<uint64_t*>(prow + j * TS) = ADD ? add2(p[j], accv) : accv;
                 mrow[j * TS] = (uint8_t)(strict[j] & 1u);
             }
         } else {
@@ -333,7 +334,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32) c3_ws_kernel(const __grid_cons
                     const float4 r = slow_sample(G + fbase, MASKS ? Gm + fbase : nullptr, H, W, X, Y);
                     su = r.x; sv = r.y; strict = r.z != 0.f;
                 }
-                prow[j * TS] = make_float2(__fadd_rn(pv.x, su), __fadd_rn(pv.y, sv));
+                prow[j * TS] = ADD ? make_float2(__fadd_rn(pv.x, su), __fadd_rn(pv.y, sv)) : make_float2(su, sv);
                 mrow[j * TS] = (uint8_t)(pm[j] & strict & 1u);
             }
             __syncwarp();
@@ -442,8 +443,8 @@ int launch_c3_zero_flags(const float* A, const uint8_t* Am, const float* B, cons
 
 // Returns 1 if the kernel was launched, 0 if the configuration is not eligible (caller uses the rows kernel),
 // negative OFK_E* on error. P/G are the pointwise / gathered operands, sign = -1 ('t') or +1 ('s').
-int launch_combine3_ws(const float* P, const uint8_t* Pm, const float* G, const uint8_t* Gm, float sign, float* out,
-                       uint8_t* omask, int N, int H, int W, cudaStream_t st) {
+int launch_combine3_ws(const float* P, const uint8_t* Pm, const float* G, const uint8_t* Gm, float sign, bool add,
+                       float* out, uint8_t* omask, int N, int H, int W, cudaStream_t st) {
     using namespace c3ws;
     const bool masks = Pm != nullptr && Gm != nullptr;
     if ((Pm == nullptr) != (Gm == nullptr)) return 0;
@@ -464,25 +465,25 @@ int launch_combine3_ws(const float* P, const uint8_t* Pm, const float* G, const 
     unsigned grid = (unsigned)sm_count() * 2;
     if (grid > total) grid = total;
     const size_t smem = sizeof(Smem<WS_NP, WS_NB>);
-#define OFK_WS(MK)                                                                                                    \
+#define OFK_WS(MK, AD)                                                                                                  \
     do {                                                                                                              \
         static bool attr_done_dev[64] = {false};   /* the attribute is per device */                                  \
         int dev_ = 0;                                                                                                 \
         if (cudaGetDevice(&dev_) != cudaSuccess || dev_ < 0 || dev_ >= 64) return 0;                                  \
         bool& attr_done = attr_done_dev[dev_];                                                                        \
         if (!attr_done) {                                                                                             \
-            if (cudaFuncSetAttribute(c3_ws_kernel<MK, WS_NP, WS_NB, WS_LA>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+            if (cudaFuncSetAttribute(c3_ws_kernel<MK, AD, WS_NP, WS_NB, WS_LA>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      (int)smem) != cudaSuccess) {                                                     \
                 cudaGetLastError();                                                                                   \
                 return 0;                                                                                             \
             }                                                                                                         \
             attr_done = true;                                                                                         \
         }                                                                                                             \
-        c3_ws_kernel<MK, WS_NP, WS_NB, WS_LA><<<grid, (NCW + 1) * 32, smem, st>>>(                                    \
+        c3_ws_kernel<MK, AD, WS_NP, WS_NB, WS_LA><<<grid, (NCW + 1) * 32, smem, st>>>(                                    \
             maps, (const float2*)G, Gm, sign, H, W, tx, tx * ty, total, 0x8000000080000000ull);                       \
     } while (0)
-    if (masks) OFK_WS(true);
-    else OFK_WS(false);
+    if (masks) { if (add) OFK_WS(true, true); else OFK_WS(true, false); }
+    else { if (add) OFK_WS(false, true); else OFK_WS(false, false); }
 #undef OFK_WS
     OFK_LAUNCHED();
     return 1;

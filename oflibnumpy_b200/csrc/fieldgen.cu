@@ -14,13 +14,41 @@ struct MatBatch {
     Mat3 mats[8];
 };
 
+// AFFINE: last matrix row is exactly (0, 0, 1), so tz == 1.0 exactly and the two float64 divisions (the bulk of the
+// work: the kernel is otherwise 8 B/px write-only) are the identity.
+template <bool AFFINE>
 __device__ __forceinline__ void eval_pixel(const double* __restrict__ m, int x, int y, float sign, float& u, float& v) {
     const double gx = static_cast<double>(x), gy = static_cast<double>(y);
     const double tx = __dadd_rn(__fma_rn(m[0], gx, __dmul_rn(m[1], gy)), m[2]);
     const double ty = __dadd_rn(__fma_rn(m[3], gx, __dmul_rn(m[4], gy)), m[5]);
-    const double tz = __dadd_rn(__fma_rn(m[6], gx, __dmul_rn(m[7], gy)), m[8]);
-    u = sign * __double2float_rn(__dsub_rn(__ddiv_rn(tx, tz), gx));
-    v = sign * __double2float_rn(__dsub_rn(__ddiv_rn(ty, tz), gy));
+    if (AFFINE) {
+        u = sign * __double2float_rn(__dsub_rn(tx, gx));
+        v = sign * __double2float_rn(__dsub_rn(ty, gy));
+    } else {
+        const double tz = __dadd_rn(__fma_rn(m[6], gx, __dmul_rn(m[7], gy)), m[8]);
+        u = sign * __double2float_rn(__dsub_rn(__ddiv_rn(tx, tz), gx));
+        v = sign * __double2float_rn(__dsub_rn(__ddiv_rn(ty, tz), gy));
+    }
+}
+
+template <bool AFFINE>
+__device__ __forceinline__ void fill_row(const double* __restrict__ m, float* __restrict__ row, int y, float sign, int W,
+                                         int vec_ok) {
+    if (vec_ok) {
+        for (int x = (blockIdx.x * blockDim.x + threadIdx.x) * 2; x < W; x += gridDim.x * blockDim.x * 2) {
+            float u0, v0, u1, v1;
+            eval_pixel<AFFINE>(m, x, y, sign, u0, v0);
+            eval_pixel<AFFINE>(m, x + 1, y, sign, u1, v1);
+            st_stream_f4(reinterpret_cast<float4*>(row + (size_t)x * 2), make_float4(u0, v0, u1, v1));
+        }
+    } else {
+        for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < W; x += gridDim.x * blockDim.x) {
+            float u, v;
+            eval_pixel<AFFINE>(m, x, y, sign, u, v);
+            row[(size_t)x * 2] = u;
+            row[(size_t)x * 2 + 1] = v;
+        }
+    }
 }
 
 // 2 pixels per thread -> one 16-byte store; rows are walked with a grid-stride loop over "pixel pairs".
@@ -33,21 +61,8 @@ __global__ void __launch_bounds__(256) from_matrix_kernel(const double* __restri
     for (int k = 0; k < 9; ++k) m[k] = use_host ? host_mats.mats[n].m[k] : mats_dev[(size_t)(n0 + n) * 9 + k];
     const int y = blockIdx.y;
     float* row = out + (((size_t)(n0 + n) * H + y) * W) * 2;
-    if (vec_ok) {
-        for (int x = (blockIdx.x * blockDim.x + threadIdx.x) * 2; x < W; x += gridDim.x * blockDim.x * 2) {
-            float u0, v0, u1, v1;
-            eval_pixel(m, x, y, sign, u0, v0);
-            eval_pixel(m, x + 1, y, sign, u1, v1);
-            st_stream_f4(reinterpret_cast<float4*>(row + (size_t)x * 2), make_float4(u0, v0, u1, v1));
-        }
-    } else {
-        for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < W; x += gridDim.x * blockDim.x) {
-            float u, v;
-            eval_pixel(m, x, y, sign, u, v);
-            row[(size_t)x * 2] = u;
-            row[(size_t)x * 2 + 1] = v;
-        }
-    }
+    if (m[6] == 0.0 && m[7] == 0.0 && m[8] == 1.0) fill_row<true>(m, row, y, sign, W, vec_ok);     // block-uniform
+    else fill_row<false>(m, row, y, sign, W, vec_ok);
 }
 
 }  // namespace ofk

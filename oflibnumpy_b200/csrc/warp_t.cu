@@ -467,6 +467,10 @@ static int launch_generic(const void* payload, int C, const float* flow, float s
 int launch_warp_u8x3_ws(bool half_even, const void* payload, const float* flow, float sign, const uint8_t* pmask,
                         const uint8_t* fmask, void* out, uint8_t* omask, int rule, int N, int H, int W, cudaStream_t st);
 bool warp_ws_enabled();
+// combine3_ws.cu
+int launch_combine3_ws(const float* P, const uint8_t* Pm, const float* G, const uint8_t* Gm, float sign, bool add,
+                       float* out, uint8_t* omask, int N, int H, int W, cudaStream_t st);
+bool c3_ws_enabled();
 
 }  // namespace ofk
 
@@ -510,6 +514,14 @@ extern "C" int ofk_warp_t(const void* payload, int dtype, int C, int arith, cons
 #define OFK_ROWS(T, CC, AR) \
     return launch_rows<T, CC, AR>(payload, flow, flow_sign, payload_mask, flow_mask, out, out_mask, mask_rule, N, H, W, st)
         if (C == 0) OFK_ROWS(uint8_t, 0, AR_U8_FIXED);
+        // a flow warped by a flow (Flow.apply(Flow), 27 B/px): the composition kernel without its addition
+        if (dtype == OFK_F32 && C == 2 && out_mask != nullptr && mask_rule == OFK_RULE_STRICT && c3_ws_enabled() &&
+            ((payload_mask == nullptr) == (flow_mask == nullptr)) && aligned16(flow) && aligned16(out_mask) &&
+            aligned16(payload_mask) && aligned16(flow_mask)) {
+            const int ws = launch_combine3_ws(flow, flow_mask, static_cast<const float*>(payload), payload_mask, flow_sign,
+                                              false, static_cast<float*>(out), out_mask, N, H, W, st);
+            if (ws != 0) return ws < 0 ? ws : OFK_OK;
+        }
         if (dtype == OFK_U8 && C == 3 && warp_ws_enabled()) {
             const int ws = launch_warp_u8x3_ws(ar == AR_RINT, payload, flow, flow_sign, payload_mask, flow_mask, out,
                                                out_mask, mask_rule, N, H, W, st);
