@@ -103,8 +103,12 @@ __global__ void __launch_bounds__(256) fwd_scatter(const float* __restrict__ flo
         const double area2 = orient(p0, p1, p2);
         if (area2 == 0.0) continue;
         const double sgn = area2 > 0 ? 1.0 : -1.0;
-        int xmin = (int)ceil(fmin(p0.x, fmin(p1.x, p2.x))), xmax = (int)floor(fmax(p0.x, fmax(p1.x, p2.x)));
-        int ymin = (int)ceil(fmin(p0.y, fmin(p1.y, p2.y))), ymax = (int)floor(fmax(p0.y, fmax(p1.y, p2.y)));
+        // candidate pixels: bounding box in float32, rounded outwards (a superset is enough: coverage is decided by
+        // the exact edge functions below)
+        int xmin = (int)ceilf(fminf(__double2float_rd(p0.x), fminf(__double2float_rd(p1.x), __double2float_rd(p2.x))));
+        int xmax = (int)floorf(fmaxf(__double2float_ru(p0.x), fmaxf(__double2float_ru(p1.x), __double2float_ru(p2.x))));
+        int ymin = (int)ceilf(fminf(__double2float_rd(p0.y), fminf(__double2float_rd(p1.y), __double2float_rd(p2.y))));
+        int ymax = (int)floorf(fmaxf(__double2float_ru(p0.y), fmaxf(__double2float_ru(p1.y), __double2float_ru(p2.y))));
         xmin = max(xmin, 0);
         ymin = max(ymin, 0);
         xmax = min(xmax, W - 1);
@@ -126,7 +130,8 @@ __global__ void __launch_bounds__(256) fwd_gather(const float* __restrict__ payl
                                                   const float* __restrict__ flow, float sign,
                                                   const uint8_t* __restrict__ payload_mask,
                                                   const unsigned int* __restrict__ winner, float* __restrict__ out,
-                                                  uint8_t* __restrict__ out_mask, int rule, int H, int W) {
+                                                  uint8_t* __restrict__ out_mask, int rule, int H, int W,
+                                                  unsigned long long inv_w /* ceil(2^64 / W) */) {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
     const int n = blockIdx.z;
@@ -141,7 +146,7 @@ __global__ void __launch_bounds__(256) fwd_gather(const float* __restrict__ payl
     }
     const unsigned int code = id - 1u;
     const int diag = code & 1, tri = (code >> 1) & 1, cell = (int)(code >> 2);
-    const int i = cell / W, j = cell - i * W;
+    const int i = (int)__umul64hi((unsigned long long)cell, inv_w), j = cell - i * W;   // exact: cell < 2^29
     const float2* fl = reinterpret_cast<const float2*>(flow) + fbase;
     int vidx[3];
     P2 p[3];
@@ -154,8 +159,11 @@ __global__ void __launch_bounds__(256) fwd_gather(const float* __restrict__ payl
     }
     const double area2 = orient(p[0], p[1], p[2]);
     const double qx = x, qy = y;
-    double w0 = edge_fn(p[1], vidx[1], p[2], vidx[2], qx, qy) / area2;
-    double w1 = edge_fn(p[2], vidx[2], p[0], vidx[0], qx, qy) / area2;
+    // one reciprocal instead of two divisions: the weights move by an ulp at most (values are compared at 1e-3, the
+    // mask tests below are decided by exact zeros and by margins far above an ulp)
+    const double inv_area = __drcp_rn(area2);
+    double w0 = edge_fn(p[1], vidx[1], p[2], vidx[2], qx, qy) * inv_area;
+    double w1 = edge_fn(p[2], vidx[2], p[0], vidx[0], qx, qy) * inv_area;
     double w2 = 1.0 - w0 - w1;
     const float* pay = payload + fbase * C;
     for (int c = 0; c < C; ++c) {
@@ -212,7 +220,9 @@ extern "C" int ofk_forward_s(const float* payload, int C, const float* flow, flo
         OFK_LAUNCHED();
     }
     dim3 grid((W + 31) / 32, (H + 7) / 8, N);
-    fwd_gather<<<grid, 256, 0, st>>>(payload, C, flow, flow_sign, payload_mask, winner, out, out_mask, mask_rule, H, W);
+    const unsigned long long inv_w = W > 1 ? ~0ull / (unsigned long long)W + 1ull : 0ull;   // ceil(2^64 / W), W >= 2
+    fwd_gather<<<grid, 256, 0, st>>>(payload, C, flow, flow_sign, payload_mask, winner, out, out_mask, mask_rule, H, W,
+                                     inv_w);
     OFK_LAUNCHED();
     return OFK_OK;
 }
