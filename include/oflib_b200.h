@@ -253,6 +253,10 @@ int ofk_rt_event_sync(void* event);
 int ofk_rt_event_elapsed_ms(void* start, void* stop, float* ms);
 /* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */
 unsigned long long ofk_rt_launch_count(void);
+/* how often each implementation of the two headline operations ran (tests assert that eligible shapes take the TMA
+ * kernels): which = 0 ofk_combine3 / TMA kernel, 1 ofk_combine3 / gather kernels, 2 ofk_warp_t / TMA kernels,
+ * 3 ofk_warp_t / gather kernels */
+unsigned long long ofk_rt_path_count(int which);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

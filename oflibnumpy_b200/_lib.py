@@ -70,9 +70,10 @@ _SIGNATURES = {
     'ofk_rt_event_sync': (_i, [_vp]),
     'ofk_rt_event_elapsed_ms': (_i, [_vp, _vp, C.POINTER(_f)]),
     'ofk_rt_launch_count': (C.c_ulonglong, []),
+    'ofk_rt_path_count': (C.c_ulonglong, [C.c_int]),
 }
 
-_NO_CHECK = {'ofk_last_error', 'ofk_version', 'ofk_forward_s_workspace', 'ofk_rt_launch_count'}
+_NO_CHECK = {'ofk_last_error', 'ofk_version', 'ofk_forward_s_workspace', 'ofk_rt_launch_count', 'ofk_rt_path_count'}
 
 _lib = None
 

@@ -361,6 +361,7 @@ extern "C" int ofk_combine3(const float* A, const uint8_t* Am, const float* B, c
         }
     }
     if (ws != 1 && flags != nullptr) OFK_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 2 * (size_t)N, st));
+    g_paths[ws == 1 ? 0 : 1].fetch_add(1, std::memory_order_relaxed);
     if (ws == 1) {
         // launched
     } else if (fast) {

@@ -12,6 +12,7 @@ namespace ofk {
 // ------------------------------------------------------------------------------------------------ host-side plumbing
 void set_error(const char* fmt, ...);
 extern std::atomic<unsigned long long> g_launches;
+extern std::atomic<unsigned long long> g_paths[4];   // see ofk_rt_path_count
 
 #define OFK_CHECK_ARG(cond, ...)                \
     do {                                        \

@@ -12,6 +12,7 @@ namespace ofk {
 
 static thread_local char t_error[512] = "";
 std::atomic<unsigned long long> g_launches{0};
+std::atomic<unsigned long long> g_paths[4];
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -39,6 +40,7 @@ using namespace ofk;
 extern "C" const char* ofk_last_error(void) { return t_error; }
 extern "C" int ofk_version(void) { return OFK_VERSION; }
 extern "C" unsigned long long ofk_rt_launch_count(void) { return g_launches.load(); }
+extern "C" unsigned long long ofk_rt_path_count(int which) { return (which >= 0 && which < 4) ? g_paths[which].load() : 0ull; }
 
 // ------------------------------------------------------------------------------------------------------- runtime
 extern "C" int ofk_rt_device_count(int* count) {

@@ -498,6 +498,10 @@ extern "C" int ofk_warp_t(const void* payload, int dtype, int C, int arith, cons
     cudaStream_t st = as_stream(stream);
 
     const bool same_frame = (Hs == H && Ws == W);
+    struct PathCount {   // every exit below that is not a TMA launch is a gather-kernel launch
+        bool tma = false;
+        ~PathCount() { g_paths[tma ? 2 : 3].fetch_add(1, std::memory_order_relaxed); }
+    } path;
     int ar;
     switch (dtype) {
         case OFK_U8: ar = (arith == OFK_ARITH_RINT) ? AR_RINT : AR_U8_FIXED; break;
@@ -520,11 +524,13 @@ extern "C" int ofk_warp_t(const void* payload, int dtype, int C, int arith, cons
             aligned16(payload_mask) && aligned16(flow_mask)) {
             const int ws = launch_combine3_ws(flow, flow_mask, static_cast<const float*>(payload), payload_mask, flow_sign,
                                               false, static_cast<float*>(out), out_mask, N, H, W, st);
+            path.tma = ws > 0;
             if (ws != 0) return ws < 0 ? ws : OFK_OK;
         }
         if (dtype == OFK_U8 && C == 3 && warp_ws_enabled()) {
             const int ws = launch_warp_u8x3_ws(ar == AR_RINT, payload, flow, flow_sign, payload_mask, flow_mask, out,
                                                out_mask, mask_rule, N, H, W, st);
+            path.tma = ws > 0;
             if (ws != 0) return ws < 0 ? ws : OFK_OK;
         }
         if (dtype == OFK_U8 && C == 3)

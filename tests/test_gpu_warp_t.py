@@ -452,3 +452,73 @@ print("fallback parity ok")
     res = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout + res.stderr
     assert 'fallback parity ok' in res.stdout
+
+
+def _smooth_flow(rng, h, w, amp):
+    """Affine (rotation / scale / shear / translation) + low-frequency ripple + a little noise: the regime of the TMA
+    kernels' box estimate (mostly covered) with pixels that escape it (noise, borders)."""
+    yy, xx = np.mgrid[:h, :w].astype(np.float32)
+    a = rng.uniform(-0.15, 0.15, 4).astype(np.float32)
+    t = rng.uniform(-amp, amp, 2).astype(np.float32)
+    u = a[0] * (xx - w / 2) + a[1] * (yy - h / 2) + t[0] + 2 * np.sin(xx / 9 + rng.uniform(0, 6)) * np.cos(yy / 7)
+    v = a[2] * (xx - w / 2) + a[3] * (yy - h / 2) + t[1] + 2 * np.cos(xx / 8) * np.sin(yy / 11 + rng.uniform(0, 6))
+    f = np.stack([u, v], -1).astype(np.float32)
+    f += (rng.random((h, w, 2)).astype(np.float32) - np.float32(0.5)) * np.float32(rng.choice([0, 0.5, 3]))
+    if rng.random() < 0.3:                                   # a few wild vectors far outside any box / the frame
+        idx = rng.integers(0, h * w, 5)
+        f.reshape(-1, 2)[idx] = rng.uniform(-5000, 5000, (5, 2)).astype(np.float32)
+    return f
+
+
+def test_tma_kernels_randomized(of):
+    """Randomised shapes (W % 16 == 0, partial tiles in both directions), batches and flow regimes through every
+    variant of the warp-specialised TMA kernels -- composition with / without masks, both references; image warp with
+    fixed-point / round-half-even arithmetic, no / geometric / resampled validity, with and without a flow mask; a flow
+    warped by a flow -- against the oracle, bit for bit, and twice (the kernels are pipelines of asynchronous copies:
+    results must not depend on timing)."""
+    from oflibnumpy_b200 import _lib
+    lib = _lib.load()
+    before = [lib.ofk_rt_path_count(k) for k in range(4)]
+    rng = np.random.default_rng(77)
+    shapes = [(1, 16), (5, 32), (31, 48), (32, 32), (33, 64), (47, 80), (64, 96), (70, 144), (97, 208), (130, 256)]
+    for k, (h, w) in enumerate(shapes):
+        n = int(rng.integers(1, 4))
+        amp = float(rng.choice([1.5, 12, 40]))
+        a = np.stack([_smooth_flow(rng, h, w, amp) for _ in range(n)])
+        b = np.stack([_smooth_flow(rng, h, w, amp) for _ in range(n)])
+        am, bm = rng.random((n, h, w)) > 0.1, rng.random((n, h, w)) > 0.1
+        img = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+        for r in ('t', 's'):
+            for rep in range(2):
+                v, m = of.FlowBatch(a, r, am).combine_with(of.FlowBatch(b, r, bm), 3).numpy()
+                for i in range(n):
+                    want = R.combine(R.make(a[i], r, am[i]), R.make(b[i], r, bm[i]), 3)
+                    same(m[i].view(np.bool_), want.mask)
+                    same(v[i], want.vecs)
+            got = of.combine_flows(a[0], b[0], 3, r)
+            same(got, R.combine(R.make(a[0], r), R.make(b[0], r), 3).vecs)
+        for i in range(n):
+            fa = of.Flow(a[i], 't', am[i])
+            ra = R.make(a[i], 't', am[i])
+            for rep in range(2):
+                same(fa.apply(img[i]), R.apply(ra, img[i]))                                    # fixed point, no mask
+                w1, m1 = fa.apply(img[i], return_valid_area=True)                              # half-even, geometry
+                w2, m2 = R.apply(ra, img[i], return_valid_area=True)
+                same(w1, w2)
+                same(m1, m2)
+                w1, m1 = fa.apply(img[i], target_mask=bm[i], return_valid_area=True)           # resampled mask
+                w2, m2 = R.apply(ra, img[i], target_mask=bm[i], return_valid_area=True)
+                same(w1, w2)
+                same(m1, m2)
+                w1, m1 = fa.apply(img[i], return_valid_area=True, consider_mask=False)         # no flow mask
+                w2, m2 = R.apply(ra, img[i], return_valid_area=True, consider_mask=False)
+                same(w1, w2)
+                same(m1, m2)
+                res = fa.apply(of.Flow(b[i], 't', bm[i]))                                      # flow warped by flow
+                want = R.apply(ra, R.make(b[i], 't', bm[i]))
+                same(res.mask, want.mask)
+                same(res.vecs, want.vecs)
+    after = [lib.ofk_rt_path_count(k) for k in range(4)]
+    # every call above is eligible for the TMA kernels (W % 16 == 0, pool allocations are 256-byte aligned)
+    assert after[0] > before[0] and after[2] > before[2]
+    assert after[1] == before[1] and after[3] == before[3], (before, after)
