@@ -369,7 +369,8 @@ __device__ __forceinline__ bool nz(float c, float thr) { return thr > 0.f ? !(c 
 constexpr int PROBE_SAMPLES = 2048;
 __global__ void __launch_bounds__(256) c3_probe_nonzero(const float2* __restrict__ A, const uint8_t* __restrict__ Am,
                                                         const float2* __restrict__ B, const uint8_t* __restrict__ Bm,
-                                                        float thr, int* __restrict__ flags, size_t frame) {
+                                                        float thr, int* __restrict__ flags, size_t frame,
+                                                        int stride /* flags per frame: 2, or 1 when B == NULL */) {
     const int n = blockIdx.x;
     const size_t base = (size_t)n * frame;
     const size_t step = frame / PROBE_SAMPLES > 0 ? frame / PROBE_SAMPLES : 1;
@@ -377,40 +378,51 @@ __global__ void __launch_bounds__(256) c3_probe_nonzero(const float2* __restrict
     for (size_t k = threadIdx.x; k < PROBE_SAMPLES; k += blockDim.x) {
         const size_t i = k * step;
         if (i >= frame) break;
-        const float2 va = __ldg(A + base + i), vb = __ldg(B + base + i);
+        const float2 va = __ldg(A + base + i);
         a = a || ((Am == nullptr || Am[base + i]) && (nz(va.x, thr) || nz(va.y, thr)));
-        b = b || ((Bm == nullptr || Bm[base + i]) && (nz(vb.x, thr) || nz(vb.y, thr)));
+        if (B != nullptr) {
+            const float2 vb = __ldg(B + base + i);
+            b = b || ((Bm == nullptr || Bm[base + i]) && (nz(vb.x, thr) || nz(vb.y, thr)));
+        }
     }
     const int fa = __syncthreads_or(a), fb = __syncthreads_or(b);
     if (threadIdx.x == 0) {
-        flags[n * 2 + 0] = fa ? 1 : 0;
-        flags[n * 2 + 1] = fb ? 1 : 0;
+        flags[n * stride + 0] = fa ? 1 : 0;
+        if (B != nullptr) flags[n * stride + 1] = fb ? 1 : 0;
     }
 }
 
 // Complete scan of the operands the probe left undecided (flag still 0); CTAs of decided frames exit at once.
 __global__ void __launch_bounds__(256) c3_scan_nonzero(const float2* __restrict__ A, const uint8_t* __restrict__ Am,
                                                        const float2* __restrict__ B, const uint8_t* __restrict__ Bm,
-                                                       float thr, int* __restrict__ flags, size_t frame) {
+                                                       float thr, int* __restrict__ flags, size_t frame, int stride) {
     const int n = blockIdx.y;
-    const bool need_a = flags[n * 2 + 0] == 0, need_b = flags[n * 2 + 1] == 0;   // written by the previous kernel
+    // flags were written by the previous kernel
+    const bool need_a = flags[n * stride + 0] == 0, need_b = B != nullptr && flags[n * stride + 1] == 0;
     if (!need_a && !need_b) return;
     const size_t base = (size_t)n * frame;
     bool a = false, b = false;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < frame; i += (size_t)gridDim.x * blockDim.x) {
-        if (need_a && !a) {
-            const float2 v = __ldg(A + base + i);
-            a = (Am == nullptr || Am[base + i]) && (nz(v.x, thr) || nz(v.y, thr));
-        }
-        if (need_b && !b) {
-            const float2 v = __ldg(B + base + i);
-            b = (Bm == nullptr || Bm[base + i]) && (nz(v.x, thr) || nz(v.y, thr));
+    const size_t step = (size_t)gridDim.x * blockDim.x;
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < frame; i0 += 4 * step) {
+        // four independent loads per operand in flight
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const size_t i = i0 + k * step;
+            if (i >= frame) break;
+            if (need_a) {
+                const float2 v = __ldg(A + base + i);
+                a = a || ((Am == nullptr || Am[base + i]) && (nz(v.x, thr) || nz(v.y, thr)));
+            }
+            if (need_b) {
+                const float2 v = __ldg(B + base + i);
+                b = b || ((Bm == nullptr || Bm[base + i]) && (nz(v.x, thr) || nz(v.y, thr)));
+            }
         }
     }
     const int fa = __syncthreads_or(a), fb = __syncthreads_or(b);
     if (threadIdx.x == 0) {
-        if (fa) atomicOr(&flags[n * 2 + 0], 1);
-        if (fb) atomicOr(&flags[n * 2 + 1], 1);
+        if (fa) atomicOr(&flags[n * stride + 0], 1);
+        if (fb) atomicOr(&flags[n * stride + 1], 1);
     }
 }
 
@@ -428,15 +440,18 @@ bool c3_ws_enabled() {
     return state == 1;
 }
 
-// The zero tests of combine3: flags[n] = {A_nonzero, B_nonzero}. 2 launches; the second is a no-op for decided frames.
+// The zero tests: flags[n] = {A_nonzero, B_nonzero} (combine3), or flags[n] = A_nonzero when B == NULL
+// (ofk_nonzero_flags). 2 launches; the second is a no-op for frames the probe decided.
 int launch_c3_zero_flags(const float* A, const uint8_t* Am, const float* B, const uint8_t* Bm, float thr, int* flags,
                          int N, int H, int W, cudaStream_t st) {
     const size_t frame = (size_t)H * W;
-    c3ws::c3_probe_nonzero<<<N, 256, 0, st>>>((const float2*)A, Am, (const float2*)B, Bm, thr, flags, frame);
+    const int stride = B != nullptr ? 2 : 1;
+    c3ws::c3_probe_nonzero<<<N, 256, 0, st>>>((const float2*)A, Am, (const float2*)B, Bm, thr, flags, frame, stride);
     OFK_LAUNCHED();
     int bx = (int)((frame + 256 * 16 - 1) / (256 * 16));
     if (bx > 64) bx = 64;
-    c3ws::c3_scan_nonzero<<<dim3(bx, N), 256, 0, st>>>((const float2*)A, Am, (const float2*)B, Bm, thr, flags, frame);
+    c3ws::c3_scan_nonzero<<<dim3(bx, N), 256, 0, st>>>((const float2*)A, Am, (const float2*)B, Bm, thr, flags, frame,
+                                                        stride);
     OFK_LAUNCHED();
     return OFK_OK;
 }

@@ -422,6 +422,39 @@ __global__ void __launch_bounds__(256) warp_t_u8x3(const uint8_t* __restrict__ p
     }
 }
 
+
+// ------------------------------------------------------------------------------------- valid area without payload
+// valid_target (ref 't') / valid_source (ref 's'), flow_class.py:1148-1150,1179-1183: "every tap with a non-zero
+// weight lies inside the frame", AND the flow mask. Pure streaming (8 + 1 B/px in, 1 B/px out): 4 consecutive pixels
+// per thread, 2 x 16-byte flow loads, one 32-bit mask word in and out.
+__device__ __forceinline__ unsigned strict_in_frame(float X, float Y, int H, int W) {
+    // clamping keeps the fast quantiser in range; a clamped coordinate is an integer outside [0, W-1] -> invalid
+    X = fminf(fmaxf(X, -2.0f), (float)(W + 1));
+    Y = fminf(fmaxf(Y, -2.0f), (float)(H + 1));
+    const QCoord qx = quantise_fast(X), qy = quantise_fast(Y);
+    const bool ok = qx.i >= 0 && qy.i >= 0 && (qx.i + 1 < W || (qx.f == 0 && qx.i < W)) &&
+                    (qy.i + 1 < H || (qy.f == 0 && qy.i < H));
+    return ok ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256) valid_geom_vec4(const float4* __restrict__ flow, float sign,
+                                                       const uint32_t* __restrict__ fmask, uint32_t* __restrict__ out,
+                                                       int H, int W, unsigned quads_per_frame) {
+    const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;      // quad index inside frame blockIdx.y
+    if (r >= quads_per_frame) return;
+    const size_t q = (size_t)blockIdx.y * quads_per_frame + r;
+    const unsigned wq = (unsigned)W >> 2;
+    const int y = (int)(r / wq), x = (int)(r - (unsigned)y * wq) << 2;
+    const float4 f0 = ld_stream_f4(flow + 2 * q), f1 = ld_stream_f4(flow + 2 * q + 1);
+    const uint32_t m = fmask ? ld_stream_u32(fmask + q) : 0x01010101u;
+    const float Yg = (float)y;
+    uint32_t v = strict_in_frame(__fmaf_rn(sign, f0.x, (float)x), __fmaf_rn(sign, f0.y, Yg), H, W);
+    v |= strict_in_frame(__fmaf_rn(sign, f0.z, (float)(x + 1)), __fmaf_rn(sign, f0.w, Yg), H, W) << 8;
+    v |= strict_in_frame(__fmaf_rn(sign, f1.x, (float)(x + 2)), __fmaf_rn(sign, f1.y, Yg), H, W) << 16;
+    v |= strict_in_frame(__fmaf_rn(sign, f1.z, (float)(x + 3)), __fmaf_rn(sign, f1.w, Yg), H, W) << 24;
+    st_stream_u32(out + q, v & m);
+}
+
 template <typename T, int C, int AR>
 static int launch_rows(const void* payload, const float* flow, float sign, const uint8_t* pmask, const uint8_t* fmask,
                        void* out, uint8_t* omask, int rule, int N, int H, int W, cudaStream_t st) {
@@ -572,6 +605,20 @@ extern "C" int ofk_warp_t(const void* payload, int dtype, int C, int arith, cons
 extern "C" int ofk_valid_geom_t(const float* flow, float flow_sign, const uint8_t* flow_mask, uint8_t* out, int N,
                                 int H, int W, ofk_stream_t stream) {
     OFK_CHECK_ARG(out != nullptr, "ofk_valid_geom_t: out is NULL");
+    OFK_CHECK_ARG(flow != nullptr && N >= 0 && H > 0 && W > 0, "ofk_valid_geom_t: bad arguments");
+    OFK_CHECK_ARG(flow_sign == 1.0f || flow_sign == -1.0f, "ofk_valid_geom_t: flow_sign must be +1 or -1");
+    if (N == 0) return OFK_OK;
+    if (W % 4 == 0 && W < 32768 && H < 32768 && aligned16(flow) && (reinterpret_cast<uintptr_t>(out) & 3) == 0 &&
+        (reinterpret_cast<uintptr_t>(flow_mask) & 3) == 0) {
+        const size_t qpf = (size_t)H * W / 4;
+        if (qpf < 0x7fffff00ull && N <= 65535) {
+            valid_geom_vec4<<<dim3((unsigned)((qpf + 255) / 256), N), 256, 0, as_stream(stream)>>>(
+                reinterpret_cast<const float4*>(flow), flow_sign, reinterpret_cast<const uint32_t*>(flow_mask),
+                reinterpret_cast<uint32_t*>(out), H, W, (unsigned)qpf);
+            OFK_LAUNCHED();
+            return OFK_OK;
+        }
+    }
     return ofk_warp_t(nullptr, OFK_U8, 0, OFK_ARITH_NATIVE, flow, flow_sign, nullptr, flow_mask, nullptr, out,
                       OFK_RULE_STRICT, N, H, W, H, W, 0, 0, 1, stream);
 }
