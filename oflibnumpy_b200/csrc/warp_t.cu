@@ -497,8 +497,8 @@ static int launch_generic(const void* payload, int C, const float* flow, float s
 }
 
 // warp_t_ws.cu
-int launch_warp_u8x3_ws(bool half_even, const void* payload, const float* flow, float sign, const uint8_t* pmask,
-                        const uint8_t* fmask, void* out, uint8_t* omask, int rule, int N, int H, int W, cudaStream_t st);
+int launch_warp_u8_ws(int C, bool half_even, const void* payload, const float* flow, float sign, const uint8_t* pmask,
+                      const uint8_t* fmask, void* out, uint8_t* omask, int rule, int N, int H, int W, cudaStream_t st);
 bool warp_ws_enabled();
 // combine3_ws.cu
 int launch_combine3_ws(const float* P, const uint8_t* Pm, const float* G, const uint8_t* Gm, float sign, bool add,
@@ -560,9 +560,9 @@ extern "C" int ofk_warp_t(const void* payload, int dtype, int C, int arith, cons
             path.tma = ws > 0;
             if (ws != 0) return ws < 0 ? ws : OFK_OK;
         }
-        if (dtype == OFK_U8 && C == 3 && warp_ws_enabled()) {
-            const int ws = launch_warp_u8x3_ws(ar == AR_RINT, payload, flow, flow_sign, payload_mask, flow_mask, out,
-                                               out_mask, mask_rule, N, H, W, st);
+        if (dtype == OFK_U8 && (C == 1 || C == 3 || C == 4) && warp_ws_enabled()) {
+            const int ws = launch_warp_u8_ws(C, ar == AR_RINT, payload, flow, flow_sign, payload_mask, flow_mask, out,
+                                             out_mask, mask_rule, N, H, W, st);
             path.tma = ws > 0;
             if (ws != 0) return ws < 0 ? ws : OFK_OK;
         }

@@ -6,9 +6,12 @@
 namespace ofk {
 
 // Pixels whose taps touch the border (or whose coordinates leave the fast-quantisation range): exact but slow, out
-// of line, by-value in / out (no stack traffic). Returns the 3 result bytes in bits 0..23 and the validity in bit 24.
-static __device__ __noinline__ uint32_t border_px_u8x3(const uint8_t* __restrict__ p, const uint8_t* __restrict__ pm, float X,
-                                                float Y, int H, int W, int half_even, int rule) {
+// of line, by-value in / out (no stack traffic). C interleaved uint8 channels (C <= 4): returns the C result bytes in
+// bits 0..8C-1 and the validity in bit 32.
+template <int C>
+static __device__ __noinline__ unsigned long long border_px_u8c(const uint8_t* __restrict__ p,
+                                                                const uint8_t* __restrict__ pm, float X, float Y, int H,
+                                                                int W, int half_even, int rule) {
     const QCoord qx = quantise(X), qy = quantise(Y);
     const int ix = qx.i, iy = qy.i;
     const QWeights w = qweights(qx.f, qy.f);
@@ -19,22 +22,31 @@ static __device__ __noinline__ uint32_t border_px_u8x3(const uint8_t* __restrict
     const long long o = (long long)iy * W + ix;
     const long long off[4] = {o, o + 1, o + W, o + W + 1};
     const int wi[4] = {w.w00, w.w01, w.w10, w.w11};
-    int acc[3] = {0, 0, 0}, S = 0;
+    int acc[C], S = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         if (!in[k]) continue;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) acc[c] += (int)p[off[k] * 3 + c] * wi[k];
+        for (int c = 0; c < C; ++c) acc[c] += (int)p[off[k] * C + c] * wi[k];
         if (pm == nullptr || pm[off[k]]) S += wi[k];
     }
-    uint32_t v = 0;
+    unsigned long long v = 0;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
+    for (int c = 0; c < C; ++c) {
         const int a = acc[c];
         const uint32_t r = half_even ? (uint32_t)(a + 511 + ((a >> 10) & 1)) >> 10 : (uint32_t)(a + 512) >> 10;
-        v |= r << (8 * c);
+        v |= (unsigned long long)r << (8 * c);
     }
-    return v | (mask_rule_pass(S, rule) ? (1u << 24) : 0u);
+    return v | (mask_rule_pass(S, rule) ? (1ull << 32) : 0ull);
+}
+
+// 3 channels, packed for warp_t.cu: result bytes in bits 0..23, validity in bit 24
+static __device__ __forceinline__ uint32_t border_px_u8x3(const uint8_t* __restrict__ p, const uint8_t* __restrict__ pm,
+                                                         float X, float Y, int H, int W, int half_even, int rule) {
+    const unsigned long long r = border_px_u8c<3>(p, pm, X, Y, H, W, half_even, rule);
+    return (uint32_t)r | ((uint32_t)(r >> 32) << 24);
 }
 
 }  // namespace ofk

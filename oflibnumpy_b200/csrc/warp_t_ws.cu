@@ -26,21 +26,24 @@ using namespace ws;
 
 constexpr int TS = 32;
 constexpr int BH = 48;            // box rows
-constexpr int BWB = 160;          // image box width in bytes: 48 pixels x 3 + up to 15 bytes of alignment slack
 constexpr int BMW = 64;           // mask box width (bytes): start is aligned down to 16
 constexpr int NCW = 8;            // consumer warps
-constexpr int IMG_STAGE = 7808;   // BH * BWB = 7680 rounded up to 128 (word loads may run 6 bytes past the last tap)
+// image box width in bytes for C interleaved uint8 channels: 48 pixels x C + up to 15 bytes of alignment slack, rounded
+// up to the 16 bytes TMA needs (C = 1: 64, C = 3: 160, C = 4: 208)
+__host__ __device__ constexpr int box_bytes(int C) { return (48 * C + 15 + 15) / 16 * 16; }
+// BH rows, rounded up to 128 with room for the word loads that run a few bytes past the last tap
+__host__ __device__ constexpr int img_stage(int C) { return (BH * box_bytes(C) + 16 + 127) / 128 * 128; }
 
 enum : int { MM_NONE = 0, MM_GEOM = 1, MM_PMASK = 2 };
 
-template <int NP, int NB, bool PMBOX>
+template <int NP, int NB, bool PMBOX, int C>
 struct Smem {
     struct PStage {
-        float2 f[TS * TS];        // flow tile; rows [4w, 4w+4) double as warp w's output staging (4 x 96 bytes)
+        float2 f[TS * TS];        // flow tile; rows [4w, 4w+4) double as warp w's output staging (4 x 32*C bytes)
         uint8_t fm[TS * TS];      // flow-mask tile; overwritten by the validity bytes
     };
     struct BStage {
-        uint8_t img[IMG_STAGE];
+        uint8_t img[img_stage(C)];
         uint8_t m[PMBOX ? BH * BMW : 128];
     };
     alignas(128) PStage ps[NP];
@@ -81,6 +84,73 @@ __device__ __forceinline__ void blend_u8x3(uint32_t r0w0, uint32_t r0w1, uint32_
     }
 }
 
+template <bool HALF_EVEN>
+__device__ __forceinline__ uint32_t round_u8(uint32_t acc) {      // acc = sum t*w + 512
+    uint32_t v = acc >> 10;
+    if (HALF_EVEN && (acc & 1023u) == 0u) v &= ~1u;
+    return v;
+}
+__device__ __forceinline__ void weights_u8(unsigned a, unsigned b, uint32_t& W0, uint32_t& W1) {
+    const uint32_t pa = a * 65535u + 32u;              // (32 - a) | a << 16
+    W0 = pa * (32u - b);
+    W1 = pa * b;
+}
+// 1 channel: the two taps of a row are adjacent bytes (2 aligned words per row cover them)
+template <bool HALF_EVEN>
+__device__ __forceinline__ uint32_t blend_u8x1(uint32_t r0w0, uint32_t r0w1, uint32_t r1w0, uint32_t r1w1, unsigned sh8,
+                                               unsigned a, unsigned b, uint32_t& W0, uint32_t& W1) {
+    const uint32_t lo0 = __funnelshift_r(r0w0, r0w1, sh8), lo1 = __funnelshift_r(r1w0, r1w1, sh8);
+    weights_u8(a, b, W0, W1);
+    return round_u8<HALF_EVEN>(__dp2a_lo(W1, lo1, __dp2a_lo(W0, lo0, 512u)));
+}
+// 4 channels: a pixel is one aligned word; returns the four result bytes packed
+template <bool HALF_EVEN>
+__device__ __forceinline__ uint32_t blend_u8x4(uint32_t t00, uint32_t t01, uint32_t t10, uint32_t t11, unsigned a,
+                                               unsigned b, uint32_t& W0, uint32_t& W1) {
+    // [c0t0 c0t1 c1t0 c1t1] and [c2t0 c2t1 c3t0 c3t1] per row
+    const uint32_t X0 = __byte_perm(t00, t01, 0x5140), Y0 = __byte_perm(t00, t01, 0x7362);
+    const uint32_t X1 = __byte_perm(t10, t11, 0x5140), Y1 = __byte_perm(t10, t11, 0x7362);
+    weights_u8(a, b, W0, W1);
+    const uint32_t v0 = round_u8<HALF_EVEN>(__dp2a_lo(W1, X1, __dp2a_lo(W0, X0, 512u)));
+    const uint32_t v1 = round_u8<HALF_EVEN>(__dp2a_hi(W1, X1, __dp2a_hi(W0, X0, 512u)));
+    const uint32_t v2 = round_u8<HALF_EVEN>(__dp2a_lo(W1, Y1, __dp2a_lo(W0, Y0, 512u)));
+    const uint32_t v3 = round_u8<HALF_EVEN>(__dp2a_hi(W1, Y1, __dp2a_hi(W0, Y0, 512u)));
+    return v0 | (v1 << 8) | (v2 << 16) | (v3 << 24);
+}
+
+// words per pixel that hold its taps (two rows): C = 3 needs 3 aligned words per row, C = 1 and C = 4 need 2
+template <int C>
+struct TapWords {
+    static constexpr int N = (C == 3) ? 6 : 4;
+};
+// phase 1: the aligned words around the taps of one pixel (o = byte offset of tap 00 in the box)
+template <int C>
+__device__ __forceinline__ void load_taps(const uint8_t* __restrict__ box, unsigned o, uint32_t (&w)[TapWords<C>::N]) {
+    constexpr int PITCH = box_bytes(C) / 4;
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(box + (o & ~3u));
+    if constexpr (C == 3) {
+        w[0] = q[0]; w[1] = q[1]; w[2] = q[2];
+        w[3] = q[PITCH]; w[4] = q[PITCH + 1]; w[5] = q[PITCH + 2];
+    } else {
+        w[0] = q[0]; w[1] = q[1];
+        w[2] = q[PITCH]; w[3] = q[PITCH + 1];
+    }
+}
+// phase 2: blend and store the C result bytes of the pixel at dst
+template <bool HALF_EVEN, int C>
+__device__ __forceinline__ void blend_store(const uint32_t (&w)[TapWords<C>::N], unsigned o, unsigned a, unsigned b,
+                                            uint8_t* __restrict__ dst, uint32_t& W0, uint32_t& W1) {
+    if constexpr (C == 1) {
+        dst[0] = (uint8_t)blend_u8x1<HALF_EVEN>(w[0], w[1], w[2], w[3], o << 3, a, b, W0, W1);
+    } else if constexpr (C == 3) {
+        uint32_t v0, v1, v2;
+        blend_u8x3<HALF_EVEN>(w[0], w[1], w[2], w[3], w[4], w[5], o << 3, a, b, W0, W1, v0, v1, v2);
+        dst[0] = (uint8_t)v0; dst[1] = (uint8_t)v1; dst[2] = (uint8_t)v2;
+    } else {
+        *reinterpret_cast<uint32_t*>(dst) = blend_u8x4<HALF_EVEN>(w[0], w[1], w[2], w[3], a, b, W0, W1);
+    }
+}
+
 // which taps of (ix, iy) lie inside the frame, one byte each (tap order 00, 01, 10, 11)
 __device__ __forceinline__ uint32_t taps_in_frame(int ix, int iy, int H, int W) {
     const bool x0 = (unsigned)ix < (unsigned)W, x1 = (unsigned)(ix + 1) < (unsigned)W;
@@ -88,14 +158,15 @@ __device__ __forceinline__ uint32_t taps_in_frame(int ix, int iy, int H, int W) 
     return (x0 && y0 ? 1u : 0u) | (x1 && y0 ? 1u << 8 : 0u) | (x0 && y1 ? 1u << 16 : 0u) | (x1 && y1 ? 1u << 24 : 0u);
 }
 
-template <bool HALF_EVEN, int MM, bool FM, int NP, int NB, int LA>
-__global__ void __launch_bounds__((NCW + 1) * 32) warp_u8x3_ws_kernel(const __grid_constant__ Maps maps,
+template <int C, bool HALF_EVEN, int MM, bool FM, int NP, int NB, int LA>
+__global__ void __launch_bounds__((NCW + 1) * 32) warp_u8_ws_kernel(const __grid_constant__ Maps maps,
                                                                       const uint8_t* __restrict__ img,
                                                                       const uint8_t* __restrict__ pmask, float sign,
                                                                       int rule, int H, int W, unsigned tiles_x,
                                                                       unsigned tiles_per_frame, unsigned total_tiles) {
     static_assert(NP >= NB + LA + 1, "P stages must outlive the box pipeline and the output store");
-    using SM = Smem<NP, NB, MM == MM_PMASK>;
+    using SM = Smem<NP, NB, MM == MM_PMASK, C>;
+    constexpr int BWB = box_bytes(C);
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     SM& sm = *reinterpret_cast<SM*>(smem_raw);   // no static shared memory in this kernel: the window starts aligned
     if (smem_u32(smem_raw) & 127u) __trap();
@@ -168,12 +239,12 @@ __global__ void __launch_bounds__((NCW + 1) * 32) warp_u8x3_ws_kernel(const __gr
                 // centre the needed range [x0, x1 + 1] in the box (spare margin on both sides for curved flows)
                 const int needw = x1 + 2 - x0, needh = y1 + 2 - y0;
                 const int vx0 = x0 - max(0, (48 - needw) / 2);
-                const int bx0 = (3 * vx0) & ~15;             // 16-byte aligned box start, in bytes of the 3*W-byte row
+                const int bx0 = (C * vx0) & ~15;             // 16-byte aligned box start, in bytes of the C*W-byte row
                 const int mx0 = vx0 & ~15;
                 const int by0 = y0 - max(0, (BH - needh) / 2);
                 if (i >= NB) mbar_wait(&sm.bempty[b], b_ph ^ 1);
                 // every tap of a pixel covered by a box that lies inside the frame is inside the frame
-                const int inframe = (bx0 >= 0 && bx0 + BWB <= 3 * W && by0 >= 0 && by0 + BH <= H) ? 1 : 0;
+                const int inframe = (bx0 >= 0 && bx0 + BWB <= C * W && by0 >= 0 && by0 + BH <= H) ? 1 : 0;
                 sm.binfo[b][0] = make_int4(bx0, mx0, by0, inframe);
                 sm.binfo[b][1] = make_int4(tx0, ty0, n, 0);
                 mbar_expect_tx(&sm.bfull[b], B_BYTES);
@@ -191,7 +262,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32) warp_u8x3_ws_kernel(const __gr
     // ---------------------------------------------------------------------------------------------- consumer warps
     const unsigned s_pass = rule == OFK_RULE_STRICT ? 1024u : (rule == OFK_RULE_GT_HALF ? 513u : 512u);   // S >= s_pass
     const unsigned own = wrp * 4 * TS + lane;          // this thread's pixel in row 4w of a tile (+ j * TS)
-    const unsigned own3 = wrp * 4 * TS * 8 + lane * 3; // byte offset of its first output byte in the flow tile (+ j * 96)
+    const unsigned own3 = wrp * 4 * TS * 8 + lane * C; // byte offset of its first output byte in the flow tile (+ j * 32 * C)
     unsigned s = 0, s_ph = 0, b = 0, b_ph = 0;
     int prev_s = -1;
     for (unsigned i = 0; i < T; ++i) {
@@ -219,22 +290,19 @@ __global__ void __launch_bounds__((NCW + 1) * 32) warp_u8x3_ws_kernel(const __gr
             const QCoord qx = quantise_fast(X), qy = quantise_fast(Y);
             ixs[j] = qx.i; iys[j] = qy.i;
             fa[j] = (unsigned)qx.f; fb[j] = (unsigned)qy.f;
-            dxb[j] = 3 * qx.i - info.x;
+            dxb[j] = C * qx.i - info.x;
             dy[j] = qy.i - info.z;
             // Covered by the box? Everything else is decided per pixel. No range test is needed for the fast quantiser:
             // it is exact for |X| < 2^17, and beyond that (or for NaN / Inf) the integer it produces is far outside
             // [-2^16, 2^16], so such a pixel can never pass the box test (frames are smaller than 32768).
-            ok = ok && (unsigned)dxb[j] <= (unsigned)(BWB - 6) && (unsigned)dy[j] <= (unsigned)(BH - 2);
+            ok = ok && (unsigned)dxb[j] <= (unsigned)(BWB - 2 * C) && (unsigned)dy[j] <= (unsigned)(BH - 2);
         }
         if (__all_sync(0xffffffffu, ok)) {
-            uint32_t w[4][6];
+            uint32_t w[4][TapWords<C>::N];
             uint32_t mt[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const unsigned o = (unsigned)(dy[j] * BWB + dxb[j]);
-                const uint32_t* q = reinterpret_cast<const uint32_t*>(bs.img + (o & ~3u));
-                w[j][0] = q[0]; w[j][1] = q[1]; w[j][2] = q[2];
-                w[j][3] = q[BWB / 4]; w[j][4] = q[BWB / 4 + 1]; w[j][5] = q[BWB / 4 + 2];
+                load_taps<C>(bs.img, (unsigned)(dy[j] * BWB + dxb[j]), w[j]);
                 if (MM == MM_PMASK) {
                     const uint8_t* mm = bs.m + (dy[j] * BMW + (ixs[j] - info.y));
                     mt[j] = (uint32_t)mm[0] | ((uint32_t)mm[1] << 8) | ((uint32_t)mm[BMW] << 16) |
@@ -244,18 +312,13 @@ __global__ void __launch_bounds__((NCW + 1) * 32) warp_u8x3_ws_kernel(const __gr
             // everything loaded from the box is consumed by the reduction below before the stage is handed back
             unsigned dep = 0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dep |= w[j][5] | (MM == MM_PMASK ? mt[j] : 0u);
+            for (int j = 0; j < 4; ++j) dep |= w[j][TapWords<C>::N - 1] | (MM == MM_PMASK ? mt[j] : 0u);
             dep = __reduce_or_sync(0xffffffffu, dep);
             if (lane == 0) mbar_arrive_after(&sm.bempty[b], dep);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const unsigned o = (unsigned)(dy[j] * BWB + dxb[j]);
-                uint32_t W0, W1, v0, v1, v2;
-                blend_u8x3<HALF_EVEN>(w[j][0], w[j][1], w[j][2], w[j][3], w[j][4], w[j][5], o << 3, fa[j], fb[j], W0, W1,
-                                      v0, v1, v2);
-                orow[j * 96 + 0] = (uint8_t)v0;
-                orow[j * 96 + 1] = (uint8_t)v1;
-                orow[j * 96 + 2] = (uint8_t)v2;
+                uint32_t W0, W1;
+                blend_store<HALF_EVEN, C>(w[j], (unsigned)(dy[j] * BWB + dxb[j]), fa[j], fb[j], orow + j * (TS * C), W0, W1);
                 if (MM == MM_PMASK) {
                     const unsigned valid = __dp2a_hi(W1, mt[j], __dp2a_lo(W0, mt[j], 0u)) >= s_pass;
                     mrow[j * TS] = (uint8_t)(valid & fmv[j]);
@@ -274,15 +337,14 @@ __global__ void __launch_bounds__((NCW + 1) * 32) warp_u8x3_ws_kernel(const __gr
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float X = __fmaf_rn(sign, f[j].x, xg), Y = __fmaf_rn(sign, f[j].y, yg + (float)j);
-                const bool inbox = (unsigned)dxb[j] <= (unsigned)(BWB - 6) && (unsigned)dy[j] <= (unsigned)(BH - 2);
-                uint32_t v0, v1, v2;
+                const bool inbox = (unsigned)dxb[j] <= (unsigned)(BWB - 2 * C) && (unsigned)dy[j] <= (unsigned)(BH - 2);
+                uint8_t* dst = orow + j * (TS * C);
                 unsigned valid;
                 if (inbox) {
                     const unsigned o = (unsigned)(dy[j] * BWB + dxb[j]);
-                    const uint32_t* q = reinterpret_cast<const uint32_t*>(bs.img + (o & ~3u));
-                    uint32_t W0, W1;
-                    blend_u8x3<HALF_EVEN>(q[0], q[1], q[2], q[BWB / 4], q[BWB / 4 + 1], q[BWB / 4 + 2], o << 3, fa[j], fb[j],
-                                          W0, W1, v0, v1, v2);
+                    uint32_t wj[TapWords<C>::N], W0, W1;
+                    load_taps<C>(bs.img, o, wj);
+                    blend_store<HALF_EVEN, C>(wj, o, fa[j], fb[j], dst, W0, W1);
                     uint32_t in;
                     if (MM == MM_PMASK) {
                         const uint8_t* mm = bs.m + (dy[j] * BMW + (ixs[j] - info.y));
@@ -293,16 +355,16 @@ __global__ void __launch_bounds__((NCW + 1) * 32) warp_u8x3_ws_kernel(const __gr
                     }
                     valid = __dp2a_hi(W1, in, __dp2a_lo(W0, in, 0u)) >= s_pass;
                 } else if (X <= -1.0f || Y <= -1.0f || X >= (float)W || Y >= (float)H) {
-                    v0 = v1 = v2 = 0u; valid = 0u;       // every tap lies outside the frame
+#pragma unroll
+                    for (int c = 0; c < C; ++c) dst[c] = 0;      // every tap lies outside the frame
+                    valid = 0u;
                 } else {
-                    const uint32_t r = border_px_u8x3(img + fbase * 3, MM == MM_PMASK ? pmask + fbase : nullptr, X, Y, H,
-                                                      W, HALF_EVEN, rule);
-                    v0 = r & 0xffu; v1 = (r >> 8) & 0xffu; v2 = (r >> 16) & 0xffu;
-                    valid = r >> 24;
+                    const unsigned long long r = border_px_u8c<C>(img + fbase * C, MM == MM_PMASK ? pmask + fbase : nullptr,
+                                                                  X, Y, H, W, HALF_EVEN, rule);
+#pragma unroll
+                    for (int c = 0; c < C; ++c) dst[c] = (uint8_t)(r >> (8 * c));
+                    valid = (unsigned)(r >> 32);
                 }
-                orow[j * 96 + 0] = (uint8_t)v0;
-                orow[j * 96 + 1] = (uint8_t)v1;
-                orow[j * 96 + 2] = (uint8_t)v2;
                 if (MM != MM_NONE) mrow[j * TS] = (uint8_t)(valid & fmv[j] & 1u);
             }
             __syncwarp();
@@ -312,7 +374,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32) warp_u8x3_ws_kernel(const __gr
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-            tma_store_3d(&maps.oi, ps.f + (int)wrp * 4 * TS, 3 * tx0, ty0 + (int)wrp * 4, n);
+            tma_store_3d(&maps.oi, ps.f + (int)wrp * 4 * TS, C * tx0, ty0 + (int)wrp * 4, n);
             if (MM != MM_NONE) tma_store_3d(&maps.om, ps.fm + (int)wrp * 4 * TS, tx0, ty0 + (int)wrp * 4, n);
             bulk_commit();
             if (prev_s >= 0) {
@@ -329,14 +391,14 @@ __global__ void __launch_bounds__((NCW + 1) * 32) warp_u8x3_ws_kernel(const __gr
 
 constexpr int WS_NP = 6, WS_NB = 2, WS_LA = 3;
 
-template <bool HALF_EVEN, int MM, bool FM>
+template <int C, bool HALF_EVEN, int MM, bool FM>
 static int launch_variant(const Maps& maps, const uint8_t* img, const uint8_t* pmask, float sign, int rule, int H, int W,
                           unsigned tx, unsigned ty, unsigned total, int ctas_per_sm, cudaStream_t st) {
-    using SM = Smem<WS_NP, WS_NB, MM == MM_PMASK>;
+    using SM = Smem<WS_NP, WS_NB, MM == MM_PMASK, C>;
     static bool attr_done_dev[64] = {false};   // the attribute is per device
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
-    auto kernel = warp_u8x3_ws_kernel<HALF_EVEN, MM, FM, WS_NP, WS_NB, WS_LA>;
+    auto kernel = warp_u8_ws_kernel<C, HALF_EVEN, MM, FM, WS_NP, WS_NB, WS_LA>;
     if (!attr_done_dev[dev]) {
         if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM)) != cudaSuccess) {
             cudaGetLastError();
@@ -359,33 +421,16 @@ static int launch_variant(const Maps& maps, const uint8_t* img, const uint8_t* p
     return 1;
 }
 
-}  // namespace wtws
-
-bool warp_ws_enabled() {
-    static int state = -1;
-    if (state < 0) {
-        const char* e = getenv("OFK_WARP_WS");
-        state = (e != nullptr && e[0] == '0') ? 0 : 1;
-    }
-    return state == 1;
-}
-
-// Returns 1 if the kernel was launched, 0 if the configuration is not eligible (caller uses the gather kernel),
-// negative OFK_E* on error.
-int launch_warp_u8x3_ws(bool half_even, const void* payload, const float* flow, float sign, const uint8_t* pmask,
-                        const uint8_t* fmask, void* out, uint8_t* omask, int rule, int N, int H, int W,
-                        cudaStream_t st) {
-    using namespace wtws;
-    if (W % 16 != 0 || H >= 32768 || W >= 32768) return 0;    // 16-byte row pitch of the uint8 tensors
-    const uintptr_t align = reinterpret_cast<uintptr_t>(payload) | reinterpret_cast<uintptr_t>(flow) |
-                            reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(omask) |
-                            reinterpret_cast<uintptr_t>(pmask) | reinterpret_cast<uintptr_t>(fmask);
-    if (align & 15) return 0;
+template <int C>
+static int launch_channels(bool half_even, const void* payload, const float* flow, float sign, const uint8_t* pmask,
+                           const uint8_t* fmask, void* out, uint8_t* omask, int rule, int N, int H, int W,
+                           cudaStream_t st) {
     const int mm = omask == nullptr ? MM_NONE : (pmask != nullptr ? MM_PMASK : MM_GEOM);
     const bool fm = omask != nullptr && fmask != nullptr;
     Maps maps;
-    if (!make_map3(&maps.f, flow, 8, W, H, N, TS, TS) || !make_map3(&maps.ib, payload, 1, (size_t)W * 3, H, N, BWB, BH) ||
-        !make_map3(&maps.oi, out, 1, (size_t)W * 3, H, N, 96, 4))
+    if (!make_map3(&maps.f, flow, 8, W, H, N, TS, TS) ||
+        !make_map3(&maps.ib, payload, 1, (size_t)W * C, H, N, box_bytes(C), BH) ||
+        !make_map3(&maps.oi, out, 1, (size_t)W * C, H, N, TS * C, 4))
         return 0;
     maps.fm = maps.pmb = maps.om = maps.f;
     if (fm && !make_map3(&maps.fm, fmask, 1, W, H, N, TS, TS)) return 0;
@@ -401,7 +446,8 @@ int launch_warp_u8x3_ws(bool half_even, const void* payload, const float* flow, 
         if (cps < 1 || cps > 4) cps = 3;
     }
     int rc;
-#define OFK_WV(HE, MMV, FMV) rc = launch_variant<HE, MMV, FMV>(maps, (const uint8_t*)payload, pmask, sign, rule, H, W, tx, ty, total, cps, st)
+#define OFK_WV(HE, MMV, FMV) \
+    rc = launch_variant<C, HE, MMV, FMV>(maps, (const uint8_t*)payload, pmask, sign, rule, H, W, tx, ty, total, cps, st)
 #define OFK_WV_HE(MMV, FMV)            \
     do {                               \
         if (half_even) OFK_WV(true, MMV, FMV);  \
@@ -412,6 +458,37 @@ int launch_warp_u8x3_ws(bool half_even, const void* payload, const float* flow, 
     else { if (fm) OFK_WV_HE(MM_PMASK, true); else OFK_WV_HE(MM_PMASK, false); }
 #undef OFK_WV_HE
 #undef OFK_WV
+    return rc;
+}
+
+}  // namespace wtws
+
+bool warp_ws_enabled() {
+    static int state = -1;
+    if (state < 0) {
+        const char* e = getenv("OFK_WARP_WS");
+        state = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return state == 1;
+}
+
+// uint8 images with C = 1, 3 or 4 interleaved channels. Returns 1 if the kernel was launched, 0 if the configuration
+// is not eligible (caller uses the gather kernels), negative OFK_E* on error.
+int launch_warp_u8_ws(int C, bool half_even, const void* payload, const float* flow, float sign, const uint8_t* pmask,
+                      const uint8_t* fmask, void* out, uint8_t* omask, int rule, int N, int H, int W, cudaStream_t st) {
+    using namespace wtws;
+    if (W % 16 != 0 || H >= 32768 || W >= 32768) return 0;    // 16-byte row pitch of the uint8 tensors
+    const uintptr_t align = reinterpret_cast<uintptr_t>(payload) | reinterpret_cast<uintptr_t>(flow) |
+                            reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(omask) |
+                            reinterpret_cast<uintptr_t>(pmask) | reinterpret_cast<uintptr_t>(fmask);
+    if (align & 15) return 0;
+    int rc;
+    switch (C) {
+        case 1: rc = launch_channels<1>(half_even, payload, flow, sign, pmask, fmask, out, omask, rule, N, H, W, st); break;
+        case 3: rc = launch_channels<3>(half_even, payload, flow, sign, pmask, fmask, out, omask, rule, N, H, W, st); break;
+        case 4: rc = launch_channels<4>(half_even, payload, flow, sign, pmask, fmask, out, omask, rule, N, H, W, st); break;
+        default: return 0;
+    }
     if (rc != 1) return rc;
     OFK_LAUNCHED();
     return 1;

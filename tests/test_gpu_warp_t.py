@@ -514,6 +514,18 @@ def test_tma_kernels_randomized(of):
                 w2, m2 = R.apply(ra, img[i], return_valid_area=True, consider_mask=False)
                 same(w1, w2)
                 same(m1, m2)
+                for chans in (0, 1, 4):                                                        # grey (2-D), 1 and 4 channels
+                    im = img[i, ..., 0] if chans == 0 else np.ascontiguousarray(
+                        np.concatenate([img[i], img[i][..., :1]], -1)[..., :chans])
+                    same(fa.apply(im), R.apply(ra, im))
+                    w1, m1 = fa.apply(im, return_valid_area=True)
+                    w2, m2 = R.apply(ra, im, return_valid_area=True)
+                    same(w1, w2)
+                    same(m1, m2)
+                    w1, m1 = fa.apply(im, target_mask=bm[i], return_valid_area=True)
+                    w2, m2 = R.apply(ra, im, target_mask=bm[i], return_valid_area=True)
+                    same(w1, w2)
+                    same(m1, m2)
                 res = fa.apply(of.Flow(b[i], 't', bm[i]))                                      # flow warped by flow
                 want = R.apply(ra, R.make(b[i], 't', bm[i]))
                 same(res.mask, want.mask)

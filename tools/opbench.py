@@ -92,6 +92,21 @@ timeit("apply 't' u8x3 + target mask + valid (17 B/px)", 17,
 timeit("apply 't' f32x3 (32 B/px)", 32,
        lambda: c('ofk_warp_t', imgf.ptr, _lib.F32, 3, _lib.ARITH_NATIVE, fa.vecs.ptr, -1.0, None, None, o_imgf.ptr, None,
                  _lib.RULE_STRICT, N, H, W, H, W, 0, 0, 1, s))
+img1c = DeviceArray.empty((N, H, W, 1), np.uint8)
+o_img1c = DeviceArray.empty((N, H, W, 1), np.uint8)
+img4c = DeviceArray.empty((N, H, W, 4), np.uint8)
+o_img4c = DeviceArray.empty((N, H, W, 4), np.uint8)
+imgf1 = DeviceArray.empty((N, H, W, 1), np.float32)
+o_imgf1 = DeviceArray.empty((N, H, W, 1), np.float32)
+timeit("apply 't' u8x1 + valid area (8+1+1+1+1 = 12 B/px)", 12,
+       lambda: c('ofk_warp_t', img1c.ptr, _lib.U8, 1, _lib.ARITH_RINT, fa.vecs.ptr, -1.0, None, fa.masks.ptr, o_img1c.ptr,
+                 o_m.ptr, _lib.RULE_GT_HALF, N, H, W, H, W, 0, 0, 1, s))
+timeit("apply 't' u8x4 (8+4+4 = 16 B/px)", 16,
+       lambda: c('ofk_warp_t', img4c.ptr, _lib.U8, 4, _lib.ARITH_NATIVE, fa.vecs.ptr, -1.0, None, None, o_img4c.ptr, None,
+                 _lib.RULE_STRICT, N, H, W, H, W, 0, 0, 1, s))
+timeit("apply 't' f32x1 + valid area (8+4+4+1+1 = 18 B/px)", 18,
+       lambda: c('ofk_warp_t', imgf1.ptr, _lib.F32, 1, _lib.ARITH_NATIVE, fa.vecs.ptr, -1.0, None, fa.masks.ptr, o_imgf1.ptr,
+                 o_m.ptr, _lib.RULE_STRICT, N, H, W, H, W, 0, 0, 1, s))
 timeit("Flow.apply(Flow) 't' (27 B/px)", 27,
        lambda: c('ofk_warp_t', fb.vecs.ptr, _lib.F32, 2, _lib.ARITH_NATIVE, fa.vecs.ptr, -1.0, fb.masks.ptr, fa.masks.ptr,
                  o_v.ptr, o_m.ptr, _lib.RULE_STRICT, N, H, W, H, W, 0, 0, 1, s))
