@@ -91,7 +91,7 @@ __device__ __forceinline__ void quant(float X, int& i, int& f) {
 }
 
 // exact per-pixel path from global memory (any coordinates); returns sample in (u, v) and strict validity
-__device__ __noinline__ float4 slow_sample(const float2* __restrict__ G, const uint8_t* __restrict__ Gm, int H, int W,
+__device__ __forceinline__ float4 slow_sample(const float2* __restrict__ G, const uint8_t* __restrict__ Gm, int H, int W,
                                            float X, float Y) {
     int sx = __float2int_rn(X * 32.0f), sy = __float2int_rn(Y * 32.0f);
     const int ix = max(-32768, min(32767, sx >> 5)), iy = max(-32768, min(32767, sy >> 5));
