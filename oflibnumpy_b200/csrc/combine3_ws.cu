@@ -29,6 +29,20 @@ namespace ofk {
 namespace c3ws {
 using namespace ws;
 
+#ifdef OFK_TRACE   // timeline instrumentation for tools/exp_trace.cu (never defined in the library build)
+__device__ unsigned long long* g_trace = nullptr;   // [tile][16] global-timer stamps of CTA 0
+__device__ __forceinline__ void trace(unsigned tile, int slot) {
+    if (blockIdx.x == 0 && g_trace != nullptr && tile < 512) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_trace[tile * 16 + slot] = t;
+    }
+}
+#define OFK_TR(tile, slot) trace(tile, slot)
+#else
+#define OFK_TR(tile, slot)
+#endif
+
 constexpr int TS = 32;
 constexpr int BW = 48, BH = 48;   // vector box (pixels)
 constexpr int BMW = 64;           // mask box width (bytes): start is aligned down to 16
@@ -122,7 +136,7 @@ __device__ __forceinline__ float4 slow_sample(const float2* __restrict__ G, cons
 
 // ADD: out = P + Q(G, ...) (composition); otherwise out = Q(G, ...) alone (Flow.apply of a flow: ofk_warp_t, float32 x2)
 template <bool MASKS, bool ADD, int NP, int NB, int LA>
-__global__ void __launch_bounds__((NCW + 1) * 32) c3_ws_kernel(const __grid_constant__ Maps maps,
+__global__ void __launch_bounds__((NCW + 1) * 32, 2) c3_ws_kernel(const __grid_constant__ Maps maps,
                                                                const float2* __restrict__ G,
                                                                const uint8_t* __restrict__ Gm, float sign,
                                                                int H, int W, unsigned tiles_x, unsigned tiles_per_frame,
@@ -169,34 +183,30 @@ __global__ void __launch_bounds__((NCW + 1) * 32) c3_ws_kernel(const __grid_cons
         for (unsigned i = 0; i < T; ++i) {
             const int tx0 = bit.tx * TS, ty0 = bit.ty * TS, n = bit.n;
             bit.advance((int)tiles_x, tiles_y);
+            if (lane == 0) OFK_TR(i, 0);
             mbar_wait(&sm.pfull[s], s_ph);
-            // sample positions along the tile perimeter and two interior rows (lane = column for the rows, lane = row
-            // for the two columns): exact for affine fields, an estimate otherwise (consumers verify per pixel)
-            const float2* p = sm.ps[s].p;
-            float mnx = 1e30f, mxx = -1e30f, mny = 1e30f, mxy = -1e30f;
-            auto acc = [&](int r, int c) {
+            if (lane == 0) OFK_TR(i, 1);
+            // Sample positions on a 4 x 4 grid over the tile (corners included): exact bounding box for affine fields, an
+            // estimate otherwise (consumers verify per pixel). One shared-memory load per lane, four integer warp
+            // reductions (REDUX): the producer's serial time per tile is what paces the whole pipeline.
+            int x0, x1, y0, y1;
+            {
+                const int r = (int)(((lane >> 2) & 3) * 31 + 1) / 3, c = (int)((lane & 3) * 31 + 1) / 3;   // 0, 10, 21, 31
                 const int x = tx0 + c, y = ty0 + r;
+                int fx0 = 0x7fffffff, fx1 = -0x7fffffff, fy0 = 0x7fffffff, fy1 = -0x7fffffff;
                 if (x < W && y < H) {
-                    const float2 v = p[r * TS + c];
-                    const float X = __fmaf_rn(sign, v.x, (float)x), Y = __fmaf_rn(sign, v.y, (float)y);
-                    mnx = fminf(mnx, X); mxx = fmaxf(mxx, X);
-                    mny = fminf(mny, Y); mxy = fmaxf(mxy, Y);
+                    const float2 v = sm.ps[s].p[r * TS + c];
+                    const float lim = 60000.f;
+                    const float X = fminf(fmaxf(__fmaf_rn(sign, v.x, (float)x), -lim), lim);
+                    const float Y = fminf(fmaxf(__fmaf_rn(sign, v.y, (float)y), -lim), lim);
+                    fx0 = fx1 = __float2int_rd(X);
+                    fy0 = fy1 = __float2int_rd(Y);
                 }
-            };
-            acc(0, lane); acc(10, lane); acc(21, lane); acc(31, lane);
-            acc(lane, 0); acc(lane, 31);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
-                mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
-                mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
-                mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+                x0 = __reduce_min_sync(0xffffffffu, fx0); x1 = __reduce_max_sync(0xffffffffu, fx1);
+                y0 = __reduce_min_sync(0xffffffffu, fy0); y1 = __reduce_max_sync(0xffffffffu, fy1);
             }
             if (lane == 0) {
                 // integer tap range, clamped to the taps that can contribute: ix in [-1, W-1], iy in [-1, H-1]
-                const float lim = 60000.f;
-                int x0 = (int)floorf(fminf(fmaxf(mnx, -lim), lim)), x1 = (int)floorf(fminf(fmaxf(mxx, -lim), lim));
-                int y0 = (int)floorf(fminf(fmaxf(mny, -lim), lim)), y1 = (int)floorf(fminf(fmaxf(mxy, -lim), lim));
                 x0 = max(-1, min(W - 1, x0)); x1 = max(-1, min(W - 1, x1));
                 y0 = max(-1, min(H - 1, y0)); y1 = max(-1, min(H - 1, y1));
                 // centre the needed range [x0, x1 + 1] in the box (spare margin on both sides for curved flows)
@@ -205,13 +215,17 @@ __global__ void __launch_bounds__((NCW + 1) * 32) c3_ws_kernel(const __grid_cons
                 vx0 &= ~1;                                   // 16-byte aligned box start (float2 elements)
                 const int by0 = y0 - max(0, (BH - needh) / 2);
                 const int mx0 = vx0 & ~15;
+                OFK_TR(i, 2);
                 if (i >= NB) mbar_wait(&sm.bempty[b], b_ph ^ 1);
+                OFK_TR(i, 3);
                 sm.binfo[b][0] = make_int4(vx0, vx0 - mx0, by0, 0);
                 sm.binfo[b][1] = make_int4(tx0, ty0, n, 0);
                 mbar_expect_tx(&sm.bfull[b], B_BYTES);
                 tma_load_3d(sm.bs[b].v, &maps.gb, &sm.bfull[b], vx0, by0, n);
                 if (MASKS) tma_load_3d(sm.bs[b].m, &maps.gmb, &sm.bfull[b], mx0, by0, n);
+                OFK_TR(i, 4);
                 if (i + LA < T) issue_p(i + LA >= NP);
+                OFK_TR(i, 5);
             }
             __syncwarp();
             if (++s == NP) { s = 0; s_ph ^= 1; }
@@ -225,8 +239,12 @@ __global__ void __launch_bounds__((NCW + 1) * 32) c3_ws_kernel(const __grid_cons
     unsigned s = 0, s_ph = 0, b = 0, b_ph = 0;
     int prev_s = -1;
     for (unsigned i = 0; i < T; ++i) {
+        if (lane == 0 && wrp == 0) OFK_TR(i, 8);
+        if (lane == 0 && wrp == 7) OFK_TR(i, 12);
         mbar_wait(&sm.bfull[b], b_ph);
         mbar_wait(&sm.pfull[s], s_ph);
+        if (lane == 0 && wrp == 0) OFK_TR(i, 9);
+        if (lane == 0 && wrp == 7) OFK_TR(i, 13);
         const int4 info = sm.binfo[b][0], tile = sm.binfo[b][1];
         typename SM::PStage& ps = sm.ps[s];
         const typename SM::BStage& bs = sm.bs[b];
@@ -285,6 +303,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32) c3_ws_kernel(const __grid_cons
             }
             dep = __reduce_or_sync(0xffffffffu, dep);
             if (lane == 0) mbar_arrive_after(&sm.bempty[b], dep);
+            if (lane == 0 && wrp == 0) OFK_TR(i, 10);
+            if (lane == 0 && wrp == 7) OFK_TR(i, 14);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const unsigned a = fa[j], bb = fb[j];
@@ -354,6 +374,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32) c3_ws_kernel(const __grid_cons
                 mbar_arrive(&sm.pempty[prev_s]);
             }
         }
+        if (lane == 0 && wrp == 0) OFK_TR(i, 11);
+        if (lane == 0 && wrp == 7) OFK_TR(i, 15);
         prev_s = (int)s;
         if (++s == NP) { s = 0; s_ph ^= 1; }
         if (++b == NB) { b = 0; b_ph ^= 1; }

@@ -159,7 +159,7 @@ __device__ __forceinline__ uint32_t taps_in_frame(int ix, int iy, int H, int W) 
 }
 
 template <int C, bool HALF_EVEN, int MM, bool FM, int NP, int NB, int LA>
-__global__ void __launch_bounds__((NCW + 1) * 32) warp_u8_ws_kernel(const __grid_constant__ Maps maps,
+__global__ void __launch_bounds__((NCW + 1) * 32, 3) warp_u8_ws_kernel(const __grid_constant__ Maps maps,
                                                                       const uint8_t* __restrict__ img,
                                                                       const uint8_t* __restrict__ pmask, float sign,
                                                                       int rule, int H, int W, unsigned tiles_x,
@@ -207,33 +207,27 @@ __global__ void __launch_bounds__((NCW + 1) * 32) warp_u8_ws_kernel(const __grid
             const int tx0 = bit.tx * TS, ty0 = bit.ty * TS, n = bit.n;
             bit.advance((int)tiles_x, tiles_y);
             mbar_wait(&sm.pfull[s], s_ph);
-            // sample positions along the tile perimeter and two interior rows (lane = column for the rows, lane = row
-            // for the two columns): exact for affine fields, an estimate otherwise (consumers verify per pixel)
-            const float2* p = sm.ps[s].f;
-            float mnx = 1e30f, mxx = -1e30f, mny = 1e30f, mxy = -1e30f;
-            auto acc = [&](int r, int c) {
+            // Sample positions on a 4 x 4 grid over the tile (corners included): exact bounding box for affine fields, an
+            // estimate otherwise (consumers verify per pixel). One shared-memory load per lane, four integer warp
+            // reductions (REDUX): the producer's serial time per tile is what paces the whole pipeline.
+            int x0, x1, y0, y1;
+            {
+                const int r = (int)(((lane >> 2) & 3) * 31 + 1) / 3, c = (int)((lane & 3) * 31 + 1) / 3;   // 0, 10, 21, 31
                 const int x = tx0 + c, y = ty0 + r;
+                int fx0 = 0x7fffffff, fx1 = -0x7fffffff, fy0 = 0x7fffffff, fy1 = -0x7fffffff;
                 if (x < W && y < H) {
-                    const float2 v = p[r * TS + c];
-                    const float X = __fmaf_rn(sign, v.x, (float)x), Y = __fmaf_rn(sign, v.y, (float)y);
-                    mnx = fminf(mnx, X); mxx = fmaxf(mxx, X);
-                    mny = fminf(mny, Y); mxy = fmaxf(mxy, Y);
+                    const float2 v = sm.ps[s].f[r * TS + c];
+                    const float lim = 60000.f;
+                    const float X = fminf(fmaxf(__fmaf_rn(sign, v.x, (float)x), -lim), lim);
+                    const float Y = fminf(fmaxf(__fmaf_rn(sign, v.y, (float)y), -lim), lim);
+                    fx0 = fx1 = __float2int_rd(X);
+                    fy0 = fy1 = __float2int_rd(Y);
                 }
-            };
-            acc(0, lane); acc(10, lane); acc(21, lane); acc(31, lane);
-            acc(lane, 0); acc(lane, 31);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
-                mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
-                mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
-                mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+                x0 = __reduce_min_sync(0xffffffffu, fx0); x1 = __reduce_max_sync(0xffffffffu, fx1);
+                y0 = __reduce_min_sync(0xffffffffu, fy0); y1 = __reduce_max_sync(0xffffffffu, fy1);
             }
             if (lane == 0) {
                 // integer tap range, clamped to the taps that can contribute: ix in [-1, W-1], iy in [-1, H-1]
-                const float lim = 60000.f;
-                int x0 = (int)floorf(fminf(fmaxf(mnx, -lim), lim)), x1 = (int)floorf(fminf(fmaxf(mxx, -lim), lim));
-                int y0 = (int)floorf(fminf(fmaxf(mny, -lim), lim)), y1 = (int)floorf(fminf(fmaxf(mxy, -lim), lim));
                 x0 = max(-1, min(W - 1, x0)); x1 = max(-1, min(W - 1, x1));
                 y0 = max(-1, min(H - 1, y0)); y1 = max(-1, min(H - 1, y1));
                 // centre the needed range [x0, x1 + 1] in the box (spare margin on both sides for curved flows)
