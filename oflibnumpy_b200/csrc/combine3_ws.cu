@@ -135,8 +135,8 @@ __device__ __forceinline__ float4 slow_sample(const float2* __restrict__ G, cons
 }
 
 // ADD: out = P + Q(G, ...) (composition); otherwise out = Q(G, ...) alone (Flow.apply of a flow: ofk_warp_t, float32 x2)
-template <bool MASKS, bool ADD, int NP, int NB, int LA>
-__global__ void __launch_bounds__((NCW + 1) * 32, 2) c3_ws_kernel(const __grid_constant__ Maps maps,
+template <bool MASKS, bool ADD, int NP, int NB, int LA, int PW>
+__global__ void __launch_bounds__((NCW + PW) * 32, 2) c3_ws_kernel(const __grid_constant__ Maps maps,
                                                                const float2* __restrict__ G,
                                                                const uint8_t* __restrict__ Gm, float sign,
                                                                int H, int W, unsigned tiles_x, unsigned tiles_per_frame,
@@ -161,6 +161,27 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 2) c3_ws_kernel(const __grid_c
     }
     __syncthreads();
 
+    if (PW == 2 && wrp == NCW + 1) {
+        // -------------------------------------------------------------------------------------------- P loader warp
+        // Streams the pointwise tiles into the ring of P stages as fast as stages are released: independent of the
+        // box pipeline, so neither the box warp nor the consumers ever wait for a P request to be issued.
+        if (lane == 0) {
+            const int tiles_y = (int)(tiles_per_frame / tiles_x);
+            TileIter pit;
+            pit.init(first, stride, (int)tiles_x, tiles_y);
+            unsigned ps_i = 0, ps_ph = 0;
+            for (unsigned i = 0; i < T; ++i) {
+                const int tx0 = pit.tx * TS, ty0 = pit.ty * TS, n = pit.n;
+                pit.advance((int)tiles_x, tiles_y);
+                if (i >= NP) mbar_wait(&sm.pempty[ps_i], ps_ph ^ 1);
+                mbar_expect_tx(&sm.pfull[ps_i], P_BYTES);
+                tma_load_3d(sm.ps[ps_i].p, &maps.p, &sm.pfull[ps_i], tx0, ty0, n);
+                if (MASKS) tma_load_3d(sm.ps[ps_i].pm, &maps.pm, &sm.pfull[ps_i], tx0, ty0, n);
+                if (++ps_i == NP) { ps_i = 0; ps_ph ^= 1; }
+            }
+        }
+        return;
+    }
     if (wrp == NCW) {
         // ------------------------------------------------------------------------------------------ producer warp
         const int tiles_y = (int)(tiles_per_frame / tiles_x);
@@ -177,7 +198,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 2) c3_ws_kernel(const __grid_c
             if (MASKS) tma_load_3d(sm.ps[ps_i].pm, &maps.pm, &sm.pfull[ps_i], tx0, ty0, n);
             if (++ps_i == NP) { ps_i = 0; ps_ph ^= 1; }
         };
-        if (lane == 0)
+        if (PW == 1 && lane == 0)
             for (unsigned k = 0; k < (unsigned)LA && k < T; ++k) issue_p(false);
         unsigned s = 0, s_ph = 0, b = 0, b_ph = 0;
         for (unsigned i = 0; i < T; ++i) {
@@ -224,7 +245,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 2) c3_ws_kernel(const __grid_c
                 tma_load_3d(sm.bs[b].v, &maps.gb, &sm.bfull[b], vx0, by0, n);
                 if (MASKS) tma_load_3d(sm.bs[b].m, &maps.gmb, &sm.bfull[b], mx0, by0, n);
                 OFK_TR(i, 4);
-                if (i + LA < T) issue_p(i + LA >= NP);
+                if (PW == 1 && i + LA < T) issue_p(i + LA >= NP);
                 OFK_TR(i, 5);
             }
             __syncwarp();
@@ -449,7 +470,8 @@ __global__ void __launch_bounds__(256) c3_scan_nonzero(const float2* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-constexpr int WS_NP = 6, WS_NB = 2, WS_LA = 3;   // measured best on B200 (profiles/): 6 P stages, 2 boxes, P 3 tiles ahead
+constexpr int WS_NP = 5, WS_NB = 3, WS_LA = 1;   // 5 P stages, 3 box stages (LA only matters with a single producer warp)
+constexpr int WS_PW = 2;                         // producer warps: box warp + P loader warp
 
 }  // namespace c3ws
 
@@ -509,14 +531,14 @@ int launch_combine3_ws(const float* P, const uint8_t* Pm, const float* G, const 
         if (cudaGetDevice(&dev_) != cudaSuccess || dev_ < 0 || dev_ >= 64) return 0;                                  \
         bool& attr_done = attr_done_dev[dev_];                                                                        \
         if (!attr_done) {                                                                                             \
-            if (cudaFuncSetAttribute(c3_ws_kernel<MK, AD, WS_NP, WS_NB, WS_LA>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+            if (cudaFuncSetAttribute(c3_ws_kernel<MK, AD, WS_NP, WS_NB, WS_LA, WS_PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      (int)smem) != cudaSuccess) {                                                     \
                 cudaGetLastError();                                                                                   \
                 return 0;                                                                                             \
             }                                                                                                         \
             attr_done = true;                                                                                         \
         }                                                                                                             \
-        c3_ws_kernel<MK, AD, WS_NP, WS_NB, WS_LA><<<grid, (NCW + 1) * 32, smem, st>>>(                                    \
+        c3_ws_kernel<MK, AD, WS_NP, WS_NB, WS_LA, WS_PW><<<grid, (NCW + WS_PW) * 32, smem, st>>>(                                    \
             maps, (const float2*)G, Gm, sign, H, W, tx, tx * ty, total, 0x8000000080000000ull);                       \
     } while (0)
     if (masks) { if (add) OFK_WS(true, true); else OFK_WS(true, false); }
