@@ -158,8 +158,8 @@ __device__ __forceinline__ uint32_t taps_in_frame(int ix, int iy, int H, int W) 
     return (x0 && y0 ? 1u : 0u) | (x1 && y0 ? 1u << 8 : 0u) | (x0 && y1 ? 1u << 16 : 0u) | (x1 && y1 ? 1u << 24 : 0u);
 }
 
-template <int C, bool HALF_EVEN, int MM, bool FM, int NP, int NB, int LA>
-__global__ void __launch_bounds__((NCW + 1) * 32, 3) warp_u8_ws_kernel(const __grid_constant__ Maps maps,
+template <int C, bool HALF_EVEN, int MM, bool FM, int NP, int NB, int LA, int PW>
+__global__ void __launch_bounds__((NCW + PW) * 32, 3) warp_u8_ws_kernel(const __grid_constant__ Maps maps,
                                                                       const uint8_t* __restrict__ img,
                                                                       const uint8_t* __restrict__ pmask, float sign,
                                                                       int rule, int H, int W, unsigned tiles_x,
@@ -184,6 +184,27 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 3) warp_u8_ws_kernel(const __g
     }
     __syncthreads();
 
+    if (PW == 2 && wrp == NCW + 1) {
+        // -------------------------------------------------------------------------------------------- P loader warp
+        // Streams the flow tiles into the ring of P stages as fast as stages are released, independent of the box
+        // pipeline.
+        if (lane == 0) {
+            const int tiles_y = (int)(tiles_per_frame / tiles_x);
+            TileIter pit;
+            pit.init(first, stride, (int)tiles_x, tiles_y);
+            unsigned ps_i = 0, ps_ph = 0;
+            for (unsigned i = 0; i < T; ++i) {
+                const int tx0 = pit.tx * TS, ty0 = pit.ty * TS, n = pit.n;
+                pit.advance((int)tiles_x, tiles_y);
+                if (i >= NP) mbar_wait(&sm.pempty[ps_i], ps_ph ^ 1);
+                mbar_expect_tx(&sm.pfull[ps_i], P_BYTES);
+                tma_load_3d(sm.ps[ps_i].f, &maps.f, &sm.pfull[ps_i], tx0, ty0, n);
+                if (FM) tma_load_3d(sm.ps[ps_i].fm, &maps.fm, &sm.pfull[ps_i], tx0, ty0, n);
+                if (++ps_i == NP) { ps_i = 0; ps_ph ^= 1; }
+            }
+        }
+        return;
+    }
     if (wrp == NCW) {
         // ------------------------------------------------------------------------------------------ producer warp
         const int tiles_y = (int)(tiles_per_frame / tiles_x);
@@ -200,7 +221,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 3) warp_u8_ws_kernel(const __g
             if (FM) tma_load_3d(sm.ps[ps_i].fm, &maps.fm, &sm.pfull[ps_i], tx0, ty0, n);
             if (++ps_i == NP) { ps_i = 0; ps_ph ^= 1; }
         };
-        if (lane == 0)
+        if (PW == 1 && lane == 0)
             for (unsigned k = 0; k < (unsigned)LA && k < T; ++k) issue_p(false);
         unsigned s = 0, s_ph = 0, b = 0, b_ph = 0;
         for (unsigned i = 0; i < T; ++i) {
@@ -244,7 +265,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 3) warp_u8_ws_kernel(const __g
                 mbar_expect_tx(&sm.bfull[b], B_BYTES);
                 tma_load_3d(sm.bs[b].img, &maps.ib, &sm.bfull[b], bx0, by0, n);
                 if (MM == MM_PMASK) tma_load_3d(sm.bs[b].m, &maps.pmb, &sm.bfull[b], mx0, by0, n);
-                if (i + LA < T) issue_p(i + LA >= NP);
+                if (PW == 1 && i + LA < T) issue_p(i + LA >= NP);
             }
             __syncwarp();
             if (++s == NP) { s = 0; s_ph ^= 1; }
@@ -383,7 +404,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 3) warp_u8_ws_kernel(const __g
     if (lane == 0) bulk_wait_all();
 }
 
-constexpr int WS_NP = 6, WS_NB = 2, WS_LA = 3;
+constexpr int WS_NP = 6, WS_NB = 2, WS_LA = 3, WS_PW = 1;   // measured best: one producer warp (a P loader warp costs the 3rd CTA its registers)
 
 template <int C, bool HALF_EVEN, int MM, bool FM>
 static int launch_variant(const Maps& maps, const uint8_t* img, const uint8_t* pmask, float sign, int rule, int H, int W,
@@ -392,7 +413,7 @@ static int launch_variant(const Maps& maps, const uint8_t* img, const uint8_t* p
     static bool attr_done_dev[64] = {false};   // the attribute is per device
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
-    auto kernel = warp_u8_ws_kernel<C, HALF_EVEN, MM, FM, WS_NP, WS_NB, WS_LA>;
+    auto kernel = warp_u8_ws_kernel<C, HALF_EVEN, MM, FM, WS_NP, WS_NB, WS_LA, WS_PW>;
     if (!attr_done_dev[dev]) {
         if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM)) != cudaSuccess) {
             cudaGetLastError();
@@ -403,7 +424,7 @@ static int launch_variant(const Maps& maps, const uint8_t* img, const uint8_t* p
     static int resident[64] = {0};              // co-resident CTAs per SM (shared memory / registers), per device
     if (resident[dev] == 0) {
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, (NCW + 1) * 32, sizeof(SM)) != cudaSuccess || nb < 1) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, (NCW + WS_PW) * 32, sizeof(SM)) != cudaSuccess || nb < 1) {
             cudaGetLastError();
             nb = 1;
         }
@@ -411,7 +432,7 @@ static int launch_variant(const Maps& maps, const uint8_t* img, const uint8_t* p
     }
     unsigned grid = (unsigned)(sm_count() * (ctas_per_sm < resident[dev] ? ctas_per_sm : resident[dev]));
     if (grid > total) grid = total;
-    kernel<<<grid, (NCW + 1) * 32, sizeof(SM), st>>>(maps, img, pmask, sign, rule, H, W, tx, tx * ty, total);
+    kernel<<<grid, (NCW + WS_PW) * 32, sizeof(SM), st>>>(maps, img, pmask, sign, rule, H, W, tx, tx * ty, total);
     return 1;
 }
 
