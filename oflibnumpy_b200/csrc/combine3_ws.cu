@@ -29,19 +29,6 @@ namespace ofk {
 namespace c3ws {
 using namespace ws;
 
-#ifdef OFK_TRACE   // timeline instrumentation for tools/exp_trace.cu (never defined in the library build)
-__device__ unsigned long long* g_trace = nullptr;   // [tile][16] global-timer stamps of CTA 0
-__device__ __forceinline__ void trace(unsigned tile, int slot) {
-    if (blockIdx.x == 0 && g_trace != nullptr && tile < 512) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        g_trace[tile * 16 + slot] = t;
-    }
-}
-#define OFK_TR(tile, slot) trace(tile, slot)
-#else
-#define OFK_TR(tile, slot)
-#endif
 
 constexpr int TS = 32;
 constexpr int BW = 48, BH = 48;   // vector box (pixels)

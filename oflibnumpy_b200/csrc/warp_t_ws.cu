@@ -227,7 +227,9 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 3) warp_u8_ws_kernel(const __
         for (unsigned i = 0; i < T; ++i) {
             const int tx0 = bit.tx * TS, ty0 = bit.ty * TS, n = bit.n;
             bit.advance((int)tiles_x, tiles_y);
+            if (lane == 0) OFK_TR(i, 0);
             mbar_wait(&sm.pfull[s], s_ph);
+            if (lane == 0) OFK_TR(i, 1);
             // Sample positions on a 4 x 4 grid over the tile (corners included): exact bounding box for affine fields, an
             // estimate otherwise (consumers verify per pixel). One shared-memory load per lane, four integer warp
             // reductions (REDUX): the producer's serial time per tile is what paces the whole pipeline.
@@ -257,7 +259,9 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 3) warp_u8_ws_kernel(const __
                 const int bx0 = (C * vx0) & ~15;             // 16-byte aligned box start, in bytes of the C*W-byte row
                 const int mx0 = vx0 & ~15;
                 const int by0 = y0 - max(0, (BH - needh) / 2);
+                OFK_TR(i, 2);
                 if (i >= NB) mbar_wait(&sm.bempty[b], b_ph ^ 1);
+                OFK_TR(i, 3);
                 // every tap of a pixel covered by a box that lies inside the frame is inside the frame
                 const int inframe = (bx0 >= 0 && bx0 + BWB <= C * W && by0 >= 0 && by0 + BH <= H) ? 1 : 0;
                 sm.binfo[b][0] = make_int4(bx0, mx0, by0, inframe);
@@ -265,7 +269,9 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 3) warp_u8_ws_kernel(const __
                 mbar_expect_tx(&sm.bfull[b], B_BYTES);
                 tma_load_3d(sm.bs[b].img, &maps.ib, &sm.bfull[b], bx0, by0, n);
                 if (MM == MM_PMASK) tma_load_3d(sm.bs[b].m, &maps.pmb, &sm.bfull[b], mx0, by0, n);
+                OFK_TR(i, 4);
                 if (PW == 1 && i + LA < T) issue_p(i + LA >= NP);
+                OFK_TR(i, 5);
             }
             __syncwarp();
             if (++s == NP) { s = 0; s_ph ^= 1; }
@@ -281,8 +287,10 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 3) warp_u8_ws_kernel(const __
     unsigned s = 0, s_ph = 0, b = 0, b_ph = 0;
     int prev_s = -1;
     for (unsigned i = 0; i < T; ++i) {
+        if (lane == 0 && wrp == 0) OFK_TR(i, 8);
         mbar_wait(&sm.bfull[b], b_ph);
         mbar_wait(&sm.pfull[s], s_ph);
+        if (lane == 0 && wrp == 0) OFK_TR(i, 9);
         const int4 info = sm.binfo[b][0], tile = sm.binfo[b][1];
         typename SM::PStage& ps = sm.ps[s];
         const typename SM::BStage& bs = sm.bs[b];
@@ -330,6 +338,7 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 3) warp_u8_ws_kernel(const __
             for (int j = 0; j < 4; ++j) dep |= w[j][TapWords<C>::N - 1] | (MM == MM_PMASK ? mt[j] : 0u);
             dep = __reduce_or_sync(0xffffffffu, dep);
             if (lane == 0) mbar_arrive_after(&sm.bempty[b], dep);
+            if (lane == 0 && wrp == 0) OFK_TR(i, 10);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 uint32_t W0, W1;
@@ -397,6 +406,7 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 3) warp_u8_ws_kernel(const __
                 mbar_arrive(&sm.pempty[prev_s]);
             }
         }
+        if (lane == 0 && wrp == 0) OFK_TR(i, 11);
         prev_s = (int)s;
         if (++s == NP) { s = 0; s_ph ^= 1; }
         if (++b == NB) { b = 0; b_ph ^= 1; }

@@ -83,6 +83,20 @@ struct TileIter {
     }
 };
 
+#ifdef OFK_TRACE   // timeline instrumentation for tools/exp_trace.cu (never defined in the library build)
+static __device__ unsigned long long* g_trace = nullptr;   // [tile][16] global-timer stamps of CTA 0
+__device__ __forceinline__ void trace(unsigned tile, int slot) {
+    if (blockIdx.x == 0 && g_trace != nullptr && tile < 512) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_trace[tile * 16 + slot] = t;
+    }
+}
+#define OFK_TR(tile, slot) trace(tile, slot)
+#else
+#define OFK_TR(tile, slot)
+#endif
+
 #endif  // __CUDACC__
 
 // ------------------------------------------------------------------------------------------------ host side

@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <vector>
 #include "../oflibnumpy_b200/csrc/combine3_ws.cu"
+#include "../oflibnumpy_b200/csrc/warp_t_ws.cu"
 namespace ofk {
 void set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vprintf(fmt, ap); va_end(ap); printf("\n"); }
 std::atomic<unsigned long long> g_launches{0};
@@ -48,16 +49,24 @@ int main(int argc, char** argv) {
     CK(cudaDeviceSynchronize());
     unsigned long long* dtr;
     CK(cudaMalloc(&dtr, 512 * 16 * 8)); CK(cudaMemset(dtr, 0, 512 * 16 * 8));
-    for (int w = 0; w < 3; ++w) ofk::launch_combine3_ws((float*)B, Bm, (float*)A, Am, -1.0f, true, (float*)out, outm, N, H, W, 0);
+    const int mode = argc > 1 ? atoi(argv[1]) : 0;   // 0 composition, 1 image warp (uint8 x3, half-even, geometry mask, flow mask)
+    uint8_t *img, *oimg;
+    CK(cudaMalloc(&img, px * 3)); CK(cudaMalloc(&oimg, px * 3)); CK(cudaMemset(img, 77, px * 3));
+    auto run = [&]() {
+        if (mode == 0) ofk::launch_combine3_ws((float*)B, Bm, (float*)A, Am, -1.0f, true, (float*)out, outm, N, H, W, 0);
+        else ofk::launch_warp_u8_ws(3, true, img, (float*)A, -1.0f, nullptr, Am, oimg, outm, OFK_RULE_GT_HALF, N, H, W, 0);
+    };
+    for (int w = 0; w < 3; ++w) run();
+    if (false) ofk::launch_combine3_ws((float*)B, Bm, (float*)A, Am, -1.0f, true, (float*)out, outm, N, H, W, 0);
     CK(cudaDeviceSynchronize());
-    CK(cudaMemcpyToSymbol(ofk::c3ws::g_trace, &dtr, sizeof(dtr)));
+    CK(cudaMemcpyToSymbol(ofk::ws::g_trace, &dtr, sizeof(dtr)));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    ofk::launch_combine3_ws((float*)B, Bm, (float*)A, Am, -1.0f, true, (float*)out, outm, N, H, W, 0);
+    run();
     cudaEventRecord(e1);
     CK(cudaDeviceSynchronize());
     float ms; cudaEventElapsedTime(&ms, e0, e1);
-    printf("kernel %.3f ms (%.0f GB/s)\n", ms, px * 27 / ms / 1e6);
+    printf("mode %d kernel %.3f ms (%.0f GB/s)\n", mode, ms, px * (mode ? 16 : 27) / ms / 1e6);
     std::vector<unsigned long long> tr(512 * 16);
     CK(cudaMemcpy(tr.data(), dtr, tr.size() * 8, cudaMemcpyDeviceToHost));
     const unsigned long long t0 = tr[20 * 16 + 0];
