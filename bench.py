@@ -177,7 +177,10 @@ def main():
     of.device.require_gpu()
 
     dist = None
+    cpus = []
     if world > 1:
+        from oflibnumpy_b200 import dist as ofd0
+        cpus = ofd0.bind_to_gpu_cpus(local_rank)      # NUMA-local pinned buffers / copy threads for the e2e leg
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
@@ -362,6 +365,7 @@ def main():
             "config": {"workload": "cfg4: batched 1920x1080 apply(uint8x3, return_valid_area) + "
                                    "combine_with(mode=3), ref 't'", "frames_per_gpu": B, "global_batch": world * B,
                        "parallelism": "batch-sharded x%d, no collective" % world,
+                       "cpu_binding": ("rank 0 bound to %d GPU-local cores" % len(cpus)) if cpus else "none",
                        "l2": "inputs (%.1f GB per GPU) exceed L2; no flush needed" %
                              (px_rank * (8 + 8 + 1 + 1 + 3) / 1e9)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}

@@ -9,7 +9,30 @@ import numpy as np
 
 from .batch import shard_range
 
-__all__ = ['shard_range', 'rank_world', 'max_over_ranks', 'gather_frames', 'as_torch']
+__all__ = ['shard_range', 'rank_world', 'max_over_ranks', 'gather_frames', 'as_torch', 'bind_to_gpu_cpus']
+
+
+def bind_to_gpu_cpus(device_index):
+    """Pin this process to the CPU cores NVML reports as local to GPU `device_index` (same NUMA node / PCIe root), so
+    that pinned host buffers allocated afterwards and the copy-issuing threads sit next to the GPU. With one process
+    per GPU this is what keeps host<->device streaming from crossing sockets. Returns the CPU list (empty if NVML or
+    the affinity call is unavailable: then nothing is changed)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        n_cpu = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * wi + b for wi, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        cpus = [c for c in cpus if c < n_cpu]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return []
 
 
 def rank_world():
