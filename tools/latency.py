@@ -30,3 +30,34 @@ for (h, w, label) in ((375, 1242, 'cfg1 375x1242'), (436, 1024, 'cfg2 436x1024')
     t(label + ': valid_target()', lambda: f.valid_target())
     if h <= 1080:
         t(label + ': invert() (t -> t, forward resampling)', lambda: f.invert(), reps=5)
+
+# cfg 5 of BASELINE.json: 4K chain, device resident (from_transforms -> invert -> combine x4 -> apply to an image)
+import golden_inputs as gi
+img5 = gi.cfg5_image()
+
+
+def chain(cross_ref_invert):
+    f = of.Flow.from_transforms(gi.CFG5_TRANSFORMS, gi.CFG5_SHAPE, 't')
+    if cross_ref_invert:
+        g_ = f.invert('s')
+        g_ = of.Flow(g_.vecs_device, 't', g_.mask_device)
+    else:
+        g_ = f.invert()                     # same reference: forward resampling (griddata in the reference)
+    acc = f
+    for i in range(4):
+        acc = acc.combine_with(g_ if i % 2 == 0 else f, 3)
+    return acc.apply(img5, return_valid_area=True)
+
+
+t("cfg5 4K chain, invert('s') relabelled (as tests/golden digests)", lambda: chain(True), reps=5)
+t("cfg5 4K chain, same-ref invert (forward resampling)", lambda: chain(False), reps=5)
+from oracle import flowref as R
+t0 = time.perf_counter()
+f = R.make(R.from_transforms(gi.CFG5_TRANSFORMS, gi.CFG5_SHAPE, 't'), 't')
+g_ = R.invert(f, 's'); g_ = R.make(g_.vecs, 't', g_.mask)
+acc = f
+for i in range(4):
+    acc = R.combine(acc, g_ if i % 2 == 0 else f, 3)
+R.apply(acc, img5, return_valid_area=True)
+print("%-70s %8.1f ms  (CPU oracle port, cv2.remap on all threads; the same-ref variant needs griddata: minutes)" %
+      ("cfg5 4K chain, invert('s') relabelled, reference path on the host", (time.perf_counter() - t0) * 1e3))
