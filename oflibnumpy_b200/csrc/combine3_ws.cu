@@ -510,6 +510,7 @@ int launch_combine3_ws(const float* P, const uint8_t* Pm, const float* G, const 
     const unsigned total = tx * ty * (unsigned)N;
     unsigned grid = (unsigned)sm_count() * 2;
     if (grid > total) grid = total;
+    grid = ws::cap_ctas(grid);
     const size_t smem = sizeof(Smem<WS_NP, WS_NB>);
 #define OFK_WS(MK, AD)                                                                                                  \
     do {                                                                                                              \

@@ -442,6 +442,7 @@ static int launch_variant(const Maps& maps, const uint8_t* img, const uint8_t* p
     }
     unsigned grid = (unsigned)(sm_count() * (ctas_per_sm < resident[dev] ? ctas_per_sm : resident[dev]));
     if (grid > total) grid = total;
+    grid = cap_ctas(grid);
     kernel<<<grid, (NCW + WS_PW) * 32, sizeof(SM), st>>>(maps, img, pmask, sign, rule, H, W, tx, tx * ty, total);
     return 1;
 }

@@ -2,6 +2,7 @@
 // wrappers, the persistent tile iterator and the host-side tensor-map encoder.
 #pragma once
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "ofk_common.cuh"
 
@@ -100,6 +101,17 @@ __device__ __forceinline__ void trace(unsigned tile, int slot) {
 #endif  // __CUDACC__
 
 // ------------------------------------------------------------------------------------------------ host side
+// Test hook: OFK_WS_MAX_CTAS=n caps the persistent grids, so that small frames already give every CTA many tiles (stage
+// rings wrap, barrier phases flip) -- tests/test_gpu_warp_t.py runs the parity suite that way in a subprocess.
+static inline unsigned cap_ctas(unsigned grid) {
+    static int cap = -1;
+    if (cap < 0) {
+        const char* e = getenv("OFK_WS_MAX_CTAS");
+        cap = e ? atoi(e) : 0;
+    }
+    return (cap > 0 && grid > (unsigned)cap) ? (unsigned)cap : grid;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

@@ -534,3 +534,23 @@ def test_tma_kernels_randomized(of):
     # every call above is eligible for the TMA kernels (W % 16 == 0, pool allocations are 256-byte aligned)
     assert after[0] > before[0] and after[2] > before[2]
     assert after[1] == before[1] and after[3] == before[3], (before, after)
+
+
+def test_tma_kernels_long_pipelines():
+    """The same randomised parity suite with the persistent grids capped at 3 CTAs (OFK_WS_MAX_CTAS, read once per
+    process): every CTA then walks through dozens of tiles, so the stage rings wrap around and every barrier phase flips
+    many times -- the regime of the full-size batches, at test-size cost."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import oflibnumpy_b200 as of\n"
+            "import test_gpu_warp_t as t\n"
+            "t.test_tma_kernels_randomized(of)\n"
+            "t.test_zero_test_probe_and_scan(of)\n"
+            "t.test_batched_equals_per_frame(of)\n"
+            "print('long pipelines ok')\n") % (os.path.dirname(here), here)
+    env = dict(os.environ, OFK_WS_MAX_CTAS='3')
+    res = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert 'long pipelines ok' in res.stdout
