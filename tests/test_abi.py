@@ -69,3 +69,29 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', text, flags=re.M), f
                 assert 'flowref' not in text and 'remap_q32' not in text, f
+
+
+def _build_c_example():
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, 'examples', 'abi_example')
+    cmd = ['gcc', '-O2', '-std=c99', '-Wall', '-I' + os.path.join(root, 'include'), os.path.join(root, 'examples', 'abi_example.c'),
+           '-L' + os.path.join(root, 'oflibnumpy_b200', 'lib'), '-loflib_b200',
+           '-Wl,-rpath,' + os.path.join(root, 'oflibnumpy_b200', 'lib'), '-lm', '-o', exe]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    return exe
+
+
+def test_header_is_plain_c_and_links():
+    """include/oflib_b200.h compiles as C99 and examples/abi_example.c links against the library without Python."""
+    _build_c_example()
+
+
+@pytest.mark.gpu
+def test_c_example_runs():
+    """The plain-C host program (host-buffer entry points, TMA kernels) checks its own invariants on the GPU."""
+    import subprocess
+    res = subprocess.run([_build_c_example()], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert 'abi example ok' in res.stdout
