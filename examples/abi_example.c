@@ -54,10 +54,10 @@ int main(void) {
                 const int sx = x - dx, sy = y - dy;
                 const int inside = sx >= 0 && sx < W && sy >= 0 && sy < H;
                 const size_t o = (size_t)n * px + (size_t)y * W + x;
-                if (valid[o] != (uint8_t)inside) ++bad;
+                if (valid[o] != (uint8_t)inside) { if (bad < 5) printf("  valid mismatch n=%d y=%d x=%d got %d want %d\n", n, y, x, valid[o], inside); ++bad; }
                 for (int c = 0; c < C; ++c) {
                     const uint8_t want = inside ? img[((size_t)n * px + (size_t)sy * W + sx) * C + c] : 0;
-                    if (out[o * C + c] != want) ++bad;
+                    if (out[o * C + c] != want) { if (bad < 5) printf("  value mismatch n=%d y=%d x=%d c=%d got %d want %d\n", n, y, x, c, out[o * C + c], want); ++bad; }
                 }
             }
     printf("integer translation: %zu mismatches\n", bad);

@@ -304,7 +304,8 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 2) c3_ws_kernel(const __grid_
                     strict[j] = m[j][0] & (m[j][1] | ~ha) & (m[j][2] | ~hb) & (m[j][3] | ~(ha & hb)) & pm[j];
                 } else {
                     const int ix = dx[j] + info.x, iy = dy[j] + info.z;
-                    strict[j] = (ix >= 0 && iy >= 0 && (ix + 1 < W || a == 0) && (iy + 1 < H || bb == 0)) ? 1u : 0u;
+                    strict[j] = (ix >= 0 && iy >= 0 && (ix + 1 < W || (a == 0 && ix < W)) &&
+                                 (iy + 1 < H || (bb == 0 && iy < H))) ? 1u : 0u;
                     strict[j] |= (unsigned)(t[j][3] >> 63) << 8;    // data dependency on the tap loaded last
                 }
                 dep |= strict[j];
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 2) c3_ws_kernel(const __grid_
                         strict = mm[0] & (mm[1] | za) & (mm[BMW] | zb) & (mm[BMW + 1] | za | zb);
                     } else {
                         const int ix = dx[j] + info.x, iy = dy[j] + info.z;
-                        strict = (ix >= 0 && iy >= 0 && (ix + 1 < W || za) && (iy + 1 < H || zb)) ? 1u : 0u;
+                        strict = (ix >= 0 && iy >= 0 && (ix + 1 < W || (za && ix < W)) && (iy + 1 < H || (zb && iy < H))) ? 1u : 0u;
                     }
                     const float ffa = (float)a * (1.0f / 32.0f), ffb = (float)bb * (1.0f / 32.0f);
                     const float na = 1.0f - ffa, nb = 1.0f - ffb;

@@ -554,3 +554,20 @@ def test_tma_kernels_long_pipelines():
     res = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout + res.stderr
     assert 'long pipelines ok' in res.stdout
+
+
+def test_combine_flows_integer_shift_over_the_border(of):
+    """combine_flows (no masks) with integer-valued flows: sample positions with zero fractions on and beyond the
+    right / bottom border. A tap with zero weight never matters, but the tap that carries the whole weight must lie
+    inside the frame (found by examples/abi_example.c: the TMA kernel accepted ix >= W when the fraction was 0)."""
+    for (h, w) in ((48, 64), (40, 70)):              # TMA kernel / gather kernel
+        for (dx, dy) in ((7, -4), (-3, 5), (w, 0), (0, h), (w - 1, h - 1)):
+            a = np.zeros((h, w, 2), np.float32)
+            a[..., 0], a[..., 1] = dx, dy
+            b = -a
+            for r in ('t', 's'):
+                got = of.Flow(a, r).combine_with(of.Flow(b, r), 3)
+                want = R.combine(R.make(a, r), R.make(b, r), 3)
+                same(got.mask, want.mask)
+                same(got.vecs, want.vecs)
+                same(of.combine_flows(a, b, 3, r), want.vecs)
