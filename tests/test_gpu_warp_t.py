@@ -571,3 +571,32 @@ def test_combine_flows_integer_shift_over_the_border(of):
                 same(got.mask, want.mask)
                 same(got.vecs, want.vecs)
                 same(of.combine_flows(a, b, 3, r), want.vecs)
+
+
+def test_integer_and_half_pixel_shifts_over_the_border(of):
+    """Every target-referenced kernel on constant flows whose sample positions have zero or one-half fractions and run
+    over each border by less than, exactly, and more than one pixel: the cases where "the tap that carries weight" and
+    "the tap that does not" sit on opposite sides of the frame edge."""
+    rng = np.random.default_rng(5)
+    for (h, w) in ((48, 64), (37, 50)):              # TMA kernels / gather kernels
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        tmask = rng.random((h, w)) > 0.2
+        other = of.Flow((rng.random((h, w, 2)).astype(np.float32) - np.float32(0.5)) * 6, 't', rng.random((h, w)) > 0.1)
+        ro = R.make(other.vecs, 't', other.mask)
+        for (dx, dy) in ((0.5, 0), (-0.5, 0.5), (1, 1), (-1, 0), (w - 1, 0), (w - 0.5, 0), (w, 0), (0, h - 1), (0, h),
+                         (-(w - 1), -(h - 1)), (-w, 1.5), (3.5, -(h - 0.5))):
+            v = np.zeros((h, w, 2), np.float32)
+            v[..., 0], v[..., 1] = dx, dy
+            f, rf = of.Flow(v, 't'), R.make(v, 't')
+            same(f.valid_target(), R.valid_target(rf))
+            same(of.Flow(v, 's').valid_source(), R.valid_source(R.make(v, 's')))
+            for im in (img, img[..., 0], np.ascontiguousarray(np.concatenate([img, img[..., :1]], -1))):
+                same(f.apply(im), R.apply(rf, im))
+                for tm in (None, tmask):
+                    w1, m1 = f.apply(im, target_mask=tm, return_valid_area=True)
+                    w2, m2 = R.apply(rf, im, target_mask=tm, return_valid_area=True)
+                    same(w1, w2)
+                    same(m1, m2)
+            res, want = f.apply(other), R.apply(rf, ro)
+            same(res.mask, want.mask)
+            same(res.vecs, want.vecs)
