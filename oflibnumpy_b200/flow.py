@@ -25,6 +25,90 @@ def _is_dev(x):
     return dev.is_device_array(x)
 
 
+class _HostView(np.ndarray):
+    """The numpy array handed out by ``Flow.vecs`` / ``Flow.mask``.
+
+    In the reference these arrays ARE the flow's storage and its tests and docs edit them in place
+    (``flow.vecs[~mask] = 0``, ``flow.mask[:, 200:] = False``; tests/test_flow_class.py:399,580,1003, docs/usage.rst:316).
+    Here the storage lives on the device, so the host copy must be uploaded again after such an edit -- but only then:
+    the buffer is kept read-only and the two ways numpy writes in place from Python (item assignment and ufuncs with
+    ``out=`` / augmented assignment) are intercepted to mark the owning Flow dirty. Every other writer (``np.copyto``,
+    ``arr.fill``, ``arr.sort``, a C extension writing into the buffer ...) hits the read-only flag and raises instead of
+    silently leaving the device copy stale; assign through the property (``flow.vecs = new_array``) in that case.
+    Slices and views share the buffer and the tracking; results of arithmetic are plain, writeable ndarrays."""
+
+    _dirty_cell = None      # one-element list shared with the owning Flow, or None for arrays that own nothing
+
+    def __array_finalize__(self, obj):
+        self._dirty_cell = None
+        if isinstance(obj, _HostView) and obj._dirty_cell is not None and self.base is not None and \
+                np.shares_memory(self, obj):
+            self._dirty_cell = obj._dirty_cell
+
+    def _writable(self):
+        """Context manager: temporarily lift the read-only flag of the underlying buffer for an intercepted write."""
+        return _Unlock(self)
+
+    def __setitem__(self, key, value):
+        if self._dirty_cell is None:
+            return super().__setitem__(key, value)
+        with _Unlock(self):
+            super().__setitem__(key, value)
+        self._dirty_cell[0] = True
+
+    def __array_ufunc__(self, ufunc, method, *inputs, out=None, **kwargs):
+        plain = tuple(np.asarray(x) if isinstance(x, _HostView) else x for x in inputs)
+        if out is None:
+            return getattr(ufunc, method)(*plain, **kwargs)
+        tracked = [o for o in out if isinstance(o, _HostView) and o._dirty_cell is not None]
+        outs = tuple(o.view(np.ndarray) if isinstance(o, _HostView) else o for o in out)
+        locks = [_Unlock(o) for o in tracked]
+        for lk in locks:
+            lk.__enter__()
+        try:
+            # views taken before unlocking keep the read-only flag: take them again now
+            outs = tuple(o.view(np.ndarray) if isinstance(o, _HostView) else o for o in out)
+            res = getattr(ufunc, method)(*plain, out=outs, **kwargs)
+        finally:
+            for lk in reversed(locks):
+                lk.__exit__(None, None, None)
+        for o in tracked:
+            o._dirty_cell[0] = True
+        if isinstance(res, tuple):
+            return tuple(o_in if r is o_plain else r for r, o_plain, o_in in zip(res, outs, out))
+        return out[0] if res is outs[0] else res
+
+
+class _Unlock(object):
+    """Lifts ``writeable=False`` along the base chain of a _HostView for the duration of one intercepted write."""
+
+    def __init__(self, arr):
+        chain, a = [], arr
+        while isinstance(a, np.ndarray):
+            chain.append(a)
+            a = a.base
+        self.chain = chain[::-1]          # owner first: a view can only be made writeable if its base is
+
+    def __enter__(self):
+        self.was = [a.flags.writeable for a in self.chain]
+        for a in self.chain:
+            a.flags.writeable = True
+        return self
+
+    def __exit__(self, *exc):
+        for a, w in zip(reversed(self.chain), reversed(self.was)):
+            a.flags.writeable = w
+        return False
+
+
+def _tracked_view(arr, dirty_cell):
+    """Read-only _HostView of a freshly downloaded array, reporting in-place edits to `dirty_cell`."""
+    arr.flags.writeable = False
+    v = arr.view(_HostView)
+    v._dirty_cell = dirty_cell
+    return v
+
+
 class Flow(object):
     def __init__(self, flow_vectors, ref=None, mask=None):
         """:param flow_vectors: numpy array (H,W,2), channel 0 horizontal (+right), channel 1 vertical (+down);
@@ -34,6 +118,7 @@ class Flow(object):
         """
         self._dv = self._dm = None
         self._hv = self._hm = None
+        self._vdirty, self._mdirty = [False], [False]
         self.vecs = flow_vectors
         self.ref = ref
         self.mask = mask
@@ -44,6 +129,7 @@ class Flow(object):
         """Adopt device results ([1,H,W,2] float32, [1,H,W] uint8) without validation or copies."""
         f = cls.__new__(cls)
         f._dv, f._dm, f._hv, f._hm = dvecs, dmask, None, None
+        f._vdirty, f._mdirty = [False], [False]
         f._ref = ref
         if dmask is None:
             f._dm = _ones_mask(dvecs.shape[1:3])
@@ -51,14 +137,16 @@ class Flow(object):
 
     def _vd(self):
         """Device vectors. A host view handed out by ``.vecs`` may have been edited in place (the reference's array
-        IS its storage), so it is uploaded again before use."""
-        if self._hv is not None:
-            self._dv = DeviceArray.from_numpy(self._hv[None], np.float32)
+        IS its storage): it reports such edits (see _HostView) and is uploaded again only then."""
+        if self._hv is not None and self._vdirty[0]:
+            self._dv = DeviceArray.from_numpy(np.asarray(self._hv)[None], np.float32)
+            self._vdirty[0] = False
         return self._dv
 
     def _md(self):
-        if self._hm is not None:
-            self._dm = DeviceArray.from_numpy(self._hm[None].view(np.uint8))
+        if self._hm is not None and self._mdirty[0]:
+            self._dm = DeviceArray.from_numpy(np.asarray(self._hm)[None].view(np.uint8))
+            self._mdirty[0] = False
         return self._dm
 
     # ------------------------------------------------------------------------------------------ attributes
@@ -66,7 +154,8 @@ class Flow(object):
     def vecs(self):
         """Flow vectors as a float32 numpy array (H,W,2) (device -> host copy on first access)."""
         if self._hv is None:
-            self._hv = self._dv.numpy()[0]
+            self._vdirty = [False]
+            self._hv = _tracked_view(self._dv.numpy()[0], self._vdirty)
         return self._hv
 
     @vecs.setter
@@ -113,7 +202,8 @@ class Flow(object):
     def mask(self):
         """Validity mask as a bool numpy array (H,W) (device -> host copy on first access)."""
         if self._hm is None:
-            self._hm = self._dm.numpy()[0].view(np.bool_)
+            self._mdirty = [False]
+            self._hm = _tracked_view(self._dm.numpy()[0].view(np.bool_), self._mdirty)
         return self._hm
 
     @mask.setter

@@ -344,6 +344,19 @@ def test_host_views_are_live(of):
     assert not f.valid_target()[:, 20:].any()
     f.vecs[...] = 0
     assert f.is_zero(thresholded=False)
+    # reading the host views alone does not cost an upload; edits do, once
+    g = of.Flow.from_transforms([['rotation', 0, 0, 30]], (32, 32), 't')
+    d0 = g._dv
+    _ = g.vecs.sum(), g.mask.all()
+    g.valid_target()
+    assert g._vd() is d0
+    g.vecs *= 0.5
+    assert g._vd() is not d0
+    d1 = g._dv
+    g.valid_target()
+    assert g._vd() is d1
+    with pytest.raises(ValueError):
+        g.vecs.fill(0)                                # writers numpy does not let us see fail loudly
 
 
 def test_constructor_errors(of):

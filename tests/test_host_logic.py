@@ -132,3 +132,41 @@ def test_threshold_vectors_reference_golden():
     np.testing.assert_array_equal(th[:4, 0, 0], [0, 1e-4, -1e-3, 1])
     th = threshold_vectors(vecs, threshold=1e-5)
     np.testing.assert_array_equal(th[:4, 0, 0], [-1e-5, 1e-4, -1e-3, 1])
+
+
+def test_host_view_tracks_in_place_edits():
+    """Flow.vecs / Flow.mask hand out read-only views that report the in-place edits numpy can make from Python (item
+    assignment, ufuncs with out= / augmented assignment) and make every other writer fail loudly."""
+    from oflibnumpy_b200.flow import _tracked_view
+    d = [False]
+    a = _tracked_view(np.arange(12, dtype=np.float32).reshape(3, 4), d)
+    assert isinstance(a, np.ndarray) and not a.flags.writeable
+    b = a * 2
+    assert type(b) is np.ndarray and b.flags.writeable and not d[0]
+    assert float(a.sum()) == 66.0 and not d[0]
+    a[0, 0] = 5
+    assert d[0] and a[0, 0] == 5 and not a.flags.writeable
+    d[0] = False
+    a[a > 6] = 0                                      # the reference's documented idiom (docs/usage.rst:316)
+    assert d[0]
+    d[0] = False
+    a += 1
+    assert d[0] and a[0, 0] == 6
+    d[0] = False
+    v = a[1:, :2]                                     # views share buffer and tracking
+    v[...] = 9
+    assert d[0] and a[1, 0] == 9
+    d[0] = False
+    np.multiply(a, 2, out=a)
+    assert d[0]
+    d[0] = False
+    for writer in (lambda: a.fill(0), lambda: np.copyto(a, 1), lambda: a.sort()):
+        with pytest.raises(ValueError):
+            writer()
+    assert not d[0]
+    m = _tracked_view(np.ones((3, 4), bool), d)
+    m[:, 2:] = False                                  # tests/test_flow_class.py:580 of the reference
+    assert d[0] and not m[:, 2:].any()
+    c = a.copy()
+    c[0, 0] = -1                                      # copies are ordinary arrays
+    assert a[0, 0] != -1
