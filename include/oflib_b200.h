@@ -186,6 +186,14 @@ int ofk_track_bilinear(const float* flow, const double* pts, size_t n, int H, in
 /* points_inside_area (utils.py:283-295): pts float64 [n][2] (row, col) rounded half-even like numpy.round. */
 int ofk_points_inside_area(const double* pts, size_t n, int H, int W, uint8_t* out, ofk_stream_t stream);
 
+/* Dataset decoders (the data formats either side of the path, utils.py:426-490). ofk_decode_kitti: bgr is the uint16
+ * [n_pixels][3] image exactly as cv2.imread(path, IMREAD_UNCHANGED) returns it (load_kitti, utils.py:426-445);
+ * vecs[i] = ((R - 2^15) / 64, (G - 2^15) / 64) in float32 (exact), mask[i] = B != 0 (Flow.from_kitti with load_valid;
+ * mask may be NULL). ofk_decode_sintel_mask: the invalid-pixel image of load_sintel_mask (utils.py:474-490),
+ * mask = (invalid == 0). A Sintel .flo payload is float32 (u, v) already and is uploaded as is. */
+int ofk_decode_kitti(const uint16_t* bgr, float* vecs, uint8_t* mask, size_t n_pixels, ofk_stream_t stream);
+int ofk_decode_sintel_mask(const uint8_t* invalid, uint8_t* mask, size_t n_pixels, ofk_stream_t stream);
+
 /* ------------------------------------------------------------------------------- source-referenced path, device */
 
 /* Source-referenced (forward) resampling: replaces `griddata(grid + flow, payload, grid, 'linear')` + nan_to_num in

@@ -38,6 +38,8 @@ _SIGNATURES = {
     'ofk_extent': (_i, [_vp, _vp, _f, _f, _vp, _i, _i, _i, _vp]),
     'ofk_resize_flow': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _d, _vp]),
     'ofk_greater': (_i, [_vp, _f, _vp, _sz, _vp]),
+    'ofk_decode_kitti': (_i, [_vp, _vp, _vp, _sz, _vp]),
+    'ofk_decode_sintel_mask': (_i, [_vp, _vp, _sz, _vp]),
     'ofk_track_bilinear': (_i, [_vp, _vp, _sz, _i, _i, _vp, _vp, _vp]),
     'ofk_points_inside_area': (_i, [_vp, _sz, _i, _i, _vp, _vp]),
     'ofk_forward_s_workspace': (_sz, [_i, _i, _i]),

@@ -323,6 +323,25 @@ __global__ void __launch_bounds__(256) inside_kernel(const double* __restrict__ 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ dataset decoders
+// KITTI flow PNG (utils.py:426-445): uint16 BGR as OpenCV decodes it; u = (R - 2^15) / 64, v = (G - 2^15) / 64 (exact in
+// float32), valid = B != 0. Sintel .flo (utils.py:448-471) is little-endian float32 (u, v) already; its invalid-pixel
+// PNG (utils.py:474-490) is a uint8 image, valid = (value == 0).
+__global__ void __launch_bounds__(256) decode_kitti_kernel(const uint16_t* __restrict__ bgr, float2* __restrict__ vecs,
+                                                           uint8_t* __restrict__ mask, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned b = bgr[3 * i], g = bgr[3 * i + 1], r = bgr[3 * i + 2];
+        vecs[i] = make_float2((float)((int)r - 32768) * 0.015625f, (float)((int)g - 32768) * 0.015625f);
+        if (mask != nullptr) mask[i] = b != 0 ? 1 : 0;
+    }
+}
+__global__ void __launch_bounds__(256) invert_mask_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+                                                          size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = in[i] == 0 ? 1 : 0;
+}
+
 }  // namespace ofk
 
 using namespace ofk;
@@ -486,6 +505,24 @@ extern "C" int ofk_points_inside_area(const double* pts, size_t n, int H, int W,
     OFK_CHECK_ARG(pts && out, "ofk_points_inside_area: NULL argument");
     if (n == 0) return OFK_OK;
     inside_kernel<<<stream_grid(n, 256), 256, 0, as_stream(stream)>>>(pts, n, H, W, out);
+    OFK_LAUNCHED();
+    return OFK_OK;
+}
+
+extern "C" int ofk_decode_kitti(const uint16_t* bgr, float* vecs, uint8_t* mask, size_t n_pixels, ofk_stream_t stream) {
+    OFK_CHECK_ARG(bgr && vecs, "ofk_decode_kitti: NULL argument");
+    OFK_CHECK_ARG(((uintptr_t)vecs & 7) == 0 && ((uintptr_t)bgr & 1) == 0, "ofk_decode_kitti: misaligned pointer");
+    if (n_pixels == 0) return OFK_OK;
+    decode_kitti_kernel<<<stream_grid(n_pixels, 256), 256, 0, as_stream(stream)>>>(bgr, reinterpret_cast<float2*>(vecs),
+                                                                                  mask, n_pixels);
+    OFK_LAUNCHED();
+    return OFK_OK;
+}
+
+extern "C" int ofk_decode_sintel_mask(const uint8_t* invalid, uint8_t* mask, size_t n_pixels, ofk_stream_t stream) {
+    OFK_CHECK_ARG(invalid && mask, "ofk_decode_sintel_mask: NULL argument");
+    if (n_pixels == 0) return OFK_OK;
+    invert_mask_kernel<<<stream_grid(n_pixels, 256), 256, 0, as_stream(stream)>>>(invalid, mask, n_pixels);
     OFK_LAUNCHED();
     return OFK_OK;
 }

@@ -273,21 +273,37 @@ class Flow(object):
 
     @classmethod
     def from_kitti(cls, path, load_valid=None):
-        from .io import load_kitti
+        """Flow from a KITTI uint16 PNG (flow_class.py:237-256, utils.py:426-445). The file is decoded on the host by
+        OpenCV; the raw uint16 pixels (6 B/px instead of 8 + 1) go to the device and are converted there."""
+        from .io import read_kitti_raw
         load_valid = True if load_valid is None else load_valid
         if not isinstance(load_valid, bool):
             raise TypeError("Error loading flow from KITTI data: Load_valid needs to be boolean")
-        data = load_kitti(path)
-        if load_valid:
-            return cls(data[..., :2], 's', data[..., 2].astype('bool'))
-        return cls(data[..., :2], 's')
+        raw = read_kitti_raw(path)                                   # (H, W, 3) uint16, BGR as OpenCV decodes it
+        h, w = raw.shape[:2]
+        d_raw = DeviceArray.from_numpy(raw)
+        vecs = DeviceArray.empty((1, h, w, 2), np.float32)
+        mask = DeviceArray.empty((1, h, w), np.uint8) if load_valid else None
+        _lib.call('ofk_decode_kitti', d_raw.ptr, vecs.ptr, mask.ptr if mask is not None else None, h * w,
+                  dev.current_stream())
+        return cls._wrap(vecs, 's', mask)
 
     @classmethod
     def from_sintel(cls, path, inv_path=None):
-        from .io import load_sintel, load_sintel_mask
+        """Flow from a Sintel .flo file and, optionally, its invalid-pixel PNG (flow_class.py:258-275,
+        utils.py:448-490); the mask is inverted on the device."""
+        from .io import load_sintel, read_sintel_invalid_raw
         flow = load_sintel(path)
-        mask = None if inv_path is None else load_sintel_mask(inv_path)
-        return cls(flow, 's', mask)
+        f = cls(flow, 's')
+        if inv_path is not None:
+            raw = read_sintel_invalid_raw(inv_path)                  # (H, W) uint8
+            if raw.shape != f.shape:
+                raise ValueError("Error setting flow mask: Input has a different shape than the flow vectors")
+            d_raw = DeviceArray.from_numpy(raw)
+            mask = DeviceArray.empty((1,) + raw.shape, np.uint8)
+            _lib.call('ofk_decode_sintel_mask', d_raw.ptr, mask.ptr, raw.size, dev.current_stream())
+            f._dm, f._hm = mask, None
+        return f
 
     def copy(self):
         """Deep copy (device-to-device)."""

@@ -3,6 +3,30 @@ they return are uploaded by the Flow constructor."""
 import numpy as np
 
 
+def read_kitti_raw(path):
+    """The uint16 (H,W,3) BGR image of a KITTI flow PNG exactly as OpenCV decodes it (input of ofk_decode_kitti)."""
+    import cv2
+    inp = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    if inp is None:
+        raise ValueError("Error loading flow from KITTI data: Flow data could not be loaded")
+    if inp.ndim != 3 or inp.shape[-1] != 3:
+        raise ValueError("Error loading flow from KITTI data: Loaded flow data has the wrong shape")
+    if inp.dtype != np.uint16:
+        inp = inp.astype(np.uint16)        # 8-bit PNGs: the reference converts whatever it gets to float64
+    return np.ascontiguousarray(inp)
+
+
+def read_sintel_invalid_raw(path):
+    """The uint8 (H,W) invalid-pixel image of Sintel as OpenCV decodes it (input of ofk_decode_sintel_mask)."""
+    if not isinstance(path, str):
+        raise TypeError("Error loading flow from Sintel data: Path needs to be a string")
+    import cv2
+    mask = cv2.imread(path, 0)
+    if mask is None:
+        raise ValueError("Error loading flow from Sintel data: Invalid mask could not be loaded from path")
+    return np.ascontiguousarray(mask)
+
+
 def load_kitti(path):
     """KITTI uint16 PNG: channels (u, v, valid) with u, v stored as (value - 2**15) / 64. Returns float64 (H,W,3)."""
     import cv2  # only needed for PNG decoding

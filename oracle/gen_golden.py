@@ -280,7 +280,42 @@ def digests():
     return out
 
 
+def case_datasets():
+    """Dataset formats (utils.py:426-490): small synthetic KITTI / Sintel files are written next to the vectors
+    (tests/golden/files/) and read back by the reference's own loaders and Flow constructors."""
+    import cv2
+    files = os.path.join(OUT, 'files')
+    os.makedirs(files, exist_ok=True)
+    rng = np.random.default_rng(31)
+    h, w = 24, 40
+    kitti = rng.integers(0, 65536, (h, w, 3), dtype=np.uint16)            # BGR on disk: B = valid, G = v, R = u
+    kitti[..., 0] = rng.integers(0, 2, (h, w))                            # valid channel: 0 / 1 as in the dataset
+    kitti[3, 5] = (7, 32768, 32768)                                       # zero flow, "valid" stored as 7
+    kpath = os.path.join(files, 'kitti_sample.png')
+    assert cv2.imwrite(kpath, kitti)
+    flo = ((rng.random((h, w, 2)) - 0.5) * 40).astype('<f4')
+    spath = os.path.join(files, 'sintel_sample.flo')
+    with open(spath, 'wb') as fh:
+        fh.write(b'PIEH')
+        fh.write(int(w).to_bytes(4, 'little'))
+        fh.write(int(h).to_bytes(4, 'little'))
+        fh.write(flo.tobytes())
+    inv = (rng.random((h, w)) > 0.8).astype(np.uint8) * 255
+    ipath = os.path.join(files, 'sintel_invalid.png')
+    assert cv2.imwrite(ipath, inv)
+    d = {}
+    d['out_load_kitti'] = ref.utils.load_kitti(kpath)
+    flow_out('kitti_valid', ref.Flow.from_kitti(kpath), d)
+    flow_out('kitti_novalid', ref.Flow.from_kitti(kpath, load_valid=False), d)
+    d['out_load_sintel'] = ref.utils.load_sintel(spath)
+    d['out_load_sintel_mask'] = ref.utils.load_sintel_mask(ipath)
+    flow_out('sintel', ref.Flow.from_sintel(spath), d)
+    flow_out('sintel_masked', ref.Flow.from_sintel(spath, ipath), d)
+    return d
+
+
 CASES = {
+    'datasets': case_datasets,
     'warp_t': case_warp_t,
     'warp_t_padded': case_warp_t_padded,
     'combine3': case_combine3,

@@ -613,3 +613,19 @@ def test_integer_and_half_pixel_shifts_over_the_border(of):
             res, want = f.apply(other), R.apply(rf, ro)
             same(res.mask, want.mask)
             same(res.vecs, want.vecs)
+
+
+def test_dataset_constructors_decode_on_device(of):
+    """Flow.from_kitti / Flow.from_sintel (device decoders ofk_decode_kitti / ofk_decode_sintel_mask) against the
+    reference's constructors on the committed sample files."""
+    g = load_golden('datasets')
+    files = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'files')
+    kp, sp, ip = (os.path.join(files, n) for n in ('kitti_sample.png', 'sintel_sample.flo', 'sintel_invalid.png'))
+    flow_same(g, 'kitti_valid', of.Flow.from_kitti(kp))
+    flow_same(g, 'kitti_novalid', of.Flow.from_kitti(kp, load_valid=False))
+    flow_same(g, 'sintel', of.Flow.from_sintel(sp))
+    flow_same(g, 'sintel_masked', of.Flow.from_sintel(sp, ip))
+    with pytest.raises(TypeError):
+        of.Flow.from_kitti(kp, load_valid='yes')
+    with pytest.raises(ValueError):
+        of.Flow.from_kitti(sp)

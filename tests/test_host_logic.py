@@ -1,4 +1,6 @@
 """CPU-only tests of the host-side logic of the package (validators, dtype promotion table, sharding, slicing)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -170,3 +172,22 @@ def test_host_view_tracks_in_place_edits():
     c = a.copy()
     c[0, 0] = -1                                      # copies are ordinary arrays
     assert a[0, 0] != -1
+
+
+def test_dataset_loaders_match_reference():
+    """Host file readers (oflibnumpy_b200/io.py) against outputs of the reference's loaders on the committed sample
+    files (tests/golden/files, written and read back by oracle/gen_golden.py with the unmodified reference)."""
+    from conftest import load_golden
+    from oflibnumpy_b200 import io
+    g = load_golden('datasets')
+    files = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'files')
+    np.testing.assert_array_equal(io.load_kitti(os.path.join(files, 'kitti_sample.png')), g['out_load_kitti'])
+    np.testing.assert_array_equal(io.load_sintel(os.path.join(files, 'sintel_sample.flo')), g['out_load_sintel'])
+    np.testing.assert_array_equal(io.load_sintel_mask(os.path.join(files, 'sintel_invalid.png')),
+                                  g['out_load_sintel_mask'])
+    raw = io.read_kitti_raw(os.path.join(files, 'kitti_sample.png'))
+    assert raw.dtype == np.uint16 and raw.shape == g['out_load_kitti'].shape
+    with pytest.raises(ValueError):
+        io.load_kitti(os.path.join(files, 'does_not_exist.png'))
+    with pytest.raises(ValueError):
+        io.load_sintel(os.path.join(files, 'kitti_sample.png'))
