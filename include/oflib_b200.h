@@ -263,7 +263,9 @@ int ofk_rt_event_elapsed_ms(void* start, void* stop, float* ms);
 unsigned long long ofk_rt_launch_count(void);
 /* how often each implementation of the two headline operations ran (tests assert that eligible shapes take the TMA
  * kernels): which = 0 ofk_combine3 / TMA kernel, 1 ofk_combine3 / gather kernels, 2 ofk_warp_t / TMA kernels,
- * 3 ofk_warp_t / gather kernels */
+ * 3 ofk_warp_t / gather kernels. which = 4 / 5: inside the TMA kernels of ofk_combine3 / ofk_warp_t, how many
+ * (warp, tile) pairs fetched taps from global memory because the tile's box did not cover them (discontinuous or noisy
+ * flows); read synchronously from the current device. */
 unsigned long long ofk_rt_path_count(int which);
 
 #if defined(__GNUC__)

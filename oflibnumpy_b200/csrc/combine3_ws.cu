@@ -14,14 +14,16 @@
 //              tests, no border path), blend with packed f32x2 arithmetic in cv2.remap's rounding sequence, write the
 //              result over the P tile in place and hand the warp's four rows to a TMA store (clipped at the frame
 //              border by the hardware).
-// Pixels whose taps are not covered by the box (estimate too small, wild flows) take an exact global-memory path
-// individually, so the result never depends on the quality of the estimate. HBM traffic is the algorithmic 27 B/px:
+// Pixels whose taps are not covered by the box (estimate too small, discontinuous or noisy flows) fetch their taps from
+// global memory instead, with the same arithmetic, so the result never depends on the quality of the estimate. HBM traffic is the algorithmic 27 B/px:
 // P and the output stream once; the boxes overlap, but the overlap is served by L2.
 //
 // The zero tests gating the reference's early exits (flow_class.py:1338-1354) are not part of the hot loop: a probe
 // kernel looks at a sparse sample of every operand (almost always enough to prove "not zero"), a scan kernel reads the
 // operands completely only for frames the probe could not decide, and combine3_fixup (combine3.cu) applies the exits.
 #include <stdlib.h>
+
+#include <type_traits>
 
 #include "ws_common.cuh"
 
@@ -91,34 +93,136 @@ __device__ __forceinline__ void quant(float X, int& i, int& f) {
     f = bits & 31;
 }
 
-// exact per-pixel path from global memory (any coordinates); returns sample in (u, v) and strict validity
-__device__ __forceinline__ float4 slow_sample(const float2* __restrict__ G, const uint8_t* __restrict__ Gm, int H, int W,
-                                           float X, float Y) {
-    int sx = __float2int_rn(X * 32.0f), sy = __float2int_rn(Y * 32.0f);
-    const int ix = max(-32768, min(32767, sx >> 5)), iy = max(-32768, min(32767, sy >> 5));
-    const int a = sx & 31, b = sy & 31;
-    const bool x0 = (unsigned)ix < (unsigned)W, x1 = (unsigned)(ix + 1) < (unsigned)W;
-    const bool y0 = (unsigned)iy < (unsigned)H, y1 = (unsigned)(iy + 1) < (unsigned)H;
-    const long long o = (long long)iy * W + ix;
-    const float2 z = make_float2(0.f, 0.f);
-    const float2 t00 = (x0 && y0) ? __ldg(G + o) : z, t01 = (x1 && y0) ? __ldg(G + o + 1) : z;
-    const float2 t10 = (x0 && y1) ? __ldg(G + o + W) : z, t11 = (x1 && y1) ? __ldg(G + o + W + 1) : z;
-    const int w00 = (32 - a) * (32 - b), w01 = a * (32 - b), w10 = (32 - a) * b, w11 = a * b;
-    int S = 0;
-    if (x0 && y0 && (!Gm || __ldg(Gm + o))) S += w00;
-    if (x1 && y0 && (!Gm || __ldg(Gm + o + 1))) S += w01;
-    if (x0 && y1 && (!Gm || __ldg(Gm + o + W))) S += w10;
-    if (x1 && y1 && (!Gm || __ldg(Gm + o + W + 1))) S += w11;
-    const float s = 1.0f / 1024.0f;
-    const float f00 = float(w00) * s, f01 = float(w01) * s, f10 = float(w10) * s, f11 = float(w11) * s;
-    float4 r;
-    r.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t00.x, f00), __fmul_rn(t01.x, f01)), __fmul_rn(t10.x, f10)),
-                    __fmul_rn(t11.x, f11));
-    r.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t00.y, f00), __fmul_rn(t01.y, f01)), __fmul_rn(t10.y, f10)),
-                    __fmul_rn(t11.y, f11));
-    r.z = (S == 1024) ? 1.f : 0.f;
-    r.w = 0.f;
-    return r;
+// Taps of a warp's 4 x 32 pixels, all requested before the first use; then validity, release of the box, blend.
+// MODE = BOX        : every pixel of the warp is covered by the box (shared memory only, no bounds tests).
+// MODE = BOX_OR_ZERO: the pixels not covered by the box have all four taps outside the frame (the usual case along the
+//                     frame border: the box is clamped to the frame) -- their taps are zeros.
+// MODE = MIXED      : pixels outside the box fetch their taps from global memory, predicated per tap on "inside the
+//                     frame" (zero border, mask invalid outside) -- one memory round trip per warp and tile, and the
+//                     same arithmetic, so the result never depends on the box estimate.
+enum : int { BOX = 0, BOX_OR_ZERO = 1, MIXED_TAPS = 2 };
+template <bool MASKS, bool ADD, int MODE, class BStage>
+__device__ __forceinline__ void sample_rows(const BStage& bs, float2* prow, uint8_t* mrow, const uint64_t (&p)[4],
+                                            const unsigned (&pm)[4], const int (&dx)[4], const int (&dy)[4],
+                                            const int (&fa)[4], const int (&fb)[4], int4 info, int n,
+                                            const float2* __restrict__ G, const uint8_t* __restrict__ Gm, int H, int W,
+                                            uint64_t negzero2, uint64_t* bempty, unsigned lane) {
+    const uint64_t one2 = pack2(1.0f, 1.0f);
+    uint64_t t[4][4];
+    unsigned m[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const bool inbox = MODE == BOX || ((unsigned)dx[j] < (unsigned)(BW - 1) && (unsigned)dy[j] < (unsigned)(BH - 1));
+        if (inbox) {
+            const uint64_t* v = reinterpret_cast<const uint64_t*>(bs.v) + (dy[j] * BW + dx[j]);
+            t[j][0] = v[0]; t[j][1] = v[1]; t[j][2] = v[BW]; t[j][3] = v[BW + 1];
+            if (MASKS) {
+                const uint8_t* mm = bs.m + (dy[j] * BMW + dx[j] + info.y);
+                m[j][0] = mm[0]; m[j][1] = mm[1]; m[j][2] = mm[BMW]; m[j][3] = mm[BMW + 1];
+            }
+        } else if (MODE == BOX_OR_ZERO) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { t[j][k] = 0ull; m[j][k] = 0u; }
+        } else {
+            // integer coordinates from the fast quantiser: exact for |X| < 2^17, far outside the frame otherwise
+            const int ix = dx[j] + info.x, iy = dy[j] + info.z;
+            const bool x0 = (unsigned)ix < (unsigned)W, x1 = (unsigned)(ix + 1) < (unsigned)W;
+            const bool y0 = (unsigned)iy < (unsigned)H, y1 = (unsigned)(iy + 1) < (unsigned)H;
+            const long long o = (long long)n * ((long long)H * W) + ((long long)iy * W + ix);
+            const uint64_t* g = reinterpret_cast<const uint64_t*>(G) + o;
+            t[j][0] = (x0 && y0) ? __ldg(g) : 0ull;
+            t[j][1] = (x1 && y0) ? __ldg(g + 1) : 0ull;
+            t[j][2] = (x0 && y1) ? __ldg(g + W) : 0ull;
+            t[j][3] = (x1 && y1) ? __ldg(g + W + 1) : 0ull;
+            if (MASKS) {
+                const uint8_t* gm = Gm + o;
+                m[j][0] = (x0 && y0) ? __ldg(gm) : 0u;
+                m[j][1] = (x1 && y0) ? __ldg(gm + 1) : 0u;
+                m[j][2] = (x0 && y1) ? __ldg(gm + W) : 0u;
+                m[j][3] = (x1 && y1) ? __ldg(gm + W + 1) : 0u;
+            }
+        }
+    }
+    // validity first: it consumes the values loaded last, so once it is known every tap of this warp has
+    // left the box and the stage can be handed back to the producer while the blend is still running
+    unsigned strict[4], dep = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const unsigned a = fa[j], bb = fb[j];
+        const unsigned ha = min(a, 1u), hb = min(bb, 1u);      // 1 where the right / lower taps have weight
+        if (MASKS) {
+            strict[j] = m[j][0] & (m[j][1] | ~ha) & (m[j][2] | ~hb) & (m[j][3] | ~(ha & hb)) & pm[j];
+        } else {
+            const int ix = dx[j] + info.x, iy = dy[j] + info.z;
+            strict[j] = (ix >= 0 && iy >= 0 && (ix + 1 < W || (a == 0 && ix < W)) &&
+                         (iy + 1 < H || (bb == 0 && iy < H))) ? 1u : 0u;
+            strict[j] |= (unsigned)(t[j][3] >> 63) << 8;    // data dependency on the tap loaded last
+            if (MODE == MIXED_TAPS) strict[j] |= (unsigned)((t[j][0] | t[j][1] | t[j][2]) >> 63) << 8;
+        }
+        dep |= strict[j];
+    }
+    dep = __reduce_or_sync(0xffffffffu, dep);
+    if (lane == 0) mbar_arrive_after(bempty, dep);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const unsigned a = fa[j], bb = fb[j];
+        const float ffa = (float)a * (1.0f / 32.0f), ffb = (float)bb * (1.0f / 32.0f);
+        const uint64_t fa2 = pack2(ffa, ffa), fb2 = pack2(ffb, ffb);
+        const uint64_t na2 = add2(one2, fa2 ^ 0x8000000080000000ull), nb2 = add2(one2, fb2 ^ 0x8000000080000000ull);
+        uint64_t accv = mul2_nofuse(t[j][0], mul2(na2, nb2), negzero2);
+        accv = add2(accv, mul2_nofuse(t[j][1], mul2(fa2, nb2), negzero2));
+        accv = add2(accv, mul2_nofuse(t[j][2], mul2(na2, fb2), negzero2));
+        accv = add2(accv, mul2_nofuse(t[j][3], mul2(fa2, fb2), negzero2));
+        *reinterpret_cast<uint64_t*>(prow + j * TS) = ADD ? add2(p[j], accv) : accv;
+        mrow[j * TS] = (uint8_t)(strict[j] & 1u);
+    }
+}
+
+// this thread's four pixels of a tile: operand values, sample positions relative to the box, 1/32-px fractions;
+// returns whether all of them are covered by the box
+template <bool MASKS>
+__device__ __forceinline__ bool prepare_rows(const float2* prow, const uint8_t* mrow, float sign, float xg, float yg,
+                                             int4 info, uint64_t (&p)[4], unsigned (&pm)[4], int (&dx)[4], int (&dy)[4],
+                                             int (&fa)[4], int (&fb)[4]) {
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        p[j] = *reinterpret_cast<const uint64_t*>(prow + j * TS);
+        pm[j] = MASKS ? mrow[j * TS] : 1u;
+        const float2 pv = unpack2(p[j]);
+        const float X = __fmaf_rn(sign, pv.x, xg), Y = __fmaf_rn(sign, pv.y, yg + (float)j);
+        int ix, iy;
+        quant(X, ix, fa[j]);
+        quant(Y, iy, fb[j]);
+        dx[j] = ix - info.x;
+        dy[j] = iy - info.z;
+        // Covered by the box? Everything else is decided per pixel. No range test is needed for the fast quantiser:
+        // it is exact for |X| < 2^17, and beyond that (or for NaN / Inf) the integer it produces is far outside
+        // [-2^16, 2^16], so such a pixel can never pass the box test (frames are smaller than 32768).
+        ok = ok && (unsigned)dx[j] < (unsigned)(BW - 1) && (unsigned)dy[j] < (unsigned)(BH - 1);
+    }
+    return ok;
+}
+
+// The rare path, out of line so that it does not weigh on the register allocation of the kernel's main loop: redoes the
+// preparation from shared memory and samples with MODE = MIXED.
+static __device__ unsigned long long g_mixed_warp_tiles;   // test hook: how often the out-of-line path ran (per warp and tile)
+
+template <bool MASKS, bool ADD, class SM>
+__device__ __noinline__ void mixed_rows(typename SM::PStage* ps, const typename SM::BStage* bs, uint64_t* bempty,
+                                        int4 info, int4 tile, const float2* __restrict__ G,
+                                        const uint8_t* __restrict__ Gm, float sign, int H, int W, uint64_t negzero2) {
+    const unsigned lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    if (lane == 0) atomicAdd(&g_mixed_warp_tiles, 1ull);
+    float2* prow = ps->p + ((int)wrp * 4 * TS + lane);
+    uint8_t* mrow = ps->pm + ((int)wrp * 4 * TS + lane);
+    uint64_t p[4];
+    unsigned pm[4];
+    int dx[4], dy[4], fa[4], fb[4];
+    prepare_rows<MASKS>(prow, mrow, sign, (float)(tile.x + (int)lane), (float)(tile.y + (int)wrp * 4), info, p, pm, dx, dy,
+                        fa, fb);
+    sample_rows<MASKS, ADD, MIXED_TAPS>(*bs, prow, mrow, p, pm, dx, dy, fa, fb, info, tile.z, G, Gm, H, W, negzero2, bempty,
+                                  lane);
 }
 
 // ADD: out = P + Q(G, ...) (composition); otherwise out = Q(G, ...) alone (Flow.apply of a flow: ofk_warp_t, float32 x2)
@@ -328,46 +432,53 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 2) c3_ws_kernel(const __grid_
                 mrow[j * TS] = (uint8_t)(strict[j] & 1u);
             }
         } else {
-            // some pixel of this warp is not covered by the box: per-pixel decision
-            const size_t fbase = (size_t)n * ((size_t)H * W);
+            // Some pixel of this warp is not covered by the box. Along the frame border that is the rule (the box is
+            // clamped to the frame): those pixels sample nothing but the zero border. Pixels that need taps from inside
+            // the frame (discontinuous or noisy flow, estimate too small) send the warp to the out-of-line path.
+            bool need_global = false;
+            const int bx = cold_value(info.x), by = cold_value(info.z);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float2 pv = unpack2(p[j]);
-                const float X = __fmaf_rn(sign, pv.x, xg), Y = __fmaf_rn(sign, pv.y, (float)(ty0 + (int)wrp * 4 + j));
+                const int ix = dx[j] + bx, iy = dy[j] + by;
                 const bool inbox = (unsigned)dx[j] < (unsigned)(BW - 1) && (unsigned)dy[j] < (unsigned)(BH - 1);
-                float su, sv;
-                unsigned strict;
-                if (inbox) {
-                    const float2* v = bs.v + (dy[j] * BW + dx[j]);
-                    const float2 t00 = v[0], t01 = v[1], t10 = v[BW], t11 = v[BW + 1];
-                    const int a = fa[j], bb = fb[j];
-                    const unsigned za = a == 0, zb = bb == 0;
-                    if (MASKS) {
-                        const uint8_t* mm = bs.m + (dy[j] * BMW + dx[j] + info.y);
-                        strict = mm[0] & (mm[1] | za) & (mm[BMW] | zb) & (mm[BMW + 1] | za | zb);
-                    } else {
-                        const int ix = dx[j] + info.x, iy = dy[j] + info.z;
-                        strict = (ix >= 0 && iy >= 0 && (ix + 1 < W || (za && ix < W)) && (iy + 1 < H || (zb && iy < H))) ? 1u : 0u;
-                    }
-                    const float ffa = (float)a * (1.0f / 32.0f), ffb = (float)bb * (1.0f / 32.0f);
-                    const float na = 1.0f - ffa, nb = 1.0f - ffb;
-                    const float f00 = __fmul_rn(na, nb), f01 = __fmul_rn(ffa, nb), f10 = __fmul_rn(na, ffb),
-                                f11 = __fmul_rn(ffa, ffb);
-                    su = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t00.x, f00), __fmul_rn(t01.x, f01)),
-                                             __fmul_rn(t10.x, f10)), __fmul_rn(t11.x, f11));
-                    sv = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t00.y, f00), __fmul_rn(t01.y, f01)),
-                                             __fmul_rn(t10.y, f10)), __fmul_rn(t11.y, f11));
-                } else if (X <= -1.0f || Y <= -1.0f || X >= (float)W || Y >= (float)H) {
-                    su = 0.f; sv = 0.f; strict = 0;      // every tap lies outside the frame
-                } else {
-                    const float4 r = slow_sample(G + fbase, MASKS ? Gm + fbase : nullptr, H, W, X, Y);
-                    su = r.x; sv = r.y; strict = r.z != 0.f;
-                }
-                prow[j * TS] = ADD ? make_float2(__fadd_rn(pv.x, su), __fadd_rn(pv.y, sv)) : make_float2(su, sv);
-                mrow[j * TS] = (uint8_t)(pm[j] & strict & 1u);
+                need_global = need_global || !(inbox || ix < -1 || iy < -1 || ix >= W || iy >= H);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.bempty[b]);
+            if (__any_sync(0xffffffffu, need_global)) {
+                mixed_rows<MASKS, ADD, SM>(&ps, &bs, &sm.bempty[b], info, tile, G, Gm, sign, H, W, negzero2);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 pv = unpack2(p[j]);
+                    const bool inbox = (unsigned)dx[j] < (unsigned)(BW - 1) && (unsigned)dy[j] < (unsigned)(BH - 1);
+                    float su = 0.f, sv = 0.f;
+                    unsigned strict = 0;
+                    if (inbox) {
+                        const float2* v = bs.v + (dy[j] * BW + dx[j]);
+                        const float2 t00 = v[0], t01 = v[1], t10 = v[BW], t11 = v[BW + 1];
+                        const int a = fa[j], bb = fb[j];
+                        const unsigned za = a == 0, zb = bb == 0;
+                        if (MASKS) {
+                            const uint8_t* mm = bs.m + (dy[j] * BMW + dx[j] + info.y);
+                            strict = mm[0] & (mm[1] | za) & (mm[BMW] | zb) & (mm[BMW + 1] | za | zb);
+                        } else {
+                            const int ix = dx[j] + info.x, iy = dy[j] + info.z;
+                            strict = (ix >= 0 && iy >= 0 && (ix + 1 < W || (za && ix < W)) && (iy + 1 < H || (zb && iy < H))) ? 1u : 0u;
+                        }
+                        const float ffa = (float)a * (1.0f / 32.0f), ffb = (float)bb * (1.0f / 32.0f);
+                        const float na = 1.0f - ffa, nb = 1.0f - ffb;
+                        const float f00 = __fmul_rn(na, nb), f01 = __fmul_rn(ffa, nb), f10 = __fmul_rn(na, ffb),
+                                    f11 = __fmul_rn(ffa, ffb);
+                        su = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t00.x, f00), __fmul_rn(t01.x, f01)),
+                                                 __fmul_rn(t10.x, f10)), __fmul_rn(t11.x, f11));
+                        sv = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t00.y, f00), __fmul_rn(t01.y, f01)),
+                                                 __fmul_rn(t10.y, f10)), __fmul_rn(t11.y, f11));
+                    }
+                    prow[j * TS] = ADD ? make_float2(__fadd_rn(pv.x, su), __fadd_rn(pv.y, sv)) : make_float2(su, sv);
+                    mrow[j * TS] = (uint8_t)(pm[j] & strict & 1u);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.bempty[b]);
+            }
         }
         // the warp's 4 result rows go out as two bulk tensor stores (clipped at the frame border by the hardware)
         fence_async_smem();
@@ -462,6 +573,12 @@ constexpr int WS_NP = 5, WS_NB = 3, WS_LA = 1;   // 5 P stages, 3 box stages (LA
 constexpr int WS_PW = 2;                         // producer warps: box warp + P loader warp
 
 }  // namespace c3ws
+
+unsigned long long c3_ws_mixed_count() {
+    unsigned long long v = 0;
+    if (cudaMemcpyFromSymbol(&v, c3ws::g_mixed_warp_tiles, sizeof(v)) != cudaSuccess) cudaGetLastError();
+    return v;
+}
 
 bool c3_ws_enabled() {
     static int state = -1;

@@ -13,6 +13,8 @@ namespace ofk {
 void set_error(const char* fmt, ...);
 extern std::atomic<unsigned long long> g_launches;
 extern std::atomic<unsigned long long> g_paths[4];   // see ofk_rt_path_count
+unsigned long long c3_ws_mixed_count();               // combine3_ws.cu
+unsigned long long warp_ws_mixed_count();             // warp_t_ws.cu
 
 #define OFK_CHECK_ARG(cond, ...)                \
     do {                                        \

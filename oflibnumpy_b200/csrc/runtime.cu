@@ -40,7 +40,12 @@ using namespace ofk;
 extern "C" const char* ofk_last_error(void) { return t_error; }
 extern "C" int ofk_version(void) { return OFK_VERSION; }
 extern "C" unsigned long long ofk_rt_launch_count(void) { return g_launches.load(); }
-extern "C" unsigned long long ofk_rt_path_count(int which) { return (which >= 0 && which < 4) ? g_paths[which].load() : 0ull; }
+extern "C" unsigned long long ofk_rt_path_count(int which) {
+    if (which >= 0 && which < 4) return g_paths[which].load();
+    if (which == 4) return c3_ws_mixed_count();      // synchronous reads of device counters (current device)
+    if (which == 5) return warp_ws_mixed_count();
+    return 0ull;
+}
 
 // ------------------------------------------------------------------------------------------------------- runtime
 extern "C" int ofk_rt_device_count(int* count) {

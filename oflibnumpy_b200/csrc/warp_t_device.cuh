@@ -9,12 +9,10 @@ namespace ofk {
 // of line, by-value in / out (no stack traffic). C interleaved uint8 channels (C <= 4): returns the C result bytes in
 // bits 0..8C-1 and the validity in bit 32.
 template <int C>
-static __device__ __noinline__ unsigned long long border_px_u8c(const uint8_t* __restrict__ p,
-                                                                const uint8_t* __restrict__ pm, float X, float Y, int H,
-                                                                int W, int half_even, int rule) {
-    const QCoord qx = quantise(X), qy = quantise(Y);
-    const int ix = qx.i, iy = qy.i;
-    const QWeights w = qweights(qx.f, qy.f);
+static __device__ __noinline__ unsigned long long border_px_u8q(const uint8_t* __restrict__ p,
+                                                                const uint8_t* __restrict__ pm, int ix, int iy, int a,
+                                                                int b, int H, int W, int half_even, int rule) {
+    const QWeights w = qweights(a, b);
     const bool in[4] = {(unsigned)ix < (unsigned)W && (unsigned)iy < (unsigned)H,
                         (unsigned)(ix + 1) < (unsigned)W && (unsigned)iy < (unsigned)H,
                         (unsigned)ix < (unsigned)W && (unsigned)(iy + 1) < (unsigned)H,
@@ -40,6 +38,14 @@ static __device__ __noinline__ unsigned long long border_px_u8c(const uint8_t* _
         v |= (unsigned long long)r << (8 * c);
     }
     return v | (mask_rule_pass(S, rule) ? (1ull << 32) : 0ull);
+}
+// the same from float coordinates (exact quantiser, any value)
+template <int C>
+static __device__ __forceinline__ unsigned long long border_px_u8c(const uint8_t* __restrict__ p,
+                                                                   const uint8_t* __restrict__ pm, float X, float Y,
+                                                                   int H, int W, int half_even, int rule) {
+    const QCoord qx = quantise(X), qy = quantise(Y);
+    return border_px_u8q<C>(p, pm, qx.i, qy.i, qx.f, qy.f, H, W, half_even, rule);
 }
 
 // 3 channels, packed for warp_t.cu: result bytes in bits 0..23, validity in bit 24

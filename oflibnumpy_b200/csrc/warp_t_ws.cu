@@ -13,8 +13,9 @@
 //              the packed weights {(32-a)(32-b), a(32-b)} and {(32-a)b, ab}. The three result bytes and the validity
 //              byte are written over the flow tile in place; the warp's four rows leave through TMA stores (clipped at
 //              the frame border by the hardware).
-// Pixels whose taps are not covered by the box take the exact global-memory path of warp_t.cu individually.
+// Pixels whose taps are not covered by the box (discontinuous or noisy flows) read the same words from global memory.
 // HBM traffic is the algorithmic 8 (flow) + 3 + 3 (image in / out) + 1 + 1 (flow mask, validity) bytes per pixel.
+#include <type_traits>
 #include <stdlib.h>
 
 #include "warp_t_device.cuh"
@@ -136,6 +137,23 @@ __device__ __forceinline__ void load_taps(const uint8_t* __restrict__ box, unsig
         w[2] = q[PITCH]; w[3] = q[PITCH + 1];
     }
 }
+// the same words from global memory: g = address of tap 00, all four taps inside the frame. Only words that overlap a
+// tap byte are read (the frame is a multiple of 16 bytes, so every such word lies inside the buffer).
+template <int C>
+__device__ __forceinline__ void load_taps_global(const uint8_t* __restrict__ g, int W, uint32_t (&w)[TapWords<C>::N]) {
+    const unsigned ph = (unsigned)(uintptr_t)g & 3u;
+    const uint32_t* q0 = reinterpret_cast<const uint32_t*>(g - ph);
+    const uint32_t* q1 = reinterpret_cast<const uint32_t*>(g - ph + (size_t)W * C);   // W % 16 == 0: same phase
+    if constexpr (C == 3) {
+        w[0] = __ldg(q0); w[1] = __ldg(q0 + 1); w[3] = __ldg(q1); w[4] = __ldg(q1 + 1);
+        if (ph == 3u) { w[2] = __ldg(q0 + 2); w[5] = __ldg(q1 + 2); }
+    } else if constexpr (C == 1) {
+        w[0] = __ldg(q0); w[2] = __ldg(q1);
+        if (ph == 3u) { w[1] = __ldg(q0 + 1); w[3] = __ldg(q1 + 1); }
+    } else {
+        w[0] = __ldg(q0); w[1] = __ldg(q0 + 1); w[2] = __ldg(q1); w[3] = __ldg(q1 + 1);
+    }
+}
 // phase 2: blend and store the C result bytes of the pixel at dst
 template <bool HALF_EVEN, int C>
 __device__ __forceinline__ void blend_store(const uint32_t (&w)[TapWords<C>::N], unsigned o, unsigned a, unsigned b,
@@ -156,6 +174,158 @@ __device__ __forceinline__ uint32_t taps_in_frame(int ix, int iy, int H, int W) 
     const bool x0 = (unsigned)ix < (unsigned)W, x1 = (unsigned)(ix + 1) < (unsigned)W;
     const bool y0 = (unsigned)iy < (unsigned)H, y1 = (unsigned)(iy + 1) < (unsigned)H;
     return (x0 && y0 ? 1u : 0u) | (x1 && y0 ? 1u << 8 : 0u) | (x0 && y1 ? 1u << 16 : 0u) | (x1 && y1 ? 1u << 24 : 0u);
+}
+
+// this thread's four pixels of a tile: flow-mask bytes, sample positions relative to the box (bytes / rows), integer
+// taps and 1/32-px fractions; returns whether all of them are covered by the box
+template <int C, bool READ_FM>
+__device__ __forceinline__ bool prepare_rows(const float2* frow, const uint8_t* mrow, float sign, float xg, float yg,
+                                             int4 info, unsigned (&fmv)[4], int (&dxb)[4], int (&dy)[4], int (&ixs)[4],
+                                             int (&iys)[4], unsigned (&fa)[4], unsigned (&fb)[4]) {
+    constexpr int BWB = box_bytes(C);
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 fj = frow[j * TS];
+        fmv[j] = READ_FM ? mrow[j * TS] : 1u;
+        const float X = __fmaf_rn(sign, fj.x, xg), Y = __fmaf_rn(sign, fj.y, yg + (float)j);
+        const QCoord qx = quantise_fast(X), qy = quantise_fast(Y);
+        ixs[j] = qx.i; iys[j] = qy.i;
+        fa[j] = (unsigned)qx.f; fb[j] = (unsigned)qy.f;
+        dxb[j] = C * qx.i - info.x;
+        dy[j] = qy.i - info.z;
+        // Covered by the box? Everything else is decided per pixel. No range test is needed for the fast quantiser:
+        // it is exact for |X| < 2^17, and beyond that (or for NaN / Inf) the integer it produces is far outside
+        // [-2^16, 2^16], so such a pixel can never pass the box test (frames are smaller than 32768).
+        ok = ok && (unsigned)dxb[j] <= (unsigned)(BWB - 2 * C) && (unsigned)dy[j] <= (unsigned)(BH - 2);
+    }
+    return ok;
+}
+
+// Taps of rows [J0, J1) of a warp's 4 x 32 pixels, all requested before the first use; then release of the box (with the
+// last rows), blend, validity.
+// MODE = BOX        : every pixel of the warp is covered by the box (shared memory only, no bounds tests).
+// MODE = BOX_OR_ZERO: the pixels not covered by the box have all four taps outside the frame (the usual case along the
+//                     frame border: the box is clamped to the frame) -- zero result, invalid.
+// MODE = MIXED      : a pixel outside the box whose four taps lie inside the frame reads the same aligned words from
+//                     global memory (same arithmetic); only the pixels that also touch the frame border go through
+//                     the out-of-line border routine.
+enum : int { BOX = 0, BOX_OR_ZERO = 1, MIXED_TAPS = 2 };
+template <int C, bool HALF_EVEN, int MM, int MODE, int J0, int J1, class BStage>
+__device__ __forceinline__ void sample_rows(const BStage& bs, uint8_t* orow, uint8_t* mrow, const unsigned (&fmv)[4],
+                                            const int (&dxb)[4], const int (&dy)[4], const int (&ixs)[4],
+                                            const int (&iys)[4], const unsigned (&fa)[4], const unsigned (&fb)[4],
+                                            int4 info, int n, const uint8_t* __restrict__ img,
+                                            const uint8_t* __restrict__ pmask, int H, int W, int rule, unsigned s_pass,
+                                            uint64_t* bempty, unsigned lane) {
+    constexpr int BWB = box_bytes(C);
+    constexpr int NW = TapWords<C>::N;
+    uint32_t w[4][NW];
+    uint32_t mt[4];
+    auto in_box = [&](int j) {
+        return MODE == BOX || ((unsigned)dxb[j] <= (unsigned)(BWB - 2 * C) && (unsigned)dy[j] <= (unsigned)(BH - 2));
+    };
+    auto interior = [&](int j) {   // all four taps inside the frame (the fast quantiser's garbage never is)
+        return (unsigned)ixs[j] < (unsigned)(W - 1) && (unsigned)iys[j] < (unsigned)(H - 1);
+    };
+#pragma unroll
+    for (int j = J0; j < J1; ++j) {
+        if (in_box(j)) {
+            load_taps<C>(bs.img, (unsigned)(dy[j] * BWB + dxb[j]), w[j]);
+            if (MM == MM_PMASK) {
+                const uint8_t* mm = bs.m + (dy[j] * BMW + (ixs[j] - info.y));
+                mt[j] = (uint32_t)mm[0] | ((uint32_t)mm[1] << 8) | ((uint32_t)mm[BMW] << 16) |
+                        ((uint32_t)mm[BMW + 1] << 24);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NW; ++k) w[j][k] = 0u;
+            mt[j] = 0u;
+            if (MODE == MIXED_TAPS && interior(j)) {
+                const long long px = (long long)n * ((long long)H * W) + ((long long)iys[j] * W + ixs[j]);
+                load_taps_global<C>(img + px * C, W, w[j]);
+                if (MM == MM_PMASK) {
+                    const uint8_t* mm = pmask + px;
+                    mt[j] = (uint32_t)__ldg(mm) | ((uint32_t)__ldg(mm + 1) << 8) | ((uint32_t)__ldg(mm + W) << 16) |
+                            ((uint32_t)__ldg(mm + W + 1) << 24);
+                }
+            }
+        }
+    }
+    if (J1 == 4) {
+        // everything loaded from the box is consumed by the reduction below before the stage is handed back
+        unsigned dep = 0;
+#pragma unroll
+        for (int j = J0; j < J1; ++j) dep |= w[j][NW - 1] | (MM == MM_PMASK ? mt[j] : 0u);
+        dep = __reduce_or_sync(0xffffffffu, dep);
+        if (lane == 0) mbar_arrive_after(bempty, dep);
+    }
+#pragma unroll
+    for (int j = J0; j < J1; ++j) {
+        uint8_t* dst = orow + j * (TS * C);
+        const bool boxed = in_box(j);
+        if (boxed || (MODE == MIXED_TAPS && interior(j))) {
+            // the byte phase of tap 00 inside its aligned word is the same in the box and in the frame: box starts and
+            // row pitches are multiples of 16 bytes
+            uint32_t W0, W1;
+            blend_store<HALF_EVEN, C>(w[j], (unsigned)dxb[j], fa[j], fb[j], dst, W0, W1);
+            if (MM == MM_PMASK) {
+                const unsigned valid = __dp2a_hi(W1, mt[j], __dp2a_lo(W0, mt[j], 0u)) >= s_pass;
+                mrow[j * TS] = (uint8_t)(valid & fmv[j]);
+            } else if (MM == MM_GEOM) {
+                unsigned valid = 1u;
+                if (boxed && !info.w) {         // tile-uniform: the box reaches over the frame border
+                    const uint32_t in = taps_in_frame(ixs[j], iys[j], H, W);
+                    valid = __dp2a_hi(W1, in, __dp2a_lo(W0, in, 0u)) >= s_pass;
+                }
+                mrow[j * TS] = (uint8_t)(valid & fmv[j]);
+            }
+        } else {
+            // (quantised coordinates beyond the fast quantiser's range are far outside the frame)
+            unsigned valid = 0u;
+            if (MODE == BOX_OR_ZERO || ixs[j] < -1 || iys[j] < -1 || ixs[j] >= W || iys[j] >= H) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) dst[c] = 0;      // every tap lies outside the frame
+            } else {
+                const size_t fbase = (size_t)n * ((size_t)H * W);
+                const unsigned long long r = border_px_u8q<C>(img + fbase * C, MM == MM_PMASK ? pmask + fbase : nullptr,
+                                                              ixs[j], iys[j], (int)fa[j], (int)fb[j], H, W, HALF_EVEN,
+                                                              rule);
+#pragma unroll
+                for (int c = 0; c < C; ++c) dst[c] = (uint8_t)(r >> (8 * c));
+                valid = (unsigned)(r >> 32);
+            }
+            if (MM != MM_NONE) mrow[j * TS] = (uint8_t)(valid & fmv[j] & 1u);
+        }
+    }
+}
+
+// The rare path, out of line so that it does not weigh on the register allocation of the kernel's main loop: redoes the
+// preparation from shared memory and samples with MODE = MIXED, two rows at a time.
+static __device__ unsigned long long g_mixed_warp_tiles;   // test hook: how often the out-of-line path ran (per warp and tile)
+
+template <int C, bool HALF_EVEN, int MM, bool FM, class SM>
+__device__ __noinline__ void mixed_rows(SM* sm, unsigned s, unsigned b, const uint8_t* __restrict__ img,
+                                        const uint8_t* __restrict__ pmask, float sign, int H, int W, int rule) {
+    typename SM::PStage* ps = &sm->ps[s];
+    const typename SM::BStage* bs = &sm->bs[b];
+    uint64_t* bempty = &sm->bempty[b];
+    const int4 info = sm->binfo[b][0], tile = sm->binfo[b][1];
+    const unsigned lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    if (lane == 0) atomicAdd(&g_mixed_warp_tiles, 1ull);
+    const unsigned s_pass = rule == OFK_RULE_STRICT ? 1024u : (rule == OFK_RULE_GT_HALF ? 513u : 512u);
+    const unsigned own = wrp * 4 * TS + lane;
+    uint8_t* mrow = ps->fm + own;
+    uint8_t* orow = reinterpret_cast<uint8_t*>(ps->f) + (wrp * 4 * TS * 8 + lane * C);
+    unsigned fmv[4], fa[4], fb[4];
+    int dxb[4], dy[4], ixs[4], iys[4];
+    prepare_rows<C, FM && MM != MM_NONE>(ps->f + own, mrow, sign, (float)(tile.x + (int)lane),
+                                         (float)(tile.y + (int)wrp * 4), info, fmv, dxb, dy, ixs, iys, fa, fb);
+    __syncwarp();   // every lane holds its flow values before the first result bytes overwrite the tile rows
+    sample_rows<C, HALF_EVEN, MM, MIXED_TAPS, 0, 2>(*bs, orow, mrow, fmv, dxb, dy, ixs, iys, fa, fb, info, tile.z, img, pmask, H,
+                                              W, rule, s_pass, bempty, lane);
+    sample_rows<C, HALF_EVEN, MM, MIXED_TAPS, 2, 4>(*bs, orow, mrow, fmv, dxb, dy, ixs, iys, fa, fb, info, tile.z, img, pmask, H,
+                                              W, rule, s_pass, bempty, lane);
 }
 
 template <int C, bool HALF_EVEN, int MM, bool FM, int NP, int NB, int LA, int PW>
@@ -300,16 +470,15 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 3) warp_u8_ws_kernel(const __
         uint8_t* mrow = ps.fm + own;                                        // validity bytes, in place
         uint8_t* orow = reinterpret_cast<uint8_t*>(ps.f) + own3;            // image bytes, in place
 
-        float2 f[4];
         unsigned fmv[4];
         int dxb[4], dy[4], ixs[4], iys[4];
         unsigned fa[4], fb[4];
         bool ok = true;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            f[j] = frow[j * TS];
+            const float2 fj = frow[j * TS];
             fmv[j] = (FM && MM != MM_NONE) ? mrow[j * TS] : 1u;
-            const float X = __fmaf_rn(sign, f[j].x, xg), Y = __fmaf_rn(sign, f[j].y, yg + (float)j);
+            const float X = __fmaf_rn(sign, fj.x, xg), Y = __fmaf_rn(sign, fj.y, yg + (float)j);
             const QCoord qx = quantise_fast(X), qy = quantise_fast(Y);
             ixs[j] = qx.i; iys[j] = qy.i;
             fa[j] = (unsigned)qx.f; fb[j] = (unsigned)qy.f;
@@ -356,43 +525,47 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 3) warp_u8_ws_kernel(const __
                 }
             }
         } else {
-            // some pixel of this warp is not covered by the box: per-pixel decision
-            const size_t fbase = (size_t)n * ((size_t)H * W);
+            // Some pixel of this warp is not covered by the box. Along the frame border that is the rule (the box is
+            // clamped to the frame): those pixels sample nothing but the zero border. Pixels that need taps from inside
+            // the frame (discontinuous or noisy flow, estimate too small) send the warp to the out-of-line path.
+            bool need_global = false;
+            const int fw = cold_value(W), fh = cold_value(H);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float X = __fmaf_rn(sign, f[j].x, xg), Y = __fmaf_rn(sign, f[j].y, yg + (float)j);
                 const bool inbox = (unsigned)dxb[j] <= (unsigned)(BWB - 2 * C) && (unsigned)dy[j] <= (unsigned)(BH - 2);
-                uint8_t* dst = orow + j * (TS * C);
-                unsigned valid;
-                if (inbox) {
-                    const unsigned o = (unsigned)(dy[j] * BWB + dxb[j]);
-                    uint32_t wj[TapWords<C>::N], W0, W1;
-                    load_taps<C>(bs.img, o, wj);
-                    blend_store<HALF_EVEN, C>(wj, o, fa[j], fb[j], dst, W0, W1);
-                    uint32_t in;
-                    if (MM == MM_PMASK) {
-                        const uint8_t* mm = bs.m + (dy[j] * BMW + (ixs[j] - info.y));
-                        in = (uint32_t)mm[0] | ((uint32_t)mm[1] << 8) | ((uint32_t)mm[BMW] << 16) |
-                             ((uint32_t)mm[BMW + 1] << 24);
-                    } else {
-                        in = taps_in_frame(ixs[j], iys[j], H, W);
-                    }
-                    valid = __dp2a_hi(W1, in, __dp2a_lo(W0, in, 0u)) >= s_pass;
-                } else if (X <= -1.0f || Y <= -1.0f || X >= (float)W || Y >= (float)H) {
-#pragma unroll
-                    for (int c = 0; c < C; ++c) dst[c] = 0;      // every tap lies outside the frame
-                    valid = 0u;
-                } else {
-                    const unsigned long long r = border_px_u8c<C>(img + fbase * C, MM == MM_PMASK ? pmask + fbase : nullptr,
-                                                                  X, Y, H, W, HALF_EVEN, rule);
-#pragma unroll
-                    for (int c = 0; c < C; ++c) dst[c] = (uint8_t)(r >> (8 * c));
-                    valid = (unsigned)(r >> 32);
-                }
-                if (MM != MM_NONE) mrow[j * TS] = (uint8_t)(valid & fmv[j] & 1u);
+                need_global = need_global || !(inbox || ixs[j] < -1 || iys[j] < -1 || ixs[j] >= fw || iys[j] >= fh);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.bempty[b]);
+            if (__any_sync(0xffffffffu, need_global)) {
+                mixed_rows<C, HALF_EVEN, MM, FM, SM>(&sm, s, b, img, pmask, sign, H, W, rule);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const bool inbox = (unsigned)dxb[j] <= (unsigned)(BWB - 2 * C) && (unsigned)dy[j] <= (unsigned)(BH - 2);
+                    uint8_t* dst = orow + j * (TS * C);
+                    unsigned valid = 0u;
+                    if (inbox) {
+                        const unsigned o = (unsigned)(dy[j] * BWB + dxb[j]);
+                        uint32_t wj[TapWords<C>::N], W0, W1;
+                        load_taps<C>(bs.img, o, wj);
+                        blend_store<HALF_EVEN, C>(wj, o, fa[j], fb[j], dst, W0, W1);
+                        uint32_t in;
+                        if (MM == MM_PMASK) {
+                            const uint8_t* mm = bs.m + (dy[j] * BMW + (ixs[j] - info.y));
+                            in = (uint32_t)mm[0] | ((uint32_t)mm[1] << 8) | ((uint32_t)mm[BMW] << 16) |
+                                 ((uint32_t)mm[BMW + 1] << 24);
+                        } else {
+                            in = taps_in_frame(ixs[j], iys[j], H, W);
+                        }
+                        valid = __dp2a_hi(W1, in, __dp2a_lo(W0, in, 0u)) >= s_pass;
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < C; ++c) dst[c] = 0;      // every tap lies outside the frame
+                    }
+                    if (MM != MM_NONE) mrow[j * TS] = (uint8_t)(valid & fmv[j] & 1u);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.bempty[b]);
+            }
         }
         // the warp's 4 result rows go out as bulk tensor stores (clipped at the frame border by the hardware)
         fence_async_smem();
@@ -488,6 +661,12 @@ static int launch_channels(bool half_even, const void* payload, const float* flo
 }
 
 }  // namespace wtws
+
+unsigned long long warp_ws_mixed_count() {
+    unsigned long long v = 0;
+    if (cudaMemcpyFromSymbol(&v, wtws::g_mixed_warp_tiles, sizeof(v)) != cudaSuccess) cudaGetLastError();
+    return v;
+}
 
 bool warp_ws_enabled() {
     static int state = -1;

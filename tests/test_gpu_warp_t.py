@@ -549,6 +549,60 @@ def test_tma_kernels_randomized(of):
     assert after[1] == before[1] and after[3] == before[3], (before, after)
 
 
+def _rough_flow(rng, h, w, kind):
+    """Flows whose 32 x 32 tiles do not fit one 48 x 48 box: motion boundaries and white noise."""
+    if kind == 'blocks':
+        bs = int(rng.choice([7, 20, 50]))
+        by, bx = (h + bs - 1) // bs, (w + bs - 1) // bs
+        mot = rng.uniform(-25, 25, (by, bx, 2)).astype(np.float32)
+        return np.ascontiguousarray(np.repeat(np.repeat(mot, bs, 0), bs, 1)[:h, :w])
+    amp = np.float32(rng.choice([8, 30, 200]))
+    return ((rng.random((h, w, 2)).astype(np.float32) - np.float32(0.5)) * (2 * amp)).astype(np.float32)
+
+
+def test_tma_kernels_discontinuous_and_noisy_flows(of):
+    """Motion boundaries and noise: most pixels of a tile lie outside the tile's box and fetch their taps from global
+    memory (the out-of-line path of the TMA kernels). Every kernel variant, against the oracle, bit for bit, twice."""
+    from oflibnumpy_b200 import _lib
+    lib = _lib.load()
+    before = [lib.ofk_rt_path_count(k) for k in range(6)]
+    rng = np.random.default_rng(4242)
+    for (h, w), kind in (((70, 144), 'blocks'), ((97, 208), 'noise'), ((130, 256), 'blocks'), ((64, 96), 'noise')):
+        n = 2
+        a = np.stack([_rough_flow(rng, h, w, kind) for _ in range(n)])
+        b = np.stack([_rough_flow(rng, h, w, kind) for _ in range(n)])
+        am, bm = rng.random((n, h, w)) > 0.1, rng.random((n, h, w)) > 0.1
+        img = rng.integers(0, 256, (n, h, w, 4), dtype=np.uint8)
+        for r in ('t', 's'):
+            for rep in range(2):
+                v, m = of.FlowBatch(a, r, am).combine_with(of.FlowBatch(b, r, bm), 3).numpy()
+                for i in range(n):
+                    want = R.combine(R.make(a[i], r, am[i]), R.make(b[i], r, bm[i]), 3)
+                    same(m[i].view(np.bool_), want.mask)
+                    same(v[i], want.vecs)
+            same(of.combine_flows(a[0], b[0], 3, r), R.combine(R.make(a[0], r), R.make(b[0], r), 3).vecs)
+        for i in range(n):
+            fa, ra = of.Flow(a[i], 't', am[i]), R.make(a[i], 't', am[i])
+            for rep in range(2):
+                for chans in (0, 1, 3, 4):
+                    im = img[i, ..., 0] if chans == 0 else np.ascontiguousarray(img[i, ..., :chans])
+                    same(fa.apply(im), R.apply(ra, im))
+                    for kw in ({}, {'target_mask': bm[i]}, {'consider_mask': False}):
+                        w1, m1 = fa.apply(im, return_valid_area=True, **kw)
+                        w2, m2 = R.apply(ra, im, return_valid_area=True, **kw)
+                        same(w1, w2)
+                        same(m1, m2)
+                res = fa.apply(of.Flow(b[i], 't', bm[i]))
+                want = R.apply(ra, R.make(b[i], 't', bm[i]))
+                same(res.mask, want.mask)
+                same(res.vecs, want.vecs)
+    after = [lib.ofk_rt_path_count(k) for k in range(6)]
+    assert after[0] > before[0] and after[2] > before[2]
+    assert after[1] == before[1] and after[3] == before[3], (before, after)
+    # ... and inside them, warps did fetch taps from global memory (counters 4 / 5: composition / image kernels)
+    assert after[4] > before[4] and after[5] > before[5], (before, after)
+
+
 def test_tma_kernels_long_pipelines():
     """The same randomised parity suite with the persistent grids capped at 3 CTAs (OFK_WS_MAX_CTAS, read once per
     process): every CTA then walks through dozens of tiles, so the stage rings wrap around and every barrier phase flips
@@ -560,6 +614,7 @@ def test_tma_kernels_long_pipelines():
             "import oflibnumpy_b200 as of\n"
             "import test_gpu_warp_t as t\n"
             "t.test_tma_kernels_randomized(of)\n"
+            "t.test_tma_kernels_discontinuous_and_noisy_flows(of)\n"
             "t.test_zero_test_probe_and_scan(of)\n"
             "t.test_batched_equals_per_frame(of)\n"
             "print('long pipelines ok')\n") % (os.path.dirname(here), here)
