@@ -203,6 +203,17 @@ struct Slot {
     char* dev = nullptr;
     size_t cap = 0;
     size_t used = 0;
+    // Small results (the zero flags of ofh_combine3) come back through a pinned staging buffer: a device-to-host copy
+    // into the caller's pageable array would block the host until the chunk has finished and serialise the ring.
+    int* hflags = nullptr;
+    size_t hflags_cap = 0;       // ints
+    int* flags_dst = nullptr;    // where the staged flags of the chunk in flight belong
+    size_t flags_n = 0;
+    void deliver() {             // call after the slot's stream has drained
+        if (flags_dst != nullptr && flags_n) memcpy(flags_dst, hflags, flags_n * sizeof(int));
+        flags_dst = nullptr;
+        flags_n = 0;
+    }
     void* take(size_t bytes) {
         size_t off = (used + 255) & ~size_t(255);
         used = off + bytes;
@@ -222,6 +233,7 @@ int ring_prepare(int device, size_t bytes_per_slot) {
             cudaSetDevice(g_ring.device);
             for (auto& s : g_ring.slot) {
                 if (s.dev) cudaFree(s.dev);
+                if (s.hflags) cudaFreeHost(s.hflags);
                 if (s.st) cudaStreamDestroy(s.st);
                 s = Slot();
             }
@@ -230,6 +242,8 @@ int ring_prepare(int device, size_t bytes_per_slot) {
     }
     OFK_CUDA(cudaSetDevice(device));
     for (auto& s : g_ring.slot) {
+        s.flags_dst = nullptr;   // nothing is pending between calls (a call that failed half-way drops its flags)
+        s.flags_n = 0;
         if (!s.st) OFK_CUDA(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
         if (s.cap < bytes_per_slot) {
             if (s.dev) {
@@ -326,7 +340,15 @@ extern "C" int ofh_combine3(const float* A, const uint8_t* Am, const float* B, c
         Slot& s = g_ring.slot[chunk % kSlots];
         const int cn = (N - n0 < cf) ? (N - n0) : cf;
         OFK_CUDA(cudaStreamSynchronize(s.st));
+        s.deliver();
         s.used = 0;
+        if (flags && s.hflags_cap < (size_t)2 * cf) {
+            if (s.hflags) OFK_CUDA(cudaFreeHost(s.hflags));
+            s.hflags = nullptr;
+            s.hflags_cap = 0;
+            OFK_CUDA(cudaHostAlloc((void**)&s.hflags, sizeof(int) * 2 * cf, cudaHostAllocDefault));
+            s.hflags_cap = (size_t)2 * cf;
+        }
         float* dA = (float*)s.take(b_flow * cn);
         float* dB = (float*)s.take(b_flow * cn);
         float* dO = (float*)s.take(b_flow * cn);
@@ -342,9 +364,16 @@ extern "C" int ofh_combine3(const float* A, const uint8_t* Am, const float* B, c
         if (rc != OFK_OK) return rc;
         OFH_COPY_OUT(out + (size_t)n0 * px * 2, dO, b_flow * cn);
         OFH_COPY_OUT(out_mask + (size_t)n0 * px, dOm, b_m * cn);
-        if (flags) OFH_COPY_OUT(flags + (size_t)n0 * 2, dF, sizeof(int) * 2 * cn);
+        if (flags) {
+            OFH_COPY_OUT(s.hflags, dF, sizeof(int) * 2 * cn);
+            s.flags_dst = flags + (size_t)n0 * 2;
+            s.flags_n = (size_t)2 * cn;
+        }
     }
-    for (auto& s : g_ring.slot) OFK_CUDA(cudaStreamSynchronize(s.st));
+    for (auto& s : g_ring.slot) {
+        OFK_CUDA(cudaStreamSynchronize(s.st));
+        s.deliver();
+    }
     return OFK_OK;
 }
 
@@ -355,6 +384,7 @@ extern "C" int ofh_release(void) {
         for (auto& s : g_ring.slot) {
             if (s.st) cudaStreamSynchronize(s.st);
             if (s.dev) cudaFree(s.dev);
+            if (s.hflags) cudaFreeHost(s.hflags);
             if (s.st) cudaStreamDestroy(s.st);
             s = Slot();
         }
