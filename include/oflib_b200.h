@@ -177,6 +177,21 @@ int ofk_resize_flow(const float* vecs, const uint8_t* mask, float* out_vecs, uin
 /* out[i] = v[i] > thr (the `> .99` mask test of combine_with mode 2 / ref 't', flow_class.py:1410). */
 int ofk_greater(const float* v, float thr, uint8_t* out, size_t n, ofk_stream_t stream);
 
+/* Flow.visualise (flow_class.py:869-951), one frame per call.
+ * ofk_vis_magnitude: mag[p] = magnitude of threshold_vectors(flow)[p] as cv2.cartToPolar computes it (float32);
+ *   *max_out (device float) receives the maximum.
+ * ofk_kth_smallest: exact order statistics of a NON-NEGATIVE float32 device array: out[q] (device) = the element of
+ *   rank ranks_host[q] (0-based, host array, 1 <= n_ranks <= 4) in sorted order -- the values numpy.percentile
+ *   interpolates between. ws: device workspace of ofk_kth_smallest_workspace(n_ranks) bytes.
+ * ofk_visualise: out uint8 [H,W,3]; mode 0 'hsv', 1 'rgb', 2 'bgr'; range_max = magnitude mapped to full saturation
+ *   (the caller derives it from the 99th percentile / maximum as the reference does); mask may be NULL (all valid). */
+int ofk_vis_magnitude(const float* flow, float thr, float* mag, float* max_out, size_t n_pixels, ofk_stream_t stream);
+size_t ofk_kth_smallest_workspace(int n_ranks);
+int ofk_kth_smallest(const float* values, size_t n, const unsigned long long* ranks_host, int n_ranks, float* out,
+                     void* ws, size_t ws_bytes, ofk_stream_t stream);
+int ofk_visualise(const float* flow, const uint8_t* mask, float thr, int mode, int show_mask, int show_mask_borders,
+                  float range_max, uint8_t* out, int H, int W, ofk_stream_t stream);
+
 /* Point tracking through an 's' flow with float points: replaces bilinear_interpolation + `pts + flow_vecs`
  * (utils.py:161-196,605,608). flow [H,W,2] (one frame), pts float64 [n][2] (row, col); out float64 [n][2];
  * bad (int32, device) is set to 1 if any point lies outside the flow area (the reference raises IndexError). */

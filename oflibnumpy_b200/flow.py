@@ -575,6 +575,25 @@ class Flow(object):
             _, area = _ops.forward_s(self._vd(), -1.0, None, self._md(), self._md() if consider_mask else None)
         return area.numpy()[0].view(np.bool_)
 
+    def visualise(self, mode, show_mask=None, show_mask_borders=None, range_max=None):
+        """Flow as an rgb / bgr / hsv image (flow_class.py:869-951): hue = direction, saturation = magnitude scaled to
+        `range_max` (default: 99th percentile of the magnitudes, found by radix selection on the device), optionally
+        invalid areas greyed out and the mask outline in black. Returns a numpy uint8 array (H, W, 3)."""
+        show_mask = False if show_mask is None else show_mask
+        show_mask_borders = False if show_mask_borders is None else show_mask_borders
+        if not isinstance(show_mask, bool):
+            raise TypeError("Error visualising flow: Show_mask needs to be boolean")
+        if not isinstance(show_mask_borders, bool):
+            raise TypeError("Error visualising flow: Show_mask_borders needs to be boolean")
+        if range_max is not None:
+            if not isinstance(range_max, (float, int)):
+                raise TypeError("Error visualising flow: Range_max needs to be an integer or a float")
+            if range_max <= 0:
+                raise ValueError("Error visualising flow: Range_max needs to be larger than zero")
+        if mode not in ('hsv', 'rgb', 'bgr'):
+            raise ValueError("Error visualising flow: Mode needs to be either 'bgr', 'rgb', or 'hsv'")
+        return _ops.visualise(self._vd(), self._md(), mode, show_mask, show_mask_borders, range_max, DEFAULT_THRESHOLD)
+
     def get_padding(self):
         """[top, bottom, left, right] as in the reference (flow_class.py:1197-1228); masked min/max on the device."""
         mny, mxy, mnx, mxx = (float(x) for x in _ops.extent(self._vd(), self._md(), 1.0 if self._ref == 't' else -1.0,

@@ -417,3 +417,44 @@ def track(f: F, pts, int_out=False, s_exact_mode=False):
     if int_out:
         out = np.round(out).astype('i')
     return out
+
+
+# ----------------------------------------------------------------------------- visualisation (flow_class.py:869-951)
+def visualise(f: F, mode: str, show_mask: bool = False, show_mask_borders: bool = False, range_max=None):
+    """Flow.visualise: hue from cv2.cartToPolar's angle, saturation from the magnitude scaled to `range_max`
+    (default: 99th percentile, numpy.percentile), value 255 (180 on invalid pixels with show_mask), mask outline via
+    cv2.findContours / drawContours, HSV -> RGB in numpy. Third-party calls are kept at the reference's call sites."""
+    fl = threshold(f.vecs)                                                   # :895
+    hsv = np.zeros((fl.shape[0], fl.shape[1], 3), 'f')
+    mag, ang = cv2.cartToPolar(fl[..., 0], fl[..., 1], angleInDegrees=True)  # :900
+    hsv[..., 0] = np.mod(ang, 360) / 2
+    hsv[..., 2] = 255
+    if show_mask:
+        hsv[np.invert(f.mask), 2] = 180                                      # :906
+    if range_max is None:                                                    # :909-915
+        if np.percentile(mag, 99) > 0:
+            range_max = float(np.percentile(mag, 99))
+        elif np.max(mag):
+            range_max = float(np.max(mag))
+        else:
+            range_max = 1
+    hsv[..., 1] = np.clip(mag * 255 / range_max, 0, 255)                     # :920
+    if show_mask_borders:                                                    # :923-926
+        contours, _ = cv2.findContours((255 * f.mask).astype('uint8'), cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
+        cv2.drawContours(hsv, contours, -1, (0, 0, 0), 1)
+    if mode == 'hsv':
+        return np.round(hsv).astype('uint8')
+    h = hsv[..., 0] / 180                                                    # :931-945
+    s = hsv[..., 1] / 255
+    v = hsv[..., 2] / 255
+    i = np.int_(h * 6.)
+    fr = h * 6. - i
+    i = np.ravel(i)
+    t = np.ravel(1. - fr)
+    fr = np.ravel(fr)
+    i %= 6
+    c_list = (1 - np.ravel(s) * np.vstack([np.zeros_like(fr), np.ones_like(fr), fr, t])) * np.ravel(v)
+    order = np.array([[0, 3, 1], [2, 0, 1], [1, 0, 3], [1, 2, 0], [3, 1, 0], [0, 1, 2]])
+    rgb = c_list[order[i], np.arange(np.prod(h.shape))[:, None]].reshape(*h.shape, 3)
+    rgb = np.round(rgb * 255).astype('uint8')
+    return rgb[..., ::-1] if mode == 'bgr' else rgb

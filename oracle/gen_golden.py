@@ -314,7 +314,38 @@ def case_datasets():
     return d
 
 
+def visualise_inputs(seed=41, h=45, w=64):
+    """Flows for the visualisation fixtures: smooth + noise (all hues), a zero flow, a flow whose 99th percentile is 0."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[:h, :w].astype(np.float32)
+    swirl = np.stack([(yy - h / 2) * 0.4 + rng.standard_normal((h, w)) * 0.3,
+                      -(xx - w / 2) * 0.3 + rng.standard_normal((h, w)) * 0.3], -1).astype(np.float32)
+    swirl[5:9, 7:12] = 1e-4                                                # below the threshold -> exactly zero
+    mask = rng.random((h, w)) > 0.15
+    mask[10:20, 30:50] = False                                             # a hole with a clean outline
+    mask[0, :5] = False
+    sparse = np.zeros((h, w, 2), np.float32)
+    sparse.reshape(-1, 2)[rng.integers(0, h * w, 20)] = rng.uniform(-9, 9, (20, 2))   # p99 == 0, max > 0
+    return {'swirl': swirl, 'sparse': sparse, 'zero': np.zeros((h, w, 2), np.float32)}, mask
+
+
+def case_visualise():
+    """Flow.visualise (flow_class.py:869-951) of the unmodified reference: all modes, mask options, range_max."""
+    flows, mask = visualise_inputs()
+    d = {'in_mask': mask}
+    for name, v in flows.items():
+        d['in_' + name] = v
+        fl = ref.Flow(v, 't', mask)
+        for mode in ('hsv', 'rgb', 'bgr'):
+            d['out_%s_%s' % (name, mode)] = fl.visualise(mode)
+        d['out_%s_rgb_mask' % name] = fl.visualise('rgb', show_mask=True)
+        d['out_%s_hsv_borders' % name] = fl.visualise('hsv', show_mask=True, show_mask_borders=True)
+        d['out_%s_bgr_range' % name] = fl.visualise('bgr', show_mask_borders=True, range_max=7.5)
+    return d
+
+
 CASES = {
+    'visualise': case_visualise,
     'datasets': case_datasets,
     'warp_t': case_warp_t,
     'warp_t_padded': case_warp_t_padded,

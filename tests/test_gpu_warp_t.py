@@ -684,3 +684,31 @@ def test_dataset_constructors_decode_on_device(of):
         of.Flow.from_kitti(kp, load_valid='yes')
     with pytest.raises(ValueError):
         of.Flow.from_kitti(sp)
+
+
+def test_visualise_matches_reference_and_oracle(of):
+    """Flow.visualise on the device (ofk_vis_magnitude, ofk_kth_smallest, ofk_visualise) against the reference's own
+    outputs (tests/golden/visualise.npz) and, at 1080p, against the oracle: uint8 images, bit for bit -- hue from the
+    same FMA polynomial as cv2.cartToPolar, default range from an exact radix selection of the 99th percentile."""
+    from test_oracle_golden import VIS_VARIANTS
+    g = load_golden('visualise')
+    for name in ('swirl', 'sparse', 'zero'):
+        f = of.Flow(g['in_' + name], 't', g['in_mask'])
+        for key, kw in VIS_VARIANTS:
+            same(f.visualise(key.split('_')[0], **kw), g['out_%s_%s' % (name, key)])
+    rng = np.random.default_rng(12)
+    h, w = 1080, 1920
+    yy, xx = np.mgrid[:h, :w].astype(np.float32)
+    v = np.stack([8 * np.sin(xx / 40) * np.cos(yy / 55) + 0.002 * (xx - w / 2),
+                  6 * np.cos(xx / 35 + 1) * np.sin(yy / 45) - 0.003 * (yy - h / 2)], -1).astype(np.float32)
+    v += rng.standard_normal((h, w, 2)).astype(np.float32) * np.float32(0.05)
+    m = rng.random((h, w)) > 0.02
+    f, r = of.Flow(v, 's', m), R.make(v, 's', m)
+    for key, kw in VIS_VARIANTS:
+        same(f.visualise(key.split('_')[0], **kw), R.visualise(r, key.split('_')[0], **kw))
+    with pytest.raises(ValueError):
+        f.visualise('xyz')
+    with pytest.raises(TypeError):
+        f.visualise('rgb', show_mask=1)
+    with pytest.raises(ValueError):
+        f.visualise('rgb', range_max=0)

@@ -191,3 +191,19 @@ def test_dataset_loaders_match_reference():
         io.load_kitti(os.path.join(files, 'does_not_exist.png'))
     with pytest.raises(ValueError):
         io.load_sintel(os.path.join(files, 'kitti_sample.png'))
+
+
+def test_percentile_from_order_statistics_matches_numpy():
+    """The host half of Flow.visualise's default range: numpy.percentile(mag, 99) rebuilt from the two order
+    statistics the device selects (numpy's float32 virtual index and two-sided float32 lerp)."""
+    from oflibnumpy_b200 import _ops
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 3, 7, 100, 101, 1000, 2880, 45 * 64, 1080 * 1920 // 50, 1080 * 1920, 2160 * 3840):
+        for scale in (1e-3, 1.0, 300.0):
+            a = np.abs(rng.standard_normal(n) * scale).astype(np.float32)
+            if n > 10:
+                a[rng.integers(0, n, n // 3)] = 0
+            srt = np.sort(a)
+            k0, k1, gamma = _ops.percentile_plan(n)
+            got = _ops.percentile_from_order_stats(srt[k0], srt[k1], gamma)
+            assert got == float(np.percentile(a, 99)), (n, scale, got, float(np.percentile(a, 99)))
