@@ -603,6 +603,48 @@ def test_tma_kernels_discontinuous_and_noisy_flows(of):
     assert after[4] > before[4] and after[5] > before[5], (before, after)
 
 
+_FULL_SIZE_CODE = r'''
+import sys, hashlib, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import oflibnumpy_b200 as of
+import test_gpu_warp_t as t
+rng = np.random.default_rng(99)
+h, w, n = 1080, 1920, 3
+a = np.stack([t._rough_flow(rng, h, w, k) for k in ('blocks', 'noise', 'blocks')])
+b = np.stack([t._rough_flow(rng, h, w, k) for k in ('noise', 'blocks', 'blocks')])
+a[2] += t._smooth_flow(rng, h, w, 12)
+am, bm = rng.random((n, h, w)) > 0.02, rng.random((n, h, w)) > 0.02
+img = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+out = []
+for r in ('t', 's'):
+    v, m = of.FlowBatch(a, r, am).combine_with(of.FlowBatch(b, r, bm), 3).numpy()
+    out += [v, m]
+fb = of.FlowBatch(a, 't', am)
+res = fb.apply(img, return_valid_area=True)
+out += [x.numpy() for x in res]
+out += [x.numpy() for x in fb.apply(np.ascontiguousarray(img[..., 0]), target_masks=bm, return_valid_area=True)]
+print('DIGEST', hashlib.sha256(b''.join(np.ascontiguousarray(x).tobytes() for x in out)).hexdigest())
+'''
+
+
+def test_full_size_tma_and_gather_kernels_agree_on_rough_flows():
+    """Size-independent property at 1080p: the TMA kernels (with their out-of-line global-tap path) and the gather
+    kernels are independent implementations of the same arithmetic -- on motion boundaries and noise, where most of a
+    tile lies outside its box, their outputs must be byte-identical (composition both references, image warp with
+    geometric and resampled validity)."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = _FULL_SIZE_CODE % (os.path.dirname(here), here)
+    digests = []
+    for env_extra in ({}, {'OFK_C3_WS': '0', 'OFK_WARP_WS': '0'}):
+        res = subprocess.run([sys.executable, '-c', code], env=dict(os.environ, **env_extra), capture_output=True,
+                             text=True, timeout=900)
+        assert res.returncode == 0, res.stdout + res.stderr
+        digests.append([l for l in res.stdout.splitlines() if l.startswith('DIGEST')][0])
+    assert digests[0] == digests[1]
+
+
 def test_tma_kernels_long_pipelines():
     """The same randomised parity suite with the persistent grids capped at 3 CTAs (OFK_WS_MAX_CTAS, read once per
     process): every CTA then walks through dozens of tiles, so the stage rings wrap around and every barrier phase flips
