@@ -132,12 +132,20 @@ extern "C" int ofk_rt_host_unregister(void* hptr) {
     OFK_CUDA(cudaHostUnregister(hptr));
     return OFK_OK;
 }
+// Large copies from / to pageable memory go through staging.cu (worker threads + pinned pieces); everything else is a
+// plain cudaMemcpyAsync.
 extern "C" int ofk_rt_memcpy_h2d(void* dst, const void* src, size_t bytes, ofk_stream_t s) {
-    if (bytes) OFK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, as_stream(s)));
+    if (bytes == 0) return OFK_OK;
+    const int staged = staged_copy(dst, src, bytes, true, as_stream(s));
+    if (staged < 0) return staged;
+    if (staged == 0) OFK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, as_stream(s)));
     return OFK_OK;
 }
 extern "C" int ofk_rt_memcpy_d2h(void* dst, const void* src, size_t bytes, ofk_stream_t s) {
-    if (bytes) OFK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, as_stream(s)));
+    if (bytes == 0) return OFK_OK;
+    const int staged = staged_copy(dst, src, bytes, false, as_stream(s));
+    if (staged < 0) return staged;
+    if (staged == 0) OFK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, as_stream(s)));
     return OFK_OK;
 }
 extern "C" int ofk_rt_memcpy_d2d(void* dst, const void* src, size_t bytes, ofk_stream_t s) {
