@@ -23,10 +23,11 @@
 namespace ofk {
 namespace {
 
-constexpr size_t kChunk = 2u << 20;        // bytes per staged piece
+constexpr size_t kChunk = 2u << 20;        // bytes per pinned buffer = largest staged piece
 constexpr int kThreads = 4;                // worker threads per transfer
 constexpr int kBufsPerThread = 3;          // pinned pieces in flight per thread
-constexpr size_t kMinStaged = 4u << 20;    // below this the plain path wins (thread start-up, event traffic)
+constexpr size_t kMinChunk = 256u << 10;   // smallest piece (small transfers still get every lane busy)
+constexpr size_t kMinStaged = 4u << 20;    // below this the plain path wins (thread start-up, event traffic: measured)
 
 struct Lane {
     char* pinned[kBufsPerThread] = {nullptr, nullptr, nullptr};
@@ -82,16 +83,17 @@ bool prepare(Stager& s, int device) {
 }
 
 // One worker: chunks t, t + kThreads, ... of the transfer. Returns the first CUDA error it met.
-cudaError_t run_lane(Stager& s, int t, int device, bool to_device, char* dst, const char* src, size_t bytes) {
+cudaError_t run_lane(Stager& s, int t, int device, bool to_device, char* dst, const char* src, size_t bytes,
+                     size_t chunk) {
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return e;
     Lane& ln = s.lane[t];
-    const size_t n_chunks = (bytes + kChunk - 1) / kChunk;
+    const size_t n_chunks = (bytes + chunk - 1) / chunk;
     size_t issued = 0;                                   // chunks of this lane handed to the DMA engine so far
     size_t pending_off[kBufsPerThread], pending_len[kBufsPerThread];
     for (size_t k = (size_t)t; k < n_chunks; k += kThreads, ++issued) {
         const int b = (int)(issued % kBufsPerThread);
-        const size_t off = k * kChunk, len = bytes - off < kChunk ? bytes - off : kChunk;
+        const size_t off = k * chunk, len = bytes - off < chunk ? bytes - off : chunk;
         if (issued >= (size_t)kBufsPerThread) {          // the piece that used this buffer must have left it
             if ((e = cudaEventSynchronize(ln.ev[b])) != cudaSuccess) return e;
             if (!to_device) memcpy(dst + pending_off[b], ln.pinned[b], pending_len[b]);
@@ -133,14 +135,19 @@ int staged_copy(void* dst, const void* src, size_t bytes, bool to_device, cudaSt
     // the transfer starts after everything already queued on the caller's stream
     OFK_CUDA(cudaEventRecord(s.before, user));
     OFK_CUDA(cudaStreamWaitEvent(s.copy, s.before, 0));
+    // piece size: two pieces per lane at least, between kMinChunk and the pinned buffer size, a multiple of 4 KiB
+    size_t chunk = bytes / (2 * kThreads);
+    chunk = chunk < kMinChunk ? kMinChunk : (chunk > kChunk ? kChunk : chunk);
+    chunk = (chunk + 4095) & ~size_t(4095);
+    if (chunk > kChunk) chunk = kChunk;
     cudaError_t errs[kThreads];
     std::vector<std::thread> workers;
     workers.reserve(kThreads - 1);
     for (int t = 1; t < kThreads; ++t)
         workers.emplace_back([&, t]() {
-            errs[t] = run_lane(s, t, device, to_device, static_cast<char*>(dst), static_cast<const char*>(src), bytes);
+            errs[t] = run_lane(s, t, device, to_device, static_cast<char*>(dst), static_cast<const char*>(src), bytes, chunk);
         });
-    errs[0] = run_lane(s, 0, device, to_device, static_cast<char*>(dst), static_cast<const char*>(src), bytes);
+    errs[0] = run_lane(s, 0, device, to_device, static_cast<char*>(dst), static_cast<const char*>(src), bytes, chunk);
     for (auto& w : workers) w.join();
     for (int t = 0; t < kThreads; ++t)
         if (errs[t] != cudaSuccess) {

@@ -763,7 +763,7 @@ def test_large_pageable_copies_are_staged_correctly(of):
     from oflibnumpy_b200.device import DeviceArray
     rng = np.random.default_rng(8)
     mb = 1 << 20
-    for nbytes in (4 * mb - 1, 4 * mb, 4 * mb + 1, 6 * mb - 3, 8 * mb, 8 * mb + 1, 37 * mb + 5, 4 * 2 * mb * 3 + 17):
+    for nbytes in (mb - 1, mb, mb + 1, 2 * mb + 4097, 4 * mb - 1, 6 * mb - 3, 8 * mb + 1, 16 * mb, 37 * mb + 5, 4 * 2 * mb * 3 + 17):
         a = rng.integers(0, 256, nbytes, dtype=np.uint8)
         keep = a.copy()
         d = DeviceArray.from_numpy(a)
