@@ -77,10 +77,20 @@ def from_transforms(transform_list, shape, ref):
 
 
 # ------------------------------------------------------------------------------------------------- warp
+def upload_flow_array(flow, error_string):
+    """validate_flow_array + upload; float32 input is tested for NaN / Inf on the device after the upload."""
+    on_device = isinstance(flow, np.ndarray) and flow.dtype == np.float32
+    flow = validate_flow_array(flow, error_string, finite_on_device=True)
+    d = DeviceArray.from_numpy(flow[None])
+    if on_device and not _ops.all_finite(d):
+        raise ValueError(error_string + "Flow array contains NaN or Inf values")
+    return flow, d
+
+
 def apply_flow(flow, target, ref, mask=None):
     """Warp ``target`` (H,W[,C]) with ``flow`` (H,W,2): reference ``apply_flow`` (utils.py:199-261)."""
     ref = get_valid_ref(ref)
-    flow = validate_flow_array(flow, "Error applying flow to a target: ")
+    flow, dflow = upload_flow_array(flow, "Error applying flow to a target: ")
     if not isinstance(target, np.ndarray):
         raise TypeError("Error applying flow to a target: Target needs to be a numpy array")
     if target.ndim < 2 or target.ndim > 3:
@@ -95,7 +105,6 @@ def apply_flow(flow, target, ref, mask=None):
         if mask.dtype != bool:
             raise TypeError("Error applying flow to a target: Mask needs to be boolean")
     t = target[..., None] if target.ndim == 2 else target
-    dflow = DeviceArray.from_numpy(flow[None])
     if ref == 't':
         _ops.dtype_code(t.dtype)
         out, _ = _ops.warp_t(dflow, -1.0, DeviceArray.from_numpy(t[None]))
@@ -144,11 +153,11 @@ def get_flow_padding(flow, ref):
 
 def is_zero_flow(flow, thresholded=None):
     """True if every vector is zero, optionally below the 1e-3 threshold (utils.py:527-544)."""
-    flow = validate_flow_array(flow, "Error checking whether flow is zero: ")
+    flow, dflow = upload_flow_array(flow, "Error checking whether flow is zero: ")
     thresholded = True if thresholded is None else thresholded
     if not isinstance(thresholded, bool):
         raise TypeError("Error checking whether flow is zero: Thresholded needs to be a boolean")
-    flags = _ops.nonzero_flags(DeviceArray.from_numpy(flow[None]), None, DEFAULT_THRESHOLD if thresholded else 0.0)
+    flags = _ops.nonzero_flags(dflow, None, DEFAULT_THRESHOLD if thresholded else 0.0)
     return bool(flags[0] == 0)
 
 
@@ -193,9 +202,9 @@ def _resize_device(vecs, mask, scale):
 
 def resize_flow(flow, scale):
     """Resize a flow field array, scaling the vector values accordingly (utils.py:493-524)."""
-    flow = validate_flow_array(flow, "Error resizing flow: ")
+    flow, dflow = upload_flow_array(flow, "Error resizing flow: ")
     scale = _valid_scale(scale)
-    out, _ = _ops.resize_flow(DeviceArray.from_numpy(flow[None]), None, scale[0], scale[1])
+    out, _ = _ops.resize_flow(dflow, None, scale[0], scale[1])
     return out.numpy()[0]
 
 

@@ -38,8 +38,11 @@ def validate_shape(shape):
         raise ValueError("Error creating flow from matrix: Dims need to be a list or a tuple of integers above zero")
 
 
-def validate_flow_array(flow, error_string=None):
-    """Host-side shape/type checks of a flow ndarray; returns it as C-contiguous float32 (finite check included)."""
+def validate_flow_array(flow, error_string=None, finite_on_device=False):
+    """Host-side shape/type checks of a flow ndarray; returns it as C-contiguous float32. The NaN / Inf test
+    (utils.py:55-56) runs here unless `finite_on_device` is set and the array is float32 already: the caller then
+    uploads first and tests on the device (upload_flow_array) -- np.isfinite costs more than the upload at megapixel
+    sizes. Other dtypes are always tested before the float32 cast, as the reference does."""
     prefix = error_string or ''
     if not isinstance(flow, np.ndarray):
         raise TypeError(prefix + "Flow is not a numpy array")
@@ -47,7 +50,7 @@ def validate_flow_array(flow, error_string=None):
         raise ValueError(prefix + "Flow array is not 3-dimensional")
     if flow.shape[2] != 2:
         raise ValueError(prefix + "Flow array does not have 2 channels")
-    if not np.isfinite(flow).all():
+    if not (finite_on_device and flow.dtype == np.float32) and not np.isfinite(flow).all():
         raise ValueError(prefix + "Flow array contains NaN or Inf values")
     return np.ascontiguousarray(flow, dtype=np.float32)
 

@@ -776,3 +776,20 @@ def test_large_pageable_copies_are_staged_correctly(of):
     g = f + f
     assert np.array_equal(g.vecs, v + v)
     assert np.array_equal((g - f).vecs, (v + v) - v)
+
+
+def test_functional_api_rejects_non_finite_flows(of):
+    """NaN / Inf in a flow array raise ValueError with the reference's message (utils.py:55-56); float32 arrays are
+    tested on the device after the upload, other dtypes on the host before the cast (1e300 is finite as float64)."""
+    img = np.zeros((64, 64, 3), np.uint8)
+    for bad in (np.nan, np.inf, -np.inf):
+        f = np.zeros((64, 64, 2), np.float32)
+        f[3, 4, 1] = bad
+        for fn in (lambda: of.apply_flow(f, img, 't'), lambda: of.is_zero_flow(f), lambda: of.resize_flow(f, 2),
+                   lambda: of.apply_flow(f.astype(np.float64), img, 't'), lambda: of.Flow(f)):
+            with pytest.raises(ValueError, match="NaN"):
+                fn()
+    big = np.zeros((64, 64, 2), np.float64)
+    big[0, 0, 0] = 1e300                                   # finite before the cast: accepted, as in the reference
+    with np.errstate(over='ignore'):
+        of.is_zero_flow(big)
