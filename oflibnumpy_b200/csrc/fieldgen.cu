@@ -10,8 +10,10 @@ namespace ofk {
 struct Mat3 {
     double m[9];
 };
+constexpr int kMatsPerLaunch = 32;   // host matrices travel as kernel parameters: 32 x 72 B
+constexpr int kRowsPerBlock = 4;     // rows per CTA: amortises the matrix fetch and the CTA launch over 4 x W pixels
 struct MatBatch {
-    Mat3 mats[8];
+    Mat3 mats[kMatsPerLaunch];
 };
 
 // AFFINE: last matrix row is exactly (0, 0, 1), so tz == 1.0 exactly and the two float64 divisions (the bulk of the
@@ -51,7 +53,7 @@ __device__ __forceinline__ void fill_row(const double* __restrict__ m, float* __
     }
 }
 
-// 2 pixels per thread -> one 16-byte store; rows are walked with a grid-stride loop over "pixel pairs".
+// 2 pixels per thread -> one 16-byte store; a CTA walks kRowsPerBlock rows with a grid-stride loop over "pixel pairs".
 __global__ void __launch_bounds__(256) from_matrix_kernel(const double* __restrict__ mats_dev, MatBatch host_mats,
                                                           int use_host, int n0, float sign, float* __restrict__ out,
                                                           int H, int W, int vec_ok) {
@@ -59,10 +61,14 @@ __global__ void __launch_bounds__(256) from_matrix_kernel(const double* __restri
     double m[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) m[k] = use_host ? host_mats.mats[n].m[k] : mats_dev[(size_t)(n0 + n) * 9 + k];
-    const int y = blockIdx.y;
-    float* row = out + (((size_t)(n0 + n) * H + y) * W) * 2;
-    if (m[6] == 0.0 && m[7] == 0.0 && m[8] == 1.0) fill_row<true>(m, row, y, sign, W, vec_ok);     // block-uniform
-    else fill_row<false>(m, row, y, sign, W, vec_ok);
+    const bool affine = m[6] == 0.0 && m[7] == 0.0 && m[8] == 1.0;                                  // block-uniform
+    for (int r = 0; r < kRowsPerBlock; ++r) {
+        const int y = blockIdx.y * kRowsPerBlock + r;
+        if (y >= H) break;
+        float* row = out + (((size_t)(n0 + n) * H + y) * W) * 2;
+        if (affine) fill_row<true>(m, row, y, sign, W, vec_ok);
+        else fill_row<false>(m, row, y, sign, W, vec_ok);
+    }
 }
 
 }  // namespace ofk
@@ -74,7 +80,7 @@ extern "C" int ofk_from_matrix(const double* mats, int mats_on_host, float sign,
     OFK_CHECK_ARG(mats && out, "ofk_from_matrix: NULL argument");
     OFK_CHECK_ARG(N >= 0 && H > 0 && W > 0, "ofk_from_matrix: bad shape N=%d H=%d W=%d", N, H, W);
     OFK_CHECK_ARG(sign == 1.0f || sign == -1.0f, "ofk_from_matrix: sign must be +1 or -1");
-    OFK_CHECK_ARG(H <= 65535, "ofk_from_matrix: H=%d exceeds 65535", H);
+    OFK_CHECK_ARG(H <= 65535 * kRowsPerBlock, "ofk_from_matrix: H=%d too large", H);
     OFK_CHECK_ARG(!mats_on_host || N <= 64, "ofk_from_matrix: host matrices limited to N <= 64 (got %d)", N);
     if (N == 0) return OFK_OK;
     cudaStream_t st = as_stream(stream);
@@ -82,19 +88,20 @@ extern "C" int ofk_from_matrix(const double* mats, int mats_on_host, float sign,
     const int per_thread = vec_ok ? 2 : 1;
     int bx = (W + 256 * per_thread - 1) / (256 * per_thread);
     if (bx < 1) bx = 1;
+    const int by = (H + kRowsPerBlock - 1) / kRowsPerBlock;
     if (mats_on_host) {
-        for (int n0 = 0; n0 < N; n0 += 8) {
+        for (int n0 = 0; n0 < N; n0 += kMatsPerLaunch) {
             MatBatch mb;
-            const int cnt = (N - n0 < 8) ? (N - n0) : 8;
+            const int cnt = (N - n0 < kMatsPerLaunch) ? (N - n0) : kMatsPerLaunch;
             for (int i = 0; i < cnt; ++i)
                 for (int k = 0; k < 9; ++k) mb.mats[i].m[k] = mats[(size_t)(n0 + i) * 9 + k];
-            from_matrix_kernel<<<dim3(bx, H, cnt), 256, 0, st>>>(nullptr, mb, 1, n0, sign, out, H, W, vec_ok);
+            from_matrix_kernel<<<dim3(bx, by, cnt), 256, 0, st>>>(nullptr, mb, 1, n0, sign, out, H, W, vec_ok);
             OFK_LAUNCHED();
         }
     } else {
         OFK_CHECK_ARG(N <= 65535, "ofk_from_matrix: N=%d exceeds 65535", N);
         MatBatch mb = {};
-        from_matrix_kernel<<<dim3(bx, H, N), 256, 0, st>>>(mats, mb, 0, 0, sign, out, H, W, vec_ok);
+        from_matrix_kernel<<<dim3(bx, by, N), 256, 0, st>>>(mats, mb, 0, 0, sign, out, H, W, vec_ok);
         OFK_LAUNCHED();
     }
     return OFK_OK;
