@@ -51,6 +51,7 @@ struct Smem {
     alignas(128) BStage bs[NB];
     alignas(16) int4 binfo[NB][2];   // {vx0, vx0 - mx0, by0, -}, {tx0, ty0, n, -}
     uint64_t pfull[NP], pempty[NP], bfull[NB], bempty[NB];
+    uint32_t sink[NCW];              // scratch words of mbar_arrive_after, one per consumer warp
 };
 
 struct Maps {
@@ -106,7 +107,7 @@ __device__ __forceinline__ void sample_rows(const BStage& bs, float2* prow, uint
                                             const unsigned (&pm)[4], const int (&dx)[4], const int (&dy)[4],
                                             const int (&fa)[4], const int (&fb)[4], int4 info, int n,
                                             const float2* __restrict__ G, const uint8_t* __restrict__ Gm, int H, int W,
-                                            uint64_t negzero2, uint64_t* bempty, unsigned lane) {
+                                            uint64_t negzero2, uint64_t* bempty, uint32_t* sink, unsigned lane) {
     const uint64_t one2 = pack2(1.0f, 1.0f);
     uint64_t t[4][4];
     unsigned m[4][4];
@@ -152,6 +153,8 @@ __device__ __forceinline__ void sample_rows(const BStage& bs, float2* prow, uint
         const unsigned ha = min(a, 1u), hb = min(bb, 1u);      // 1 where the right / lower taps have weight
         if (MASKS) {
             strict[j] = m[j][0] & (m[j][1] | ~ha) & (m[j][2] | ~hb) & (m[j][3] | ~(ha & hb)) & pm[j];
+            // out of line the loads may be scheduled in any order: make the release wait for every tap explicitly
+            if (MODE == MIXED_TAPS) strict[j] |= (unsigned)((t[j][0] | t[j][1] | t[j][2] | t[j][3]) >> 63) << 8;
         } else {
             const int ix = dx[j] + info.x, iy = dy[j] + info.z;
             strict[j] = (ix >= 0 && iy >= 0 && (ix + 1 < W || (a == 0 && ix < W)) &&
@@ -162,7 +165,7 @@ __device__ __forceinline__ void sample_rows(const BStage& bs, float2* prow, uint
         dep |= strict[j];
     }
     dep = __reduce_or_sync(0xffffffffu, dep);
-    if (lane == 0) mbar_arrive_after(bempty, dep);
+    if (lane == 0) mbar_arrive_after(bempty, dep, sink);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const unsigned a = fa[j], bb = fb[j];
@@ -210,7 +213,7 @@ static __device__ unsigned long long g_mixed_warp_tiles;   // test hook: how oft
 
 template <bool MASKS, bool ADD, class SM>
 __device__ __noinline__ void mixed_rows(typename SM::PStage* ps, const typename SM::BStage* bs, uint64_t* bempty,
-                                        int4 info, int4 tile, const float2* __restrict__ G,
+                                        uint32_t* sink, int4 info, int4 tile, const float2* __restrict__ G,
                                         const uint8_t* __restrict__ Gm, float sign, int H, int W, uint64_t negzero2) {
     const unsigned lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     if (lane == 0) atomicAdd(&g_mixed_warp_tiles, 1ull);
@@ -222,7 +225,7 @@ __device__ __noinline__ void mixed_rows(typename SM::PStage* ps, const typename 
     prepare_rows<MASKS>(prow, mrow, sign, (float)(tile.x + (int)lane), (float)(tile.y + (int)wrp * 4), info, p, pm, dx, dy,
                         fa, fb);
     sample_rows<MASKS, ADD, MIXED_TAPS>(*bs, prow, mrow, p, pm, dx, dy, fa, fb, info, tile.z, G, Gm, H, W, negzero2, bempty,
-                                  lane);
+                                        sink, lane);
 }
 
 // ADD: out = P + Q(G, ...) (composition); otherwise out = Q(G, ...) alone (Flow.apply of a flow: ofk_warp_t, float32 x2)
@@ -415,7 +418,7 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 2) c3_ws_kernel(const __grid_
                 dep |= strict[j];
             }
             dep = __reduce_or_sync(0xffffffffu, dep);
-            if (lane == 0) mbar_arrive_after(&sm.bempty[b], dep);
+            if (lane == 0) mbar_arrive_after(&sm.bempty[b], dep, &sm.sink[wrp]);
             if (lane == 0 && wrp == 0) OFK_TR(i, 10);
             if (lane == 0 && wrp == 7) OFK_TR(i, 14);
 #pragma unroll
@@ -444,7 +447,7 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 2) c3_ws_kernel(const __grid_
                 need_global = need_global || !(inbox || ix < -1 || iy < -1 || ix >= W || iy >= H);
             }
             if (__any_sync(0xffffffffu, need_global)) {
-                mixed_rows<MASKS, ADD, SM>(&ps, &bs, &sm.bempty[b], info, tile, G, Gm, sign, H, W, negzero2);
+                mixed_rows<MASKS, ADD, SM>(&ps, &bs, &sm.bempty[b], &sm.sink[wrp], info, tile, G, Gm, sign, H, W, negzero2);
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {

@@ -94,10 +94,11 @@ cudaError_t run_lane(Stager& s, int t, int device, bool to_device, char* dst, co
     for (size_t k = (size_t)t; k < n_chunks; k += kThreads, ++issued) {
         const int b = (int)(issued % kBufsPerThread);
         const size_t off = k * chunk, len = bytes - off < chunk ? bytes - off : chunk;
-        if (issued >= (size_t)kBufsPerThread) {          // the piece that used this buffer must have left it
-            if ((e = cudaEventSynchronize(ln.ev[b])) != cudaSuccess) return e;
-            if (!to_device) memcpy(dst + pending_off[b], ln.pinned[b], pending_len[b]);
-        }
+        // The piece that used this buffer last must have left it: an earlier piece of this transfer, or -- for the
+        // first pieces -- the tail of the PREVIOUS upload, whose DMA may still be running when this call starts
+        // (an event that was never recorded counts as complete).
+        if ((e = cudaEventSynchronize(ln.ev[b])) != cudaSuccess) return e;
+        if (issued >= (size_t)kBufsPerThread && !to_device) memcpy(dst + pending_off[b], ln.pinned[b], pending_len[b]);
         if (to_device) {
             memcpy(ln.pinned[b], src + off, len);
             if ((e = cudaMemcpyAsync(dst + off, ln.pinned[b], len, cudaMemcpyHostToDevice, s.copy)) != cudaSuccess) return e;

@@ -51,6 +51,7 @@ struct Smem {
     alignas(128) BStage bs[NB];
     alignas(16) int4 binfo[NB][2];   // {bx0 (bytes), mx0 (pixels), by0, -}, {tx0, ty0, n, -}
     uint64_t pfull[NP], pempty[NP], bfull[NB], bempty[NB];
+    uint32_t sink[NCW];              // scratch words of mbar_arrive_after, one per consumer warp
 };
 
 struct Maps {
@@ -217,7 +218,7 @@ __device__ __forceinline__ void sample_rows(const BStage& bs, uint8_t* orow, uin
                                             const int (&iys)[4], const unsigned (&fa)[4], const unsigned (&fb)[4],
                                             int4 info, int n, const uint8_t* __restrict__ img,
                                             const uint8_t* __restrict__ pmask, int H, int W, int rule, unsigned s_pass,
-                                            uint64_t* bempty, unsigned lane) {
+                                            uint64_t* bempty, uint32_t* sink, unsigned lane) {
     constexpr int BWB = box_bytes(C);
     constexpr int NW = TapWords<C>::N;
     uint32_t w[4][NW];
@@ -256,9 +257,15 @@ __device__ __forceinline__ void sample_rows(const BStage& bs, uint8_t* orow, uin
         // everything loaded from the box is consumed by the reduction below before the stage is handed back
         unsigned dep = 0;
 #pragma unroll
-        for (int j = J0; j < J1; ++j) dep |= w[j][NW - 1] | (MM == MM_PMASK ? mt[j] : 0u);
+        for (int j = J0; j < J1; ++j) {
+            dep |= w[j][NW - 1] | (MM == MM_PMASK ? mt[j] : 0u);
+            if (MODE == MIXED_TAPS) {   // out of line the loads may be scheduled in any order: wait for every word
+#pragma unroll
+                for (int k = 0; k < NW - 1; ++k) dep |= w[j][k];
+            }
+        }
         dep = __reduce_or_sync(0xffffffffu, dep);
-        if (lane == 0) mbar_arrive_after(bempty, dep);
+        if (lane == 0) mbar_arrive_after(bempty, dep, sink);
     }
 #pragma unroll
     for (int j = J0; j < J1; ++j) {
@@ -323,9 +330,9 @@ __device__ __noinline__ void mixed_rows(SM* sm, unsigned s, unsigned b, const ui
                                          (float)(tile.y + (int)wrp * 4), info, fmv, dxb, dy, ixs, iys, fa, fb);
     __syncwarp();   // every lane holds its flow values before the first result bytes overwrite the tile rows
     sample_rows<C, HALF_EVEN, MM, MIXED_TAPS, 0, 2>(*bs, orow, mrow, fmv, dxb, dy, ixs, iys, fa, fb, info, tile.z, img, pmask, H,
-                                              W, rule, s_pass, bempty, lane);
+                                              W, rule, s_pass, bempty, &sm->sink[wrp], lane);
     sample_rows<C, HALF_EVEN, MM, MIXED_TAPS, 2, 4>(*bs, orow, mrow, fmv, dxb, dy, ixs, iys, fa, fb, info, tile.z, img, pmask, H,
-                                              W, rule, s_pass, bempty, lane);
+                                              W, rule, s_pass, bempty, &sm->sink[wrp], lane);
 }
 
 template <int C, bool HALF_EVEN, int MM, bool FM, int NP, int NB, int LA, int PW>
@@ -506,7 +513,7 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 3) warp_u8_ws_kernel(const __
 #pragma unroll
             for (int j = 0; j < 4; ++j) dep |= w[j][TapWords<C>::N - 1] | (MM == MM_PMASK ? mt[j] : 0u);
             dep = __reduce_or_sync(0xffffffffu, dep);
-            if (lane == 0) mbar_arrive_after(&sm.bempty[b], dep);
+            if (lane == 0) mbar_arrive_after(&sm.bempty[b], dep, &sm.sink[wrp]);
             if (lane == 0 && wrp == 0) OFK_TR(i, 10);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {

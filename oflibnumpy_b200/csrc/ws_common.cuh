@@ -17,9 +17,16 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// arrive once `dep` has been computed: ties the release of a buffer to the registers loaded from it
-__device__ __forceinline__ void mbar_arrive_after(uint64_t* bar, unsigned dep) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];  // after %1" ::"r"(smem_u32(bar)), "r"(dep) : "memory");
+// Arrive once `dep` has been computed: ties the release of a buffer to the registers loaded from it. The dependency
+// has to be real for ptxas, not just for the PTX text: `dep` is stored to a scratch word in shared memory first, and the
+// arrive (release semantics) is ordered after that store -- which cannot issue before every load feeding `dep` has
+// returned. (A version that only mentioned `dep` in the asm string let ptxas schedule the arrive ahead of the last
+// shared-memory loads in the out-of-line path: the producer's next TMA load then overwrote taps still being read.)
+__device__ __forceinline__ void mbar_arrive_after(uint64_t* bar, unsigned dep, uint32_t* sink) {
+    asm volatile(
+        "st.shared.u32 [%2], %1;\n\t"
+        "mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)), "r"(dep), "r"(smem_u32(sink))
+        : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");

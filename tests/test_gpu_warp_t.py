@@ -770,6 +770,12 @@ def test_large_pageable_copies_are_staged_correctly(of):
         a[:] = 0                                              # the upload has read its source when it returns
         back = d.numpy()
         assert back.shape == keep.shape and np.array_equal(back, keep), nbytes
+    # back-to-back uploads: the pinned pieces of one transfer may still be in flight when the next one starts
+    arrays = [rng.integers(0, 256, int(n), dtype=np.uint8) for n in (9 * mb + 7, 20 * mb, 5 * mb + 1, 33 * mb, 6 * mb, 12 * mb)]
+    for rep in range(3):
+        devs = [DeviceArray.from_numpy(a) for a in arrays]
+        for a, d in zip(arrays, devs):
+            assert np.array_equal(d.numpy(), a)
     h, w = 1500, 2048                                          # 24.6 MB of vectors: staged both ways around a kernel
     v = rng.standard_normal((h, w, 2)).astype(np.float32)
     f = of.Flow(v, 't')
@@ -793,3 +799,37 @@ def test_functional_api_rejects_non_finite_flows(of):
     big[0, 0, 0] = 1e300                                   # finite before the cast: accepted, as in the reference
     with np.errstate(over='ignore'):
         of.is_zero_flow(big)
+
+
+def test_rough_full_size_flows_repeat_exactly(of):
+    """Regression for a release-before-read race in the out-of-line path of the TMA kernels (a box stage was handed
+    back to the producer before the last shared-memory taps of a warp had been read: a handful of wrong pixels in one
+    tile row of one launch in five). 1080p motion boundaries + noise, both references and the image warp, 15 launches
+    each: the first is compared with the oracle, all must be byte-identical."""
+    rng = np.random.default_rng(99)
+    h, w, n = 1080, 1920, 2
+    a = np.stack([_rough_flow(rng, h, w, k) for k in ('blocks', 'noise')])
+    b = np.stack([_rough_flow(rng, h, w, k) for k in ('noise', 'blocks')])
+    am, bm = rng.random((n, h, w)) > 0.02, rng.random((n, h, w)) > 0.02
+    img = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+    first = {}
+    for rep in range(15):
+        for r in ('t', 's'):
+            v, m = of.FlowBatch(a, r, am).combine_with(of.FlowBatch(b, r, bm), 3).numpy()
+            if rep == 0:
+                for i in range(n):
+                    want = R.combine(R.make(a[i], r, am[i]), R.make(b[i], r, bm[i]), 3)
+                    same(m[i].view(np.bool_), want.mask)
+                    same(v[i], want.vecs)
+                first[r] = (v, m)
+            else:
+                assert np.array_equal(v, first[r][0]) and np.array_equal(m, first[r][1]), (rep, r)
+        wi, wm = (x.numpy() for x in of.FlowBatch(a, 't', am).apply(img, return_valid_area=True))
+        if rep == 0:
+            for i in range(n):
+                w2, m2 = R.apply(R.make(a[i], 't', am[i]), img[i], return_valid_area=True)
+                same(wi[i], w2)
+                same(wm[i].view(np.bool_), m2)
+            first['img'] = (wi, wm)
+        else:
+            assert np.array_equal(wi, first['img'][0]) and np.array_equal(wm, first['img'][1]), rep
