@@ -144,8 +144,8 @@ __device__ __forceinline__ void sample_rows(const BStage& bs, float2* prow, uint
             }
         }
     }
-    // validity first: it consumes the values loaded last, so once it is known every tap of this warp has
-    // left the box and the stage can be handed back to the producer while the blend is still running
+    // validity and a reduction over every tap first: once they are known all taps of this warp have left the box and
+    // the stage can be handed back to the producer while the blend is still running
     unsigned strict[4], dep = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -153,15 +153,14 @@ __device__ __forceinline__ void sample_rows(const BStage& bs, float2* prow, uint
         const unsigned ha = min(a, 1u), hb = min(bb, 1u);      // 1 where the right / lower taps have weight
         if (MASKS) {
             strict[j] = m[j][0] & (m[j][1] | ~ha) & (m[j][2] | ~hb) & (m[j][3] | ~(ha & hb)) & pm[j];
-            // out of line the loads may be scheduled in any order: make the release wait for every tap explicitly
-            if (MODE == MIXED_TAPS) strict[j] |= (unsigned)((t[j][0] | t[j][1] | t[j][2] | t[j][3]) >> 63) << 8;
         } else {
             const int ix = dx[j] + info.x, iy = dy[j] + info.z;
             strict[j] = (ix >= 0 && iy >= 0 && (ix + 1 < W || (a == 0 && ix < W)) &&
                          (iy + 1 < H || (bb == 0 && iy < H))) ? 1u : 0u;
-            strict[j] |= (unsigned)(t[j][3] >> 63) << 8;    // data dependency on the tap loaded last
-            if (MODE == MIXED_TAPS) strict[j] |= (unsigned)((t[j][0] | t[j][1] | t[j][2]) >> 63) << 8;
         }
+        // every tap feeds the release below (bit 8, masked off when the validity byte is stored): the loads may be
+        // issued in any order, so "the value loaded last" is not something the source can name
+        strict[j] |= (unsigned)((t[j][0] | t[j][1] | t[j][2] | t[j][3]) >> 63) << 8;
         dep |= strict[j];
     }
     dep = __reduce_or_sync(0xffffffffu, dep);
@@ -400,8 +399,8 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 2) c3_ws_kernel(const __grid_
                     m[j][0] = mm[0]; m[j][1] = mm[1]; m[j][2] = mm[BMW]; m[j][3] = mm[BMW + 1];
                 }
             }
-            // validity first: it consumes the values loaded last, so once it is known every tap of this warp has
-            // left the box and the stage can be handed back to the producer while the blend is still running
+            // validity and a reduction over every tap first: once they are known all taps of this warp have left the
+            // box and the stage can be handed back to the producer while the blend is still running
             unsigned strict[4], dep = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -413,8 +412,10 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 2) c3_ws_kernel(const __grid_
                     const int ix = dx[j] + info.x, iy = dy[j] + info.z;
                     strict[j] = (ix >= 0 && iy >= 0 && (ix + 1 < W || (a == 0 && ix < W)) &&
                                  (iy + 1 < H || (bb == 0 && iy < H))) ? 1u : 0u;
-                    strict[j] |= (unsigned)(t[j][3] >> 63) << 8;    // data dependency on the tap loaded last
                 }
+                // every tap feeds the release below (bit 8, masked off when the validity byte is stored): the loads
+                // may be issued in any order, so "the value loaded last" is not something the source can name
+                strict[j] |= (unsigned)((t[j][0] | t[j][1] | t[j][2] | t[j][3]) >> 63) << 8;
                 dep |= strict[j];
             }
             dep = __reduce_or_sync(0xffffffffu, dep);

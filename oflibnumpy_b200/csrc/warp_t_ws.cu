@@ -257,12 +257,10 @@ __device__ __forceinline__ void sample_rows(const BStage& bs, uint8_t* orow, uin
         // everything loaded from the box is consumed by the reduction below before the stage is handed back
         unsigned dep = 0;
 #pragma unroll
-        for (int j = J0; j < J1; ++j) {
-            dep |= w[j][NW - 1] | (MM == MM_PMASK ? mt[j] : 0u);
-            if (MODE == MIXED_TAPS) {   // out of line the loads may be scheduled in any order: wait for every word
+        for (int j = J0; j < J1; ++j) {       // every word: the loads may be issued in any order
+            dep |= (MM == MM_PMASK ? mt[j] : 0u);
 #pragma unroll
-                for (int k = 0; k < NW - 1; ++k) dep |= w[j][k];
-            }
+            for (int k = 0; k < NW; ++k) dep |= w[j][k];
         }
         dep = __reduce_or_sync(0xffffffffu, dep);
         if (lane == 0) mbar_arrive_after(bempty, dep, sink);
@@ -511,7 +509,11 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 3) warp_u8_ws_kernel(const __
             // everything loaded from the box is consumed by the reduction below before the stage is handed back
             unsigned dep = 0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dep |= w[j][TapWords<C>::N - 1] | (MM == MM_PMASK ? mt[j] : 0u);
+            for (int j = 0; j < 4; ++j) {     // every word: the loads may be issued in any order
+                dep |= (MM == MM_PMASK ? mt[j] : 0u);
+#pragma unroll
+                for (int k = 0; k < TapWords<C>::N; ++k) dep |= w[j][k];
+            }
             dep = __reduce_or_sync(0xffffffffu, dep);
             if (lane == 0) mbar_arrive_after(&sm.bempty[b], dep, &sm.sink[wrp]);
             if (lane == 0 && wrp == 0) OFK_TR(i, 10);
