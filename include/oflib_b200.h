@@ -261,6 +261,10 @@ int ofk_rt_host_alloc(void** hptr, size_t bytes);          /* pinned */
 int ofk_rt_host_free(void* hptr);
 int ofk_rt_host_register(void* hptr, size_t bytes);        /* pin an existing numpy buffer */
 int ofk_rt_host_unregister(void* hptr);
+/* Host <-> device copies, stream-ordered. Pinned / registered host memory: plain asynchronous copies. Pageable host
+ * memory (ordinary numpy arrays) of 4 MiB and more: worker threads stage 2 MiB pieces through pinned buffers so the copy
+ * runs near PCIe rate instead of the driver's single-threaded staging; h2d returns once the source has been read,
+ * d2h once the destination is complete (as cudaMemcpyAsync behaves for pageable memory). OFK_STAGED_COPIES=0 disables. */
 int ofk_rt_memcpy_h2d(void* dst, const void* src, size_t bytes, ofk_stream_t stream);
 int ofk_rt_memcpy_d2h(void* dst, const void* src, size_t bytes, ofk_stream_t stream);
 int ofk_rt_memcpy_d2d(void* dst, const void* src, size_t bytes, ofk_stream_t stream);
