@@ -155,6 +155,21 @@ __device__ __forceinline__ void load_taps_global(const uint8_t* __restrict__ g, 
         w[0] = __ldg(q0); w[1] = __ldg(q0 + 1); w[2] = __ldg(q1); w[3] = __ldg(q1 + 1);
     }
 }
+// A value that depends on every word loaded for one pixel, at no extra cost: the first intermediate results of the
+// blend (the compiler shares them with blend_store). Feeds the release of the box stage.
+template <int C>
+__device__ __forceinline__ uint32_t tap_digest(const uint32_t (&w)[TapWords<C>::N], unsigned o) {
+    const unsigned sh8 = o << 3;
+    if constexpr (C == 1) {
+        return __funnelshift_r(w[0], w[1], sh8) | __funnelshift_r(w[2], w[3], sh8);
+    } else if constexpr (C == 3) {
+        const uint32_t lo0 = __funnelshift_r(w[0], w[1], sh8), hi0 = __funnelshift_r(w[1], w[2], sh8);
+        const uint32_t lo1 = __funnelshift_r(w[3], w[4], sh8), hi1 = __funnelshift_r(w[4], w[5], sh8);
+        return __byte_perm(lo0, hi0, 0x4130) | __byte_perm(lo1, hi1, 0x4130);
+    } else {
+        return __byte_perm(w[0], w[1], 0x5140) | __byte_perm(w[2], w[3], 0x5140);
+    }
+}
 // phase 2: blend and store the C result bytes of the pixel at dst
 template <bool HALF_EVEN, int C>
 __device__ __forceinline__ void blend_store(const uint32_t (&w)[TapWords<C>::N], unsigned o, unsigned a, unsigned b,
@@ -257,11 +272,8 @@ __device__ __forceinline__ void sample_rows(const BStage& bs, uint8_t* orow, uin
         // everything loaded from the box is consumed by the reduction below before the stage is handed back
         unsigned dep = 0;
 #pragma unroll
-        for (int j = J0; j < J1; ++j) {       // every word: the loads may be issued in any order
-            dep |= (MM == MM_PMASK ? mt[j] : 0u);
-#pragma unroll
-            for (int k = 0; k < NW; ++k) dep |= w[j][k];
-        }
+        for (int j = J0; j < J1; ++j)         // every word: the loads may be issued in any order
+            dep |= tap_digest<C>(w[j], (unsigned)dxb[j]) | (MM == MM_PMASK ? mt[j] : 0u);
         dep = __reduce_or_sync(0xffffffffu, dep);
         if (lane == 0) mbar_arrive_after(bempty, dep, sink);
     }
@@ -509,11 +521,8 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 3) warp_u8_ws_kernel(const __
             // everything loaded from the box is consumed by the reduction below before the stage is handed back
             unsigned dep = 0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {     // every word: the loads may be issued in any order
-                dep |= (MM == MM_PMASK ? mt[j] : 0u);
-#pragma unroll
-                for (int k = 0; k < TapWords<C>::N; ++k) dep |= w[j][k];
-            }
+            for (int j = 0; j < 4; ++j)       // every word: the loads may be issued in any order
+                dep |= tap_digest<C>(w[j], (unsigned)(dy[j] * BWB + dxb[j])) | (MM == MM_PMASK ? mt[j] : 0u);
             dep = __reduce_or_sync(0xffffffffu, dep);
             if (lane == 0) mbar_arrive_after(&sm.bempty[b], dep, &sm.sink[wrp]);
             if (lane == 0 && wrp == 0) OFK_TR(i, 10);
