@@ -833,3 +833,54 @@ def test_rough_full_size_flows_repeat_exactly(of):
             first['img'] = (wi, wm)
         else:
             assert np.array_equal(wi, first['img'][0]) and np.array_equal(wm, first['img'][1]), rep
+
+
+def test_batches_beyond_4_gib(of):
+    """Maximum sizes: batches whose tensors exceed 2^32 bytes (300 x 1080p flows = 5 GB per operand for the composition,
+    700 frames = 11.6 GB of flows and 4.4 GB of images for the warp). Frames at the start, in the middle and at the end
+    must equal the same frame processed alone (small offsets): 64-bit addressing in the tensor maps, the tile iterators
+    and the global-tap path."""
+    from oflibnumpy_b200 import _lib, _ops
+    from oflibnumpy_b200.batch import FlowBatch
+    from oflibnumpy_b200.device import DeviceArray
+    h, w = 1080, 1920
+    rng = np.random.default_rng(3)
+    st = of.device.current_stream()
+
+    def flows(n, seed0):
+        mats = np.stack([np.linalg.pinv(R.matrix_from_transforms(gi.cfg4_transforms(seed0 + i))) for i in range(n)])
+        v = _ops.from_matrix(DeviceArray.from_numpy(mats), (h, w), -1.0)
+        m = DeviceArray.empty((n, h, w), np.uint8)
+        _lib.call('ofk_rt_memset', m.ptr, 1, m.nbytes, st)
+        for i in (0, n // 2 + 7, n - 1):                       # some invalid pixels in the frames that are checked
+            mk = (rng.random((1, h, w)) > 0.03).astype(np.uint8)
+            fr = m.frames(i, i + 1)
+            _lib.call('ofk_rt_memcpy_h2d', fr.ptr, mk.ctypes.data, mk.nbytes, st)
+            of.device.synchronize()
+        return FlowBatch._wrap(v, 't', m)
+
+    n = 300
+    fa, fb = flows(n, 0), flows(n, 5000)
+    assert fa.vecs.nbytes > (1 << 32)
+    res = fa.combine_with(fb, 3)
+    for i in (0, n // 2 + 7, n - 1):
+        one = FlowBatch._wrap(fa.vecs.frames(i, i + 1), 't', fa.masks.frames(i, i + 1)).combine_with(
+            FlowBatch._wrap(fb.vecs.frames(i, i + 1), 't', fb.masks.frames(i, i + 1)), 3)
+        same(res.vecs.frames(i, i + 1).numpy(), one.vecs.numpy())
+        same(res.masks.frames(i, i + 1).numpy(), one.masks.numpy())
+    del res, fb, fa
+    n = 700
+    fa = flows(n, 9000)
+    imgs = DeviceArray.empty((n, h, w, 3), np.uint8)
+    assert imgs.nbytes > (1 << 32)
+    pool = rng.integers(0, 256, (4, 1, h, w, 3), dtype=np.uint8)
+    for i in range(n):
+        fr = imgs.frames(i, i + 1)
+        _lib.call('ofk_rt_memcpy_h2d', fr.ptr, pool[i % 4].ctypes.data, pool[i % 4].nbytes, st)
+    of.device.synchronize()
+    out, valid = fa.apply(imgs, return_valid_area=True)
+    for i in (0, n // 2 + 7, n - 1):
+        one = FlowBatch._wrap(fa.vecs.frames(i, i + 1), 't', fa.masks.frames(i, i + 1)).apply(imgs.frames(i, i + 1),
+                                                                                               return_valid_area=True)
+        same(out.frames(i, i + 1).numpy(), one[0].numpy())
+        same(valid.frames(i, i + 1).numpy(), one[1].numpy())
