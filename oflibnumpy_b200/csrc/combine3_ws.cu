@@ -94,16 +94,12 @@ __device__ __forceinline__ void quant(float X, int& i, int& f) {
     f = bits & 31;
 }
 
-// Taps of a warp's 4 x 32 pixels, all requested before the first use; then validity, release of the box, blend.
-// MODE = BOX        : every pixel of the warp is covered by the box (shared memory only, no bounds tests).
-// MODE = BOX_OR_ZERO: the pixels not covered by the box have all four taps outside the frame (the usual case along the
-//                     frame border: the box is clamped to the frame) -- their taps are zeros.
-// MODE = MIXED      : pixels outside the box fetch their taps from global memory, predicated per tap on "inside the
-//                     frame" (zero border, mask invalid outside) -- one memory round trip per warp and tile, and the
-//                     same arithmetic, so the result never depends on the box estimate.
-enum : int { BOX = 0, BOX_OR_ZERO = 1, MIXED_TAPS = 2 };
-template <bool MASKS, bool ADD, int MODE, class BStage>
-__device__ __forceinline__ void sample_rows(const BStage& bs, float2* prow, uint8_t* mrow, const uint64_t (&p)[4],
+// The global-tap path (out of line, see mixed_rows): taps of a warp's 4 x 32 pixels, all requested before the first
+// use -- from the box for the pixels it covers, from global memory for the others, predicated per tap on "inside the
+// frame" (zero border, mask invalid outside) -- then validity, release of the box, blend: one memory round trip per
+// warp and tile and the same arithmetic as the main path, so the result never depends on the box estimate.
+template <bool MASKS, bool ADD, class BStage>
+__device__ __forceinline__ void sample_rows_mixed(const BStage& bs, float2* prow, uint8_t* mrow, const uint64_t (&p)[4],
                                             const unsigned (&pm)[4], const int (&dx)[4], const int (&dy)[4],
                                             const int (&fa)[4], const int (&fb)[4], int4 info, int n,
                                             const float2* __restrict__ G, const uint8_t* __restrict__ Gm, int H, int W,
@@ -113,7 +109,7 @@ __device__ __forceinline__ void sample_rows(const BStage& bs, float2* prow, uint
     unsigned m[4][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const bool inbox = MODE == BOX || ((unsigned)dx[j] < (unsigned)(BW - 1) && (unsigned)dy[j] < (unsigned)(BH - 1));
+        const bool inbox = (unsigned)dx[j] < (unsigned)(BW - 1) && (unsigned)dy[j] < (unsigned)(BH - 1);
         if (inbox) {
             const uint64_t* v = reinterpret_cast<const uint64_t*>(bs.v) + (dy[j] * BW + dx[j]);
             t[j][0] = v[0]; t[j][1] = v[1]; t[j][2] = v[BW]; t[j][3] = v[BW + 1];
@@ -121,9 +117,6 @@ __device__ __forceinline__ void sample_rows(const BStage& bs, float2* prow, uint
                 const uint8_t* mm = bs.m + (dy[j] * BMW + dx[j] + info.y);
                 m[j][0] = mm[0]; m[j][1] = mm[1]; m[j][2] = mm[BMW]; m[j][3] = mm[BMW + 1];
             }
-        } else if (MODE == BOX_OR_ZERO) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { t[j][k] = 0ull; m[j][k] = 0u; }
         } else {
             // integer coordinates from the fast quantiser: exact for |X| < 2^17, far outside the frame otherwise
             const int ix = dx[j] + info.x, iy = dy[j] + info.z;
@@ -207,7 +200,7 @@ __device__ __forceinline__ bool prepare_rows(const float2* prow, const uint8_t* 
 }
 
 // The rare path, out of line so that it does not weigh on the register allocation of the kernel's main loop: redoes the
-// preparation from shared memory and samples with MODE = MIXED.
+// preparation from shared memory and samples with sample_rows_mixed.
 static __device__ unsigned long long g_mixed_warp_tiles;   // test hook: how often the out-of-line path ran (per warp and tile)
 
 template <bool MASKS, bool ADD, class SM>
@@ -223,7 +216,7 @@ __device__ __noinline__ void mixed_rows(typename SM::PStage* ps, const typename 
     int dx[4], dy[4], fa[4], fb[4];
     prepare_rows<MASKS>(prow, mrow, sign, (float)(tile.x + (int)lane), (float)(tile.y + (int)wrp * 4), info, p, pm, dx, dy,
                         fa, fb);
-    sample_rows<MASKS, ADD, MIXED_TAPS>(*bs, prow, mrow, p, pm, dx, dy, fa, fb, info, tile.z, G, Gm, H, W, negzero2, bempty,
+    sample_rows_mixed<MASKS, ADD>(*bs, prow, mrow, p, pm, dx, dy, fa, fb, info, tile.z, G, Gm, H, W, negzero2, bempty,
                                         sink, lane);
 }
 

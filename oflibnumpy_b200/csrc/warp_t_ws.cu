@@ -218,17 +218,13 @@ __device__ __forceinline__ bool prepare_rows(const float2* frow, const uint8_t* 
     return ok;
 }
 
-// Taps of rows [J0, J1) of a warp's 4 x 32 pixels, all requested before the first use; then release of the box (with the
-// last rows), blend, validity.
-// MODE = BOX        : every pixel of the warp is covered by the box (shared memory only, no bounds tests).
-// MODE = BOX_OR_ZERO: the pixels not covered by the box have all four taps outside the frame (the usual case along the
-//                     frame border: the box is clamped to the frame) -- zero result, invalid.
-// MODE = MIXED      : a pixel outside the box whose four taps lie inside the frame reads the same aligned words from
-//                     global memory (same arithmetic); only the pixels that also touch the frame border go through
-//                     the out-of-line border routine.
-enum : int { BOX = 0, BOX_OR_ZERO = 1, MIXED_TAPS = 2 };
-template <int C, bool HALF_EVEN, int MM, int MODE, int J0, int J1, class BStage>
-__device__ __forceinline__ void sample_rows(const BStage& bs, uint8_t* orow, uint8_t* mrow, const unsigned (&fmv)[4],
+// The global-tap path (out of line, see mixed_rows): taps of rows [J0, J1) of a warp's 4 x 32 pixels, all requested
+// before the first use; then release of the box (with the last rows), blend, validity. A pixel covered by the box reads
+// it; a pixel outside the box whose four taps lie inside the frame reads the same aligned words from global memory (same
+// arithmetic); a pixel that samples nothing but the zero border is zero / invalid; only the pixels that straddle the
+// frame border outside the box go through the out-of-line border routine.
+template <int C, bool HALF_EVEN, int MM, int J0, int J1, class BStage>
+__device__ __forceinline__ void sample_rows_mixed(const BStage& bs, uint8_t* orow, uint8_t* mrow, const unsigned (&fmv)[4],
                                             const int (&dxb)[4], const int (&dy)[4], const int (&ixs)[4],
                                             const int (&iys)[4], const unsigned (&fa)[4], const unsigned (&fb)[4],
                                             int4 info, int n, const uint8_t* __restrict__ img,
@@ -239,7 +235,7 @@ __device__ __forceinline__ void sample_rows(const BStage& bs, uint8_t* orow, uin
     uint32_t w[4][NW];
     uint32_t mt[4];
     auto in_box = [&](int j) {
-        return MODE == BOX || ((unsigned)dxb[j] <= (unsigned)(BWB - 2 * C) && (unsigned)dy[j] <= (unsigned)(BH - 2));
+        return (unsigned)dxb[j] <= (unsigned)(BWB - 2 * C) && (unsigned)dy[j] <= (unsigned)(BH - 2);
     };
     auto interior = [&](int j) {   // all four taps inside the frame (the fast quantiser's garbage never is)
         return (unsigned)ixs[j] < (unsigned)(W - 1) && (unsigned)iys[j] < (unsigned)(H - 1);
@@ -257,7 +253,7 @@ __device__ __forceinline__ void sample_rows(const BStage& bs, uint8_t* orow, uin
 #pragma unroll
             for (int k = 0; k < NW; ++k) w[j][k] = 0u;
             mt[j] = 0u;
-            if (MODE == MIXED_TAPS && interior(j)) {
+            if (interior(j)) {
                 const long long px = (long long)n * ((long long)H * W) + ((long long)iys[j] * W + ixs[j]);
                 load_taps_global<C>(img + px * C, W, w[j]);
                 if (MM == MM_PMASK) {
@@ -281,7 +277,7 @@ __device__ __forceinline__ void sample_rows(const BStage& bs, uint8_t* orow, uin
     for (int j = J0; j < J1; ++j) {
         uint8_t* dst = orow + j * (TS * C);
         const bool boxed = in_box(j);
-        if (boxed || (MODE == MIXED_TAPS && interior(j))) {
+        if (boxed || interior(j)) {
             // the byte phase of tap 00 inside its aligned word is the same in the box and in the frame: box starts and
             // row pitches are multiples of 16 bytes
             uint32_t W0, W1;
@@ -300,7 +296,7 @@ __device__ __forceinline__ void sample_rows(const BStage& bs, uint8_t* orow, uin
         } else {
             // (quantised coordinates beyond the fast quantiser's range are far outside the frame)
             unsigned valid = 0u;
-            if (MODE == BOX_OR_ZERO || ixs[j] < -1 || iys[j] < -1 || ixs[j] >= W || iys[j] >= H) {
+            if (ixs[j] < -1 || iys[j] < -1 || ixs[j] >= W || iys[j] >= H) {
 #pragma unroll
                 for (int c = 0; c < C; ++c) dst[c] = 0;      // every tap lies outside the frame
             } else {
@@ -318,7 +314,7 @@ __device__ __forceinline__ void sample_rows(const BStage& bs, uint8_t* orow, uin
 }
 
 // The rare path, out of line so that it does not weigh on the register allocation of the kernel's main loop: redoes the
-// preparation from shared memory and samples with MODE = MIXED, two rows at a time.
+// preparation from shared memory and samples with sample_rows_mixed, two rows at a time.
 static __device__ unsigned long long g_mixed_warp_tiles;   // test hook: how often the out-of-line path ran (per warp and tile)
 
 template <int C, bool HALF_EVEN, int MM, bool FM, class SM>
@@ -339,9 +335,9 @@ __device__ __noinline__ void mixed_rows(SM* sm, unsigned s, unsigned b, const ui
     prepare_rows<C, FM && MM != MM_NONE>(ps->f + own, mrow, sign, (float)(tile.x + (int)lane),
                                          (float)(tile.y + (int)wrp * 4), info, fmv, dxb, dy, ixs, iys, fa, fb);
     __syncwarp();   // every lane holds its flow values before the first result bytes overwrite the tile rows
-    sample_rows<C, HALF_EVEN, MM, MIXED_TAPS, 0, 2>(*bs, orow, mrow, fmv, dxb, dy, ixs, iys, fa, fb, info, tile.z, img, pmask, H,
+    sample_rows_mixed<C, HALF_EVEN, MM, 0, 2>(*bs, orow, mrow, fmv, dxb, dy, ixs, iys, fa, fb, info, tile.z, img, pmask, H,
                                               W, rule, s_pass, bempty, &sm->sink[wrp], lane);
-    sample_rows<C, HALF_EVEN, MM, MIXED_TAPS, 2, 4>(*bs, orow, mrow, fmv, dxb, dy, ixs, iys, fa, fb, info, tile.z, img, pmask, H,
+    sample_rows_mixed<C, HALF_EVEN, MM, 2, 4>(*bs, orow, mrow, fmv, dxb, dy, ixs, iys, fa, fb, info, tile.z, img, pmask, H,
                                               W, rule, s_pass, bempty, &sm->sink[wrp], lane);
 }
 
