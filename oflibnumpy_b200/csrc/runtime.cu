@@ -283,8 +283,27 @@ size_t esize(int dtype) {
 }
 size_t pad256(size_t b) { return (b + 255) & ~size_t(255); }
 
-#define OFH_COPY_IN(dst, src, bytes) OFK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s.st))
-#define OFH_COPY_OUT(dst, src, bytes) OFK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s.st))
+// Copies of the ring: pinned / registered user buffers -> plain asynchronous copies on the slot's stream (they overlap
+// with the other slots); pageable buffers (plain numpy arrays) -> staging.cu (worker threads + pinned pieces), where the
+// upload returns once the source has been read and the download once the destination is complete.
+int ring_copy(void* dst, const void* src, size_t bytes, bool to_device, cudaStream_t st) {
+    if (bytes == 0) return OFK_OK;
+    const int staged = staged_copy(dst, src, bytes, to_device, st);
+    if (staged < 0) return staged;
+    if (staged == 0)
+        OFK_CUDA(cudaMemcpyAsync(dst, src, bytes, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, st));
+    return OFK_OK;
+}
+#define OFH_COPY_IN(dst, src, bytes)                                                   \
+    do {                                                                               \
+        const int rc_ = ring_copy(dst, src, bytes, true, s.st);                        \
+        if (rc_ != OFK_OK) return rc_;                                                 \
+    } while (0)
+#define OFH_COPY_OUT(dst, src, bytes)                                                  \
+    do {                                                                               \
+        const int rc_ = ring_copy(dst, src, bytes, false, s.st);                       \
+        if (rc_ != OFK_OK) return rc_;                                                 \
+    } while (0)
 
 }  // namespace
 
@@ -303,6 +322,20 @@ extern "C" int ofh_warp_t(const void* payload, int dtype, int C, int arith, cons
     if (cf > N) cf = N;
     int rc = ring_prepare(device, per_frame * cf + 4096);
     if (rc != OFK_OK) return rc;
+    struct Pending {
+        Slot* slot;
+        int n0, cn;
+        void* d_out;
+        uint8_t* d_om;
+    };
+    Pending prev = {};
+    bool have_prev = false;
+    auto download = [&](const Pending& p) -> int {
+        Slot& s = *p.slot;
+        if (C) OFH_COPY_OUT((char*)out + (size_t)p.n0 * b_pay, p.d_out, b_pay * p.cn);
+        if (p.d_om) OFH_COPY_OUT(out_mask + (size_t)p.n0 * px, p.d_om, b_m * p.cn);
+        return OFK_OK;
+    };
     int chunk = 0;
     for (int n0 = 0; n0 < N; n0 += cf, ++chunk) {
         Slot& s = g_ring.slot[chunk % kSlots];
@@ -323,8 +356,19 @@ extern "C" int ofh_warp_t(const void* payload, int dtype, int C, int arith, cons
         rc = ofk_warp_t(d_pay, dtype, C, arith, d_flow, flow_sign, d_pm, d_fm, d_out, d_om, mask_rule, cn, H, W, H, W,
                         0, 0, 1, (ofk_stream_t)s.st);
         if (rc != OFK_OK) return rc;
-        if (C) OFH_COPY_OUT((char*)out + (size_t)n0 * b_pay, d_out, b_pay * cn);
-        if (d_om) OFH_COPY_OUT(out_mask + (size_t)n0 * px, d_om, b_m * cn);
+        // The download of a chunk is issued after the NEXT chunk has been uploaded and launched: with pageable user
+        // buffers a download blocks the host, and this order keeps the device busy meanwhile (with pinned buffers the
+        // order is irrelevant, every copy is asynchronous).
+        if (have_prev) {
+            rc = download(prev);
+            if (rc != OFK_OK) return rc;
+        }
+        prev = {&s, n0, cn, d_out, d_om};
+        have_prev = true;
+    }
+    if (have_prev) {
+        rc = download(prev);
+        if (rc != OFK_OK) return rc;
     }
     for (auto& s : g_ring.slot) OFK_CUDA(cudaStreamSynchronize(s.st));
     return OFK_OK;
@@ -343,6 +387,26 @@ extern "C" int ofh_combine3(const float* A, const uint8_t* Am, const float* B, c
     if (cf > N) cf = N;
     int rc = ring_prepare(device, per_frame * cf + 4096);
     if (rc != OFK_OK) return rc;
+    struct Pending {
+        Slot* slot;
+        int n0, cn;
+        float* dO;
+        uint8_t* dOm;
+        int* dF;
+    };
+    Pending prev = {};
+    bool have_prev = false;
+    auto download = [&](const Pending& p) -> int {
+        Slot& s = *p.slot;
+        OFH_COPY_OUT(out + (size_t)p.n0 * px * 2, p.dO, b_flow * p.cn);
+        OFH_COPY_OUT(out_mask + (size_t)p.n0 * px, p.dOm, b_m * p.cn);
+        if (flags) {                                     // small: always through the slot's pinned staging words
+            OFK_CUDA(cudaMemcpyAsync(s.hflags, p.dF, sizeof(int) * 2 * p.cn, cudaMemcpyDeviceToHost, s.st));
+            s.flags_dst = flags + (size_t)p.n0 * 2;
+            s.flags_n = (size_t)2 * p.cn;
+        }
+        return OFK_OK;
+    };
     int chunk = 0;
     for (int n0 = 0; n0 < N; n0 += cf, ++chunk) {
         Slot& s = g_ring.slot[chunk % kSlots];
@@ -370,13 +434,16 @@ extern "C" int ofh_combine3(const float* A, const uint8_t* Am, const float* B, c
         if (dBm) OFH_COPY_IN(dBm, Bm + (size_t)n0 * px, b_m * cn);
         rc = ofk_combine3(dA, dAm, dB, dBm, ref, thr, dO, dOm, dF, cn, H, W, (ofk_stream_t)s.st);
         if (rc != OFK_OK) return rc;
-        OFH_COPY_OUT(out + (size_t)n0 * px * 2, dO, b_flow * cn);
-        OFH_COPY_OUT(out_mask + (size_t)n0 * px, dOm, b_m * cn);
-        if (flags) {
-            OFH_COPY_OUT(s.hflags, dF, sizeof(int) * 2 * cn);
-            s.flags_dst = flags + (size_t)n0 * 2;
-            s.flags_n = (size_t)2 * cn;
+        if (have_prev) {                                 // see ofh_warp_t: downloads trail the launches by one chunk
+            rc = download(prev);
+            if (rc != OFK_OK) return rc;
         }
+        prev = {&s, n0, cn, dO, dOm, dF};
+        have_prev = true;
+    }
+    if (have_prev) {
+        rc = download(prev);
+        if (rc != OFK_OK) return rc;
     }
     for (auto& s : g_ring.slot) {
         OFK_CUDA(cudaStreamSynchronize(s.st));

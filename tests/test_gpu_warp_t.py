@@ -884,3 +884,26 @@ def test_batches_beyond_4_gib(of):
                                                                                                return_valid_area=True)
         same(out.frames(i, i + 1).numpy(), one[0].numpy())
         same(valid.frames(i, i + 1).numpy(), one[1].numpy())
+
+
+def test_host_buffer_api_with_plain_numpy_batches(of):
+    """ofh_warp_t / ofh_combine3 on pageable numpy arrays at 1080p: uploads and downloads of the ring go through the
+    staged copies (worker threads + pinned pieces), downloads trail the launches by one chunk. Same bytes as the device
+    API, flags included."""
+    from oflibnumpy_b200.batch import FlowBatch
+    rng = np.random.default_rng(17)
+    n, h, w = 5, 1080, 1920
+    a = np.stack([_smooth_flow(rng, h, w, 20) for _ in range(n)])
+    b = np.stack([_smooth_flow(rng, h, w, 20) for _ in range(n)])
+    b[3] = 0                                                  # a zero operand: the early-exit flags must come back
+    am, bm = rng.random((n, h, w)) > 0.02, rng.random((n, h, w)) > 0.02
+    img = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+    for rep in range(2):
+        wi, wv = of.batch.apply_flow_host(a, img, flow_masks=am, return_valid_area=True)
+        d_i, d_v = FlowBatch(a, 't', am).apply(img, return_valid_area=True)
+        same(wi, d_i.numpy())
+        same(wv.view(np.uint8), d_v.numpy())
+        v, m = of.batch.combine_flows_host(a, b, 3, 't', am, bm)
+        dv, dm = FlowBatch(a, 't', am).combine_with(FlowBatch(b, 't', bm), 3).numpy()
+        same(v, dv)
+        same(m.view(np.uint8), dm.view(np.uint8))
