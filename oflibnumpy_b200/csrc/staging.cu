@@ -24,7 +24,7 @@ namespace ofk {
 namespace {
 
 constexpr size_t kChunk = 2u << 20;        // bytes per pinned buffer = largest staged piece
-constexpr int kThreads = 4;                // worker threads per transfer
+constexpr int kThreads = 4;                // worker threads per transfer (8 measure the same: host memory bound)
 constexpr int kBufsPerThread = 3;          // pinned pieces in flight per thread
 constexpr size_t kMinChunk = 256u << 10;   // smallest piece (small transfers still get every lane busy)
 constexpr size_t kMinStaged = 4u << 20;    // below this the plain path wins (thread start-up, event traffic: measured)
