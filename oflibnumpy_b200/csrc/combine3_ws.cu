@@ -578,12 +578,12 @@ unsigned long long c3_ws_mixed_count() {
 }
 
 bool c3_ws_enabled() {
-    static int state = -1;
-    if (state < 0) {
+    static std::atomic<int> state{-1};
+    if (state.load() < 0) {
         const char* e = getenv("OFK_C3_WS");
-        state = (e != nullptr && e[0] == '0') ? 0 : 1;
+        state.store((e != nullptr && e[0] == '0') ? 0 : 1);
     }
-    return state == 1;
+    return state.load() == 1;
 }
 
 // The zero tests: flags[n] = {A_nonzero, B_nonzero} (combine3), or flags[n] = A_nonzero when B == NULL
@@ -629,10 +629,10 @@ int launch_combine3_ws(const float* P, const uint8_t* Pm, const float* G, const 
     const size_t smem = sizeof(Smem<WS_NP, WS_NB>);
 #define OFK_WS(MK, AD)                                                                                                  \
     do {                                                                                                              \
-        static bool attr_done_dev[64] = {false};   /* the attribute is per device */                                  \
+        static std::atomic<bool> attr_done_dev[64];   /* the attribute is per device; racing threads set it twice */ \
         int dev_ = 0;                                                                                                 \
         if (cudaGetDevice(&dev_) != cudaSuccess || dev_ < 0 || dev_ >= 64) return 0;                                  \
-        bool& attr_done = attr_done_dev[dev_];                                                                        \
+        std::atomic<bool>& attr_done = attr_done_dev[dev_];                                                           \
         if (!attr_done) {                                                                                             \
             if (cudaFuncSetAttribute(c3_ws_kernel<MK, AD, WS_NP, WS_NB, WS_LA, WS_PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      (int)smem) != cudaSuccess) {                                                     \

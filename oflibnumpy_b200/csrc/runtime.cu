@@ -22,7 +22,7 @@ void set_error(const char* fmt, ...) {
 }
 
 int sm_count() {
-    static int cached[64] = {0};
+    static std::atomic<int> cached[64];
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
     if (cached[dev] == 0) {

@@ -45,12 +45,12 @@ struct Stager {
 Stager g_stager;
 
 int staging_mode() {              // OFK_STAGED_COPIES=0 disables
-    static int mode = -1;
-    if (mode < 0) {
+    static std::atomic<int> mode{-1};
+    if (mode.load() < 0) {
         const char* e = getenv("OFK_STAGED_COPIES");
-        mode = (e != nullptr && e[0] == '0') ? 0 : 1;
+        mode.store((e != nullptr && e[0] == '0') ? 0 : 1);
     }
-    return mode;
+    return mode.load();
 }
 
 bool is_pageable(const void* p) {

@@ -607,7 +607,7 @@ template <int C, bool HALF_EVEN, int MM, bool FM>
 static int launch_variant(const Maps& maps, const uint8_t* img, const uint8_t* pmask, float sign, int rule, int H, int W,
                           unsigned tx, unsigned ty, unsigned total, int ctas_per_sm, cudaStream_t st) {
     using SM = Smem<WS_NP, WS_NB, MM == MM_PMASK, C>;
-    static bool attr_done_dev[64] = {false};   // the attribute is per device
+    static std::atomic<bool> attr_done_dev[64];   // the attribute is per device (racing threads set it twice)
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
     auto kernel = warp_u8_ws_kernel<C, HALF_EVEN, MM, FM, WS_NP, WS_NB, WS_LA, WS_PW>;
@@ -618,7 +618,7 @@ static int launch_variant(const Maps& maps, const uint8_t* img, const uint8_t* p
         }
         attr_done_dev[dev] = true;
     }
-    static int resident[64] = {0};              // co-resident CTAs per SM (shared memory / registers), per device
+    static std::atomic<int> resident[64];       // co-resident CTAs per SM (shared memory / registers), per device
     if (resident[dev] == 0) {
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, (NCW + WS_PW) * 32, sizeof(SM)) != cudaSuccess || nb < 1) {
@@ -627,7 +627,8 @@ static int launch_variant(const Maps& maps, const uint8_t* img, const uint8_t* p
         }
         resident[dev] = nb;
     }
-    unsigned grid = (unsigned)(sm_count() * (ctas_per_sm < resident[dev] ? ctas_per_sm : resident[dev]));
+    const int res = resident[dev].load();
+    unsigned grid = (unsigned)(sm_count() * (ctas_per_sm < res ? ctas_per_sm : res));
     if (grid > total) grid = total;
     grid = cap_ctas(grid);
     kernel<<<grid, (NCW + WS_PW) * 32, sizeof(SM), st>>>(maps, img, pmask, sign, rule, H, W, tx, tx * ty, total);
@@ -683,12 +684,12 @@ unsigned long long warp_ws_mixed_count() {
 }
 
 bool warp_ws_enabled() {
-    static int state = -1;
-    if (state < 0) {
+    static std::atomic<int> state{-1};
+    if (state.load() < 0) {
         const char* e = getenv("OFK_WARP_WS");
-        state = (e != nullptr && e[0] == '0') ? 0 : 1;
+        state.store((e != nullptr && e[0] == '0') ? 0 : 1);
     }
-    return state == 1;
+    return state.load() == 1;
 }
 
 // uint8 images with C = 1, 3 or 4 interleaved channels. Returns 1 if the kernel was launched, 0 if the configuration
