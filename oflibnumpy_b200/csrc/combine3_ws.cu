@@ -481,10 +481,8 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 2) c3_ws_kernel(const __grid_
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-#ifndef C3_NO_STORE
             tma_store_3d(&maps.ov, ps.p + (int)wrp * 4 * TS, tx0, ty0 + (int)wrp * 4, n);
             tma_store_3d(&maps.om, ps.pm + (int)wrp * 4 * TS, tx0, ty0 + (int)wrp * 4, n);
-#endif
             bulk_commit();
             if (prev_s >= 0) {
                 bulk_wait_read<1>();                 // the previous tile's rows have been read out of shared memory
