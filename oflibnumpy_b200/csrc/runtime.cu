@@ -272,6 +272,15 @@ int ring_prepare(int device, size_t bytes_per_slot) {
     return OFK_OK;
 }
 
+// Leaves no transfer in flight when an ofh_* call returns, on the error paths too: the copies read and write the
+// caller's buffers, which may be freed as soon as the call is over.
+struct DrainRing {
+    ~DrainRing() {
+        for (auto& s : g_ring.slot)
+            if (s.st) cudaStreamSynchronize(s.st);
+    }
+};
+
 size_t esize(int dtype) {
     switch (dtype) {
         case OFK_U8: return 1;
@@ -322,6 +331,7 @@ extern "C" int ofh_warp_t(const void* payload, int dtype, int C, int arith, cons
     if (cf > N) cf = N;
     int rc = ring_prepare(device, per_frame * cf + 4096);
     if (rc != OFK_OK) return rc;
+    DrainRing drain_on_exit;
     struct Pending {
         Slot* slot;
         int n0, cn;
@@ -387,6 +397,7 @@ extern "C" int ofh_combine3(const float* A, const uint8_t* Am, const float* B, c
     if (cf > N) cf = N;
     int rc = ring_prepare(device, per_frame * cf + 4096);
     if (rc != OFK_OK) return rc;
+    DrainRing drain_on_exit;
     struct Pending {
         Slot* slot;
         int n0, cn;
