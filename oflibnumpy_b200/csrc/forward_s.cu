@@ -74,7 +74,7 @@ __device__ __forceinline__ double edge_fn(const P2& u, int iu, const P2& v, int 
     return -((u.x - v.x) * (qy - v.y) - (u.y - v.y) * (qx - v.x));
 }
 
-__global__ void __launch_bounds__(256) fwd_scatter(const float* __restrict__ flow, float sign,
+__global__ void __launch_bounds__(256, 4) fwd_scatter(const float* __restrict__ flow, float sign,
                                                    const uint8_t* __restrict__ point_mask,
                                                    unsigned int* __restrict__ winner, int H, int W) {
     const int j = blockIdx.x * 32 + (threadIdx.x & 31);
