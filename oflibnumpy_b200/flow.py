@@ -229,7 +229,8 @@ class Flow(object):
             raise ValueError("Error setting flow mask: Input has a different shape than the flow vectors")
         if input_mask.dtype != np.bool_ and ((input_mask != 0) & (input_mask != 1)).any():
             raise ValueError("Error setting flow mask: Values must be 0 or 1")
-        self._dm, self._hm = DeviceArray.from_numpy(input_mask.astype(np.bool_)[None].view(np.uint8)), None
+        m = np.ascontiguousarray(input_mask, dtype=np.bool_)      # no host copy for a contiguous bool array: the upload copies
+        self._dm, self._hm = DeviceArray.from_numpy(m[None].view(np.uint8)), None
 
     @property
     def shape(self):
