@@ -6,7 +6,18 @@ Flows built from transforms use the oracle's generator, itself pinned bit-exact 
 """
 import numpy as np
 
-from oracle import flowref as R
+
+
+class _LazyOracle(object):
+    """The oracle is imported only when an input builder actually needs it: bench.py takes its workload parameters from
+    this module (cfg4_transforms, plain lists) and must not pull the oracle into its GPU leg."""
+
+    def __getattr__(self, name):
+        from oracle import flowref
+        return getattr(flowref, name)
+
+
+R = _LazyOracle()
 
 RESIZE_SCALES = [0.5, 2, [1.5, 0.75]]
 CFG5_SHAPE = (2160, 3840)

@@ -2,7 +2,7 @@
 through the drop-in API on one B200 and through the CPU oracle port (cv2.remap / scipy griddata, the reference's own
 native calls) on the same host, same inputs, results compared. Wall clock, numpy in / numpy out.
 
-    python tools/config_table.py [--skip-1080p-griddata]
+    python tests/perf/config_table.py [--skip-1080p-griddata]
 """
 import os
 import sys
@@ -10,7 +10,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import golden_inputs as gi  # noqa: E402

@@ -1,7 +1,7 @@
 """Single-frame latency through the drop-in Flow API (numpy in / numpy out), the way a user of the reference calls it."""
 import os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import oflibnumpy_b200 as of
 of.device.require_gpu()

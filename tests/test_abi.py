@@ -71,6 +71,30 @@ def test_product_does_not_import_oracle():
                 assert 'flowref' not in text and 'remap_q32' not in text, f
 
 
+def test_oracle_stays_inside_tests_smoke_and_bench_cpu_legs():
+    """Nothing under tools/ or examples/ touches the oracle; bench.py imports it only inside its CPU-baseline /
+    reference-arm functions; taking workload parameters from tests/golden_inputs.py does not import it either."""
+    import subprocess
+    import sys
+    for sub in ('tools', 'examples'):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, sub)):
+            for f in files:
+                if f.endswith(('.py', '.sh', '.c', '.cu')):
+                    text = open(os.path.join(dirpath, f)).read()
+                    assert not re.search(r'^\s*(from|import)\s+oracle\b', text, flags=re.M), f
+                    assert 'flowref' not in text, f
+    bench = open(os.path.join(ROOT, 'bench.py')).read()
+    for m in re.finditer(r'^(\s*)(from|import)\s+oracle\b', bench, flags=re.M):
+        assert len(m.group(1)) > 0, "bench.py must import the oracle inside its CPU legs only"
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import golden_inputs as gi\n"
+            "gi.cfg4_transforms(3)\n"
+            "assert not any(m.startswith('oracle') for m in sys.modules), 'oracle imported'\n"
+            "print('ok')\n") % (ROOT, os.path.join(ROOT, 'tests'))
+    res = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0 and 'ok' in res.stdout, res.stdout + res.stderr
+
+
 def _build_c_example():
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
