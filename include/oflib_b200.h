@@ -224,6 +224,12 @@ int ofk_forward_s(const float* payload, int C, const float* flow, float flow_sig
                   const uint8_t* point_mask, float* out, uint8_t* out_mask, int mask_rule, int N, int H, int W,
                   void* ws, size_t ws_bytes, ofk_stream_t stream);
 
+/* Test hook: cells of the displaced grid whose in-circle determinant is within +-tol take the OTHER diagonal in
+ * subsequent ofk_forward_s calls of this process (0 = production behaviour). Similarity transforms leave the four
+ * corners of a cell co-circular to within rounding; Qhull's diagonal there is arbitrary, and the parity tests compare
+ * the reference against both answers. */
+int ofk_forward_s_set_flip_tol(double tol);
+
 /* Scattered-to-scattered barycentric interpolation on the displaced-grid mesh: replaces the direct
  * `griddata(grid - A, A||mask, grid - B, 'linear', fill_value=0)` of combine_with mode 2 / ref 't'
  * (flow_class.py:1398-1410) and the griddata calls of track_pts (utils.py:603,614).
@@ -284,7 +290,9 @@ unsigned long long ofk_rt_launch_count(void);
  * kernels): which = 0 ofk_combine3 / TMA kernel, 1 ofk_combine3 / gather kernels, 2 ofk_warp_t / TMA kernels,
  * 3 ofk_warp_t / gather kernels. which = 4 / 5: inside the TMA kernels of ofk_combine3 / ofk_warp_t, how many
  * (warp, tile) pairs fetched taps from global memory because the tile's box did not cover them (discontinuous or noisy
- * flows); read synchronously from the current device. */
+ * flows); read synchronously from the current device. which = 6..9: ofk_forward_s, pixels outside the regular mesh
+ * since process start: 6 located in a bridging / pocket triangle, 7 found outside the hull by the search, 8 searches
+ * that did not terminate (treated as outside; expected 0), 9 rejected by the per-frame hull polygon. */
 unsigned long long ofk_rt_path_count(int which);
 
 #if defined(__GNUC__)

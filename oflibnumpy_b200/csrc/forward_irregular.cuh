@@ -1,0 +1,400 @@
+// Irregular part of the source-referenced resampler (see forward_geom.cuh): point location in the Delaunay
+// triangulation of the "boundary sites" -- the valid displaced pixels that have a removed or missing neighbour
+// (frame border, rim of a `consider_mask` hole). Pixels that no intact cell produces can only lie in a Delaunay
+// triangle spanned by such sites (or outside the convex hull): scipy.interpolate.griddata triangulates the remaining
+// points after the masked ones are dropped (utils.py:249-253 of the reference), bridging holes and filling the
+// pockets between the displaced border and its hull.
+//
+// The sites are binned by position (uniform grid of BIN x BIN pixels over the frame, border bins extend to infinity).
+// locate() finds the triangle of a query point q without ever building the triangulation:
+//   1. a = site nearest to q, b = site nearest to a: (a, b) is a Delaunay edge (nearest-neighbour graph);
+//   2. for the directed edge a -> b with q on its left, the Delaunay triangle on that side has the apex c whose
+//      circumcircle through a and b contains no other site on the left (empty-circle criterion; candidates are
+//      compared with the in-circle determinant, the search is limited to the bins under the current circle cap);
+//      no site on the left at all => (a, b) is a hull edge and q is outside the hull;
+//   3. q inside (a, b, c) (edges inclusive) => done; otherwise continue across the edge that separates q from the
+//      triangle (visibility walk, terminates on Delaunay triangulations).
+// Everything is order independent (ties go to the smaller site index), so the arbitrary order of sites inside a bin
+// (filled with atomics on the device) does not influence the result.
+#pragma once
+#include "forward_geom.cuh"
+
+namespace ofk {
+namespace fwd {
+
+constexpr int BIN_SHIFT = 2;               // fine bins of 4 x 4 pixels
+constexpr int BIN = 1 << BIN_SHIFT;
+constexpr int COARSE_SHIFT = 3;            // coarse bins of 8 x 8 fine bins (32 x 32 pixels), site counts only
+constexpr uint32_t NO_SITE = 0xffffffffu;
+constexpr int HULL_DIRS = 32;
+
+struct SiteGrid {
+    int H, W;
+    int nbx, nby, ncx, ncy;
+    const uint32_t* bin_start; // [nbx * nby + 1] offset of each bin in `sites` (the last entry is the site count)
+    const uint32_t* coarse;    // [ncx * ncy] number of sites per coarse bin
+    const uint32_t* sites;     // site ids (row * W + col), grouped by bin
+    const float* flow;         // [H, W, 2] of this frame
+    float sign;
+};
+
+OFK_HD int grid_bins(int extent) { return (extent + BIN - 1) >> BIN_SHIFT; }
+OFK_HD int grid_coarse(int nb) { return (nb + (1 << COARSE_SHIFT) - 1) >> COARSE_SHIFT; }
+
+OFK_HD P2 site_pos(const SiteGrid& g, uint32_t id) {
+    const int row = (int)(id / (uint32_t)g.W), col = (int)(id - (uint32_t)row * (uint32_t)g.W);
+    const float* f = g.flow + 2 * (size_t)id;
+    return displaced(f[0], f[1], row, col, g.sign);
+}
+
+// bin coordinate of a position; positions beyond the frame fall into the border bins
+OFK_HD int bin_coord(double v, int nb) {
+    const double b = floor(v * (1.0 / BIN));
+    return b <= 0.0 ? 0 : (b >= (double)(nb - 1) ? nb - 1 : (int)b);
+}
+
+template <class F>
+OFK_HD void scan_bin(const SiteGrid& g, int bx, int by, F& f) {
+    const int b = by * g.nbx + bx;
+    const uint32_t s0 = g.bin_start[b], s1 = g.bin_start[b + 1];
+    for (uint32_t s = s0; s < s1; ++s) f(g.sites[s]);
+}
+
+// all sites of the bins at Chebyshev distance r from (cx, cy)
+template <class F>
+OFK_HD void scan_ring(const SiteGrid& g, int cx, int cy, int r, F& f) {
+    if (r == 0) {
+        scan_bin(g, cx, cy, f);
+        return;
+    }
+    const int x0 = cx - r, x1 = cx + r, y0 = cy - r, y1 = cy + r;
+    const int xa = x0 < 0 ? 0 : x0, xb = x1 >= g.nbx ? g.nbx - 1 : x1;
+    if (y0 >= 0)
+        for (int x = xa; x <= xb; ++x) scan_bin(g, x, y0, f);
+    if (y1 < g.nby)
+        for (int x = xa; x <= xb; ++x) scan_bin(g, x, y1, f);
+    const int ya = y0 + 1 < 0 ? 0 : y0 + 1, yb = y1 - 1 >= g.nby ? g.nby - 1 : y1 - 1;
+    if (x0 >= 0)
+        for (int y = ya; y <= yb; ++y) scan_bin(g, x0, y, f);
+    if (x1 < g.nbx)
+        for (int y = ya; y <= yb; ++y) scan_bin(g, x1, y, f);
+}
+
+// distance from p (inside the scanned block of bins) to the nearest position that is NOT covered by the bins
+// [cx-r, cx+r] x [cy-r, cy+r]; infinity (1e300) when the block covers the whole grid
+OFK_HD double ring_reach(const SiteGrid& g, const P2& p, int cx, int cy, int r) {
+    double reach = 1e300;
+    if (cx - r > 0) reach = fmin(reach, p.x - (double)((cx - r) * BIN));
+    if (cx + r < g.nbx - 1) reach = fmin(reach, (double)((cx + r + 1) * BIN) - p.x);
+    if (cy - r > 0) reach = fmin(reach, p.y - (double)((cy - r) * BIN));
+    if (cy + r < g.nby - 1) reach = fmin(reach, (double)((cy + r + 1) * BIN) - p.y);
+    return reach;
+}
+
+struct NearestScan {
+    const SiteGrid& g;
+    P2 p;
+    uint32_t exclude, best;
+    double best_d2;
+    OFK_HD void operator()(uint32_t s) {
+        if (s == exclude) return;
+        const P2 ps = site_pos(g, s);
+        const double dx = dsub(ps.x, p.x), dy = dsub(ps.y, p.y), d2 = dfma(dx, dx, dmul(dy, dy));
+        if (d2 < best_d2 || (d2 == best_d2 && s < best)) {
+            best_d2 = d2;
+            best = s;
+        }
+    }
+};
+
+OFK_HD uint32_t nearest_site(const SiteGrid& g, const P2& p, uint32_t exclude) {
+    const int cx = bin_coord(p.x, g.nbx), cy = bin_coord(p.y, g.nby);
+    NearestScan sc{g, p, exclude, NO_SITE, 1e300};
+    const int rmax = (g.nbx > g.nby ? g.nbx : g.nby);
+    for (int r = 0; r <= rmax; ++r) {
+        scan_ring(g, cx, cy, r, sc);
+        const double reach = ring_reach(g, p, cx, cy, r);
+        if (reach >= 1e300) break;
+        if (sc.best != NO_SITE && reach > 0 && sc.best_d2 <= reach * reach) break;
+    }
+    return sc.best;
+}
+
+// circumcircle of (pa, pb, pc) as centre / squared radius; ok = false when the three points are so close to collinear
+// that the circle is numerically a half plane
+struct Circle {
+    double ox, oy, r2;
+    bool ok;
+};
+OFK_HD Circle circumcircle(const P2& pa, const P2& pb, const P2& pc) {
+    const double bx = pb.x - pa.x, by = pb.y - pa.y, cx = pc.x - pa.x, cy = pc.y - pa.y;
+    const double dd = 2.0 * (bx * cy - by * cx);
+    const double b2 = bx * bx + by * by, c2 = cx * cx + cy * cy;
+    const double ux = (cy * b2 - by * c2) / dd, uy = (bx * c2 - cx * b2) / dd;
+    Circle c;
+    c.r2 = ux * ux + uy * uy;
+    c.ok = (dd != 0.0) && c.r2 < 1e14;
+    c.ox = pa.x + ux;
+    c.oy = pa.y + uy;
+    return c;
+}
+
+struct ApexScan {
+    const SiteGrid& g;
+    P2 pa, pb, pbest;
+    uint32_t a, b, best;
+    Circle circ;
+    OFK_HD void take(uint32_t s, const P2& ps) {
+        best = s;
+        pbest = ps;
+        circ = circumcircle(pa, pb, ps);
+    }
+    OFK_HD void operator()(uint32_t s) {
+        if (s == a || s == b || s == best) return;
+        const P2 ps = site_pos(g, s);
+        if (!(orient(pa, pb, ps) > 0)) return;
+        if (best == NO_SITE) {
+            take(s, ps);
+            return;
+        }
+        const double ic = incircle(pa, pb, pbest, ps);   // > 0: s inside the circle of the current apex -> better
+        if (ic > 0 || (ic == 0 && s < best)) take(s, ps);
+    }
+    // can the block of bins [bx0, bx1] x [by0, by1] hold a site that beats the current apex? (conservative)
+    OFK_HD bool may_hold_better(int bx0, int bx1, int by0, int by1) const {
+        const double far = 1e12;
+        const double X0 = bx0 <= 0 ? -far : (double)(bx0 * BIN), X1 = bx1 >= g.nbx - 1 ? far : (double)((bx1 + 1) * BIN);
+        const double Y0 = by0 <= 0 ? -far : (double)(by0 * BIN), Y1 = by1 >= g.nby - 1 ? far : (double)((by1 + 1) * BIN);
+        // left of a -> b: the corner furthest to the left decides
+        const double ex = pb.x - pa.x, ey = pb.y - pa.y;
+        const double qx = (ey > 0 ? X0 : X1) - pa.x, qy = (ex > 0 ? Y1 : Y0) - pa.y;   // maximises ex*qy - ey*qx
+        if (!(ex * qy - ey * qx > 0)) return false;
+        if (best == NO_SITE || !circ.ok) return true;
+        const double dx = circ.ox < X0 ? X0 - circ.ox : (circ.ox > X1 ? circ.ox - X1 : 0.0);
+        const double dy = circ.oy < Y0 ? Y0 - circ.oy : (circ.oy > Y1 ? circ.oy - Y1 : 0.0);
+        return dx * dx + dy * dy <= circ.r2 * (1.0 + 1e-9) + 1e-9;
+    }
+};
+
+// bin range [x0, x1] x [y0, y1] covering the part of the circle left of pa -> pb (the cap that can hold a better apex)
+OFK_HD void cap_bins(const SiteGrid& g, const P2& pa, const P2& pb, const Circle& c, int& x0, int& x1, int& y0,
+                     int& y1) {
+    x0 = 0;
+    x1 = g.nbx - 1;
+    y0 = 0;
+    y1 = g.nby - 1;
+    if (!c.ok) return;
+    double xlo = fmin(pa.x, pb.x), xhi = fmax(pa.x, pb.x), ylo = fmin(pa.y, pb.y), yhi = fmax(pa.y, pb.y);
+    const double rr = sqrt(c.r2) * (1.0 + 1e-9) + 1e-9;
+    const P2 ex[4] = {{c.ox - rr, c.oy}, {c.ox + rr, c.oy}, {c.ox, c.oy - rr}, {c.ox, c.oy + rr}};
+    // an axis extreme of the circle belongs to the cap when it is left of a -> b (a margin keeps it conservative)
+    const double margin = -1e-6 * (fabs(pb.x - pa.x) + fabs(pb.y - pa.y)) * rr;
+    for (int k = 0; k < 4; ++k) {
+        if (orient(pa, pb, ex[k]) >= margin) {
+            xlo = fmin(xlo, ex[k].x);
+            xhi = fmax(xhi, ex[k].x);
+            ylo = fmin(ylo, ex[k].y);
+            yhi = fmax(yhi, ex[k].y);
+        }
+    }
+    x0 = bin_coord(xlo, g.nbx);
+    x1 = bin_coord(xhi, g.nbx);
+    y0 = bin_coord(ylo, g.nby);
+    y1 = bin_coord(yhi, g.nby);
+}
+
+// apex of the Delaunay triangle left of the directed edge a -> b, NO_SITE if there is no site on that side.
+// Every site that beats a candidate lies in that candidate's circle cap, and the cap only shrinks: a few rings of bins
+// around the edge midpoint give a first candidate (the final one for the small triangles that bridge holes); whatever
+// part of its cap they do not cover is swept through the two-level grid, skipping empty coarse bins and bins the
+// current cap does not reach (the long thin triangles of hull pockets).
+OFK_HD uint32_t apex_site(const SiteGrid& g, uint32_t a, uint32_t b, const P2& pa, const P2& pb) {
+    ApexScan sc{g, pa, pb, pa, a, b, NO_SITE, {0.0, 0.0, 0.0, false}};
+    P2 mid;
+    mid.x = 0.5 * (pa.x + pb.x);
+    mid.y = 0.5 * (pa.y + pb.y);
+    const int cx = bin_coord(mid.x, g.nbx), cy = bin_coord(mid.y, g.nby);
+    constexpr int NEAR_RINGS = 2;
+    int x0, x1, y0, y1;
+    for (int r = 0; r <= NEAR_RINGS; ++r) {
+        scan_ring(g, cx, cy, r, sc);
+        if (sc.best == NO_SITE) continue;
+        cap_bins(g, pa, pb, sc.circ, x0, x1, y0, y1);
+        if (x0 >= cx - r && x1 <= cx + r && y0 >= cy - r && y1 <= cy + r) return sc.best;
+    }
+    cap_bins(g, pa, pb, sc.circ, x0, x1, y0, y1);   // whole grid while there is no candidate
+    const int cs = COARSE_SHIFT, cw = 1 << cs;
+    for (int gy = y0 >> cs; gy <= (y1 >> cs); ++gy) {
+        for (int gx = x0 >> cs; gx <= (x1 >> cs); ++gx) {
+            if (g.coarse[gy * g.ncx + gx] == 0u) continue;
+            const int fx0 = (gx << cs) > x0 ? (gx << cs) : x0, fx1 = (gx << cs) + cw - 1 < x1 ? (gx << cs) + cw - 1 : x1;
+            const int fy0 = (gy << cs) > y0 ? (gy << cs) : y0, fy1 = (gy << cs) + cw - 1 < y1 ? (gy << cs) + cw - 1 : y1;
+            if (!sc.may_hold_better(fx0, fx1, fy0, fy1)) continue;
+            for (int by = fy0; by <= fy1; ++by) {
+                for (int bx = fx0; bx <= fx1; ++bx) {
+                    const int bi = by * g.nbx + bx;
+                    if (g.bin_start[bi] == g.bin_start[bi + 1]) continue;
+                    if (bx >= cx - NEAR_RINGS && bx <= cx + NEAR_RINGS && by >= cy - NEAR_RINGS &&
+                        by <= cy + NEAR_RINGS)
+                        continue;   // already scanned
+                    if (!sc.may_hold_better(bx, bx, by, by)) continue;
+                    scan_bin(g, bx, by, sc);
+                }
+            }
+        }
+    }
+    return sc.best;
+}
+
+constexpr int LOC_FOUND = 0, LOC_OUTSIDE = 1, LOC_FAILED = 2;
+constexpr int LOC_MAX_STEPS = 256;
+
+// Delaunay triangle of the boundary sites that contains q: vertex ids and barycentric weights
+OFK_HD int locate(const SiteGrid& g, const P2& q, uint32_t (&ids)[3], double (&w)[3]) {
+    uint32_t a = nearest_site(g, q, NO_SITE);
+    if (a == NO_SITE) return LOC_OUTSIDE;
+    P2 pa = site_pos(g, a);
+    if (pa.x == q.x && pa.y == q.y) {   // q is a site: its own value (barycentric weights 1, 0, 0)
+        ids[0] = ids[1] = ids[2] = a;
+        w[0] = 1.0;
+        w[1] = w[2] = 0.0;
+        return LOC_FOUND;
+    }
+    uint32_t b = nearest_site(g, pa, a);
+    if (b == NO_SITE) return LOC_OUTSIDE;
+    P2 pb = site_pos(g, b);
+    if (orient(pa, pb, q) < 0) {
+        const uint32_t t = a; a = b; b = t;
+        const P2 tp = pa; pa = pb; pb = tp;
+    }
+    bool flipped = false;
+    for (int step = 0; step < LOC_MAX_STEPS; ++step) {
+        const uint32_t c = apex_site(g, a, b, pa, pb);
+        if (c == NO_SITE) {
+            if (!flipped && orient(pa, pb, q) == 0) {   // q on the line through a hull edge: look on the other side
+                const uint32_t t = a; a = b; b = t;
+                const P2 tp = pa; pa = pb; pb = tp;
+                flipped = true;
+                continue;
+            }
+            return LOC_OUTSIDE;
+        }
+        const P2 pc = site_pos(g, c);
+        const double o1 = orient(pb, pc, q), o2 = orient(pc, pa, q);
+        if (o1 >= 0 && o2 >= 0) {
+            const double r = drcp(orient(pa, pb, pc));
+            ids[0] = a; ids[1] = b; ids[2] = c;
+            w[0] = dmul(o1, r);
+            w[1] = dmul(o2, r);
+            w[2] = dsub(dsub(1.0, w[0]), w[1]);
+            return LOC_FOUND;
+        }
+        flipped = false;
+        if (o1 < 0 && (o2 >= 0 || o1 < o2)) {   // across b -> c: continue with c -> b (q on its left)
+            a = c; pa = pc;
+        } else {                                // across c -> a: continue with a -> c
+            b = c; pb = pc;
+        }
+    }
+    return LOC_FAILED;
+}
+
+// ---------------------------------------------------------------------------------------------- hull pre-filter
+// Most pixels that no intact cell produces are simply outside the hull (the empty band of a translation, the corners
+// left by a rotation). Per frame: the extreme sites in HULL_DIRS directions form a convex polygon inside the hull;
+// `slack[i]` is the most negative orient(v_i, v_i+1, site) over all sites, i.e. how far sites reach beyond edge i.
+// A pixel further out than that is outside the hull without any search.
+struct HullInfo {
+    int m;                         // number of polygon vertices (0: no filter)
+    int pad_;
+    double vx[HULL_DIRS], vy[HULL_DIRS], slack[HULL_DIRS];
+};
+
+// direction k of the pre-filter (the table is computed once on the host and handed to the device, so both builds
+// select the same extreme sites)
+struct HullDirs {
+    double dx[HULL_DIRS], dy[HULL_DIRS];
+};
+
+// candidate for the extreme site in direction k: larger dot product wins, ties go to the smaller id
+OFK_HD bool hull_better(double dot, uint32_t id, double best_dot, uint32_t best_id) {
+    return best_id == NO_SITE || dot > best_dot || (dot == best_dot && id < best_id);
+}
+
+// polygon of the distinct extreme sites in direction order (convex, inside the hull)
+OFK_HD void hull_polygon(const SiteGrid& g, const uint32_t (&ext)[HULL_DIRS], HullInfo& h) {
+    uint32_t ids[HULL_DIRS];
+    int m = 0;
+    for (int k = 0; k < HULL_DIRS; ++k) {
+        if (ext[k] == NO_SITE) continue;
+        if (m > 0 && ids[m - 1] == ext[k]) continue;
+        ids[m++] = ext[k];
+    }
+    while (m > 1 && ids[m - 1] == ids[0]) --m;
+    if (m < 3) m = 0;
+    h.m = m;
+    h.pad_ = 0;
+    for (int i = 0; i < m; ++i) {
+        const P2 p = site_pos(g, ids[i]);
+        h.vx[i] = p.x;
+        h.vy[i] = p.y;
+        h.slack[i] = 0.0;
+    }
+}
+
+OFK_HD double hull_edge_orient(const HullInfo& h, int i, const P2& p) {
+    const int k = i + 1 == h.m ? 0 : i + 1;
+    P2 u, v;
+    u.x = h.vx[i]; u.y = h.vy[i];
+    v.x = h.vx[k]; v.y = h.vy[k];
+    return orient(u, v, p);
+}
+
+OFK_HD bool hull_rejects(const HullInfo& h, const P2& q) {
+    for (int i = 0; i < h.m; ++i) {
+        const int k = i + 1 == h.m ? 0 : i + 1;
+        const double o = hull_edge_orient(h, i, q);
+        const double scale = fabs(h.vx[k] - h.vx[i]) + fabs(h.vy[k] - h.vy[i]);
+        if (o < h.slack[i] - 1e-9 * (scale + 1.0) * (scale + 1.0)) return true;
+    }
+    return false;
+}
+
+// serial reference of the per-frame hull kernel (the host build uses it as is; the device kernel computes the same
+// maxima / minima with a block reduction)
+inline void hull_build_serial(const SiteGrid& g, uint32_t nsites, const HullDirs& dirs, HullInfo& h) {
+    uint32_t ext[HULL_DIRS];
+    double best[HULL_DIRS];
+    for (int k = 0; k < HULL_DIRS; ++k) {
+        ext[k] = NO_SITE;
+        best[k] = 0.0;
+    }
+    for (uint32_t s = 0; s < nsites; ++s) {
+        const uint32_t id = g.sites[s];
+        const P2 p = site_pos(g, id);
+        for (int k = 0; k < HULL_DIRS; ++k) {
+            const double dot = dfma(dirs.dx[k], p.x, dmul(dirs.dy[k], p.y));
+            if (hull_better(dot, id, best[k], ext[k])) {
+                best[k] = dot;
+                ext[k] = id;
+            }
+        }
+    }
+    hull_polygon(g, ext, h);
+    for (uint32_t s = 0; s < nsites; ++s) {
+        const P2 p = site_pos(g, g.sites[s]);
+        for (int i = 0; i < h.m; ++i) h.slack[i] = fmin(h.slack[i], hull_edge_orient(h, i, p));
+    }
+}
+
+// a valid site is a boundary site when it sits on the frame border or one of its 8 neighbours has been removed
+OFK_HD bool is_boundary_site(const uint8_t* point_mask, int H, int W, int row, int col) {
+    if (point_mask != nullptr && !point_mask[(size_t)row * W + col]) return false;
+    if (row == 0 || col == 0 || row == H - 1 || col == W - 1) return true;
+    if (point_mask == nullptr) return false;
+    const uint8_t* m = point_mask + (size_t)row * W + col;
+    return !(m[-W - 1] && m[-W] && m[-W + 1] && m[-1] && m[1] && m[W - 1] && m[W] && m[W + 1]);
+}
+
+}  // namespace fwd
+}  // namespace ofk

@@ -16,6 +16,7 @@ extern std::atomic<unsigned long long> g_paths[4];   // see ofk_rt_path_count
 int staged_copy(void* dst, const void* src, size_t bytes, bool to_device, cudaStream_t user);   // staging.cu
 unsigned long long c3_ws_mixed_count();               // combine3_ws.cu
 unsigned long long warp_ws_mixed_count();             // warp_t_ws.cu
+unsigned long long forward_s_stat(int which);         // forward_s.cu
 
 #define OFK_CHECK_ARG(cond, ...)                \
     do {                                        \

@@ -344,7 +344,90 @@ def case_visualise():
     return d
 
 
+def pack(mask):
+    return np.packbits(np.ascontiguousarray(mask, dtype=bool).ravel())
+
+
+def flow_out_sampled(prefix, fl, idx, d):
+    """Full-size outputs: the mask complete (bit-packed), the vectors at the sampled pixels only."""
+    d['out_' + prefix + '_vecs_s'] = fl.vecs.reshape(-1, 2)[idx]
+    d['out_' + prefix + '_maskbits'] = pack(fl.mask)
+    d['out_' + prefix + '_ref'] = np.array(fl.ref)
+
+
+def case_cfg3_full():
+    """cfg 3 at 436x1024 through the unmodified reference: apply 's' of a float32 x3 image, same-reference invert
+    (s->s and t->t), switch_ref, the 's'-resampled valid areas; full masks and the 5 % random mask (consider_mask
+    True and False)."""
+    d = {}
+    inp = gi.cfg3_full()
+    h, w = inp['mask'].shape
+    idx = gi.sample_pixels(h, w, frac=0.02, band=2)
+    for pair in ('aff', 'smooth'):
+        for tag, m in (('full', None), ('m5', inp['mask'])):
+            t0 = time.time()
+            fs = ref.Flow(inp[pair], 's', m)
+            ft = ref.Flow(inp[pair], 't', m)
+            k = pair + '_' + tag
+            img, va = fs.apply(inp['img_f32c3'], return_valid_area=True)
+            d['out_applyva_' + k + '_img_s'] = img.reshape(-1, 3)[idx]
+            d['out_applyva_' + k + '_validbits'] = pack(va)
+            flow_out_sampled('invert_ss_' + k, fs.invert(), idx, d)
+            flow_out_sampled('invert_tt_' + k, ft.invert(), idx, d)
+            flow_out_sampled('switch_s_' + k, fs.switch_ref(), idx, d)
+            flow_out_sampled('switch_t_' + k, ft.switch_ref(), idx, d)
+            d['out_valid_target_s_' + k + '_bits'] = pack(fs.valid_target())
+            d['out_valid_source_t_' + k + '_bits'] = pack(ft.valid_source())
+            if m is not None:
+                d['out_valid_target_s_' + k + '_nocm_bits'] = pack(fs.valid_target(consider_mask=False))
+                flow_out_sampled('invert_ss_' + k + '_nocm', fs.apply(-fs, consider_mask=False), idx, d)
+            print('cfg3_full', k, round(time.time() - t0, 1), 's', flush=True)
+    return d
+
+
+def case_modes12_1080p():
+    """cfg 4 as written: one 1080p frame pair (frame 0 of the seeded batch, 2 % invalid masks) through
+    combine_with modes 1 and 2 of the unmodified reference, both references."""
+    d = {}
+    fa, fam, fb, fbm, _ = gi.cfg4_frame(0)
+    sa, sam, sb, sbm = gi.cfg4_pair_s(0)
+    idx = gi.sample_pixels(1080, 1920, frac=0.02)
+    for r, (a, am, b, bm) in (('t', (fa, fam, fb, fbm)), ('s', (sa, sam, sb, sbm))):
+        for mode in (2, 1):
+            t0 = time.time()
+            res = ref.Flow(a, r, am).combine_with(ref.Flow(b, r, bm), mode)
+            flow_out_sampled('m%d_%s' % (mode, r), res, idx, d)
+            print('modes12_1080p', mode, r, round(time.time() - t0, 1), 's', flush=True)
+    return d
+
+
+def case_cfg5_true():
+    """cfg 5 as written at 3840x2160: from_transforms -> invert() (same reference, t->t: one griddata) -> 4 x
+    combine_with(mode 3) -> apply to a uint8 x3 image with valid area."""
+    d = {}
+    t0 = time.time()
+    f = ref.Flow.from_transforms(gi.CFG5_TRANSFORMS, gi.CFG5_SHAPE, 't')
+    g = f.invert()
+    print('cfg5_true invert', round(time.time() - t0, 1), 's', flush=True)
+    h, w = gi.CFG5_SHAPE
+    idx = gi.sample_pixels(h, w, frac=0.01)
+    flow_out_sampled('g', g, idx, d)
+    acc = f
+    for i in range(4):
+        acc = acc.combine_with(g if i % 2 == 0 else f, 3)
+    flow_out_sampled('chain', acc, idx, d)
+    img = gi.cfg5_image()
+    wimg, m = acc.apply(img, return_valid_area=True)
+    d['out_chain_img_s'] = wimg.reshape(-1, 3)[idx]
+    d['out_chain_validbits'] = pack(m)
+    print('cfg5_true', round(time.time() - t0, 1), 's', flush=True)
+    return d
+
+
 CASES = {
+    'cfg3_full': case_cfg3_full,
+    'modes12_1080p': case_modes12_1080p,
+    'cfg5_true': case_cfg5_true,
     'visualise': case_visualise,
     'datasets': case_datasets,
     'warp_t': case_warp_t,

@@ -167,6 +167,39 @@ def cfg2_full():
     return a, am, b, bm
 
 
+def cfg3_full():
+    """cfg 3 of BASELINE.json at full size (436x1024): 's'-labelled rotation and smooth non-affine fields of SURVEY
+    section 8d-3, a float32 x3 image and the 5 % random flow mask that is reported separately."""
+    h, w = 436, 1024
+    rng = np.random.default_rng(33)
+    d = {}
+    d['aff'] = R.from_transforms([['rotation', 512, 218, -8]], (h, w), 's')
+    d['smooth'] = smooth_field(h, w)
+    d['img_f32c3'] = (rng.random((h, w, 3)) * 255).astype(np.float32)
+    d['mask'] = rng.random((h, w)) > 0.05
+    return d
+
+
+def sample_pixels(h, w, seed=77, frac=0.08, band=6):
+    """Flat pixel indices at which full-size goldens keep VALUES (masks are kept complete, bit-packed): a seeded
+    random subset plus every pixel of a border band (hull effects live there)."""
+    rng = np.random.default_rng(seed)
+    pick = rng.random((h, w)) < frac
+    pick[:band] = pick[-band:] = True
+    pick[:, :band] = pick[:, -band:] = True
+    return np.flatnonzero(pick.ravel())
+
+
+def cfg4_pair_s(idx, h=1080, w=1920):
+    """cfg4_frame's two flows in the other direction ('s' generators of the same transforms), same masks."""
+    rng = np.random.default_rng(1000 + idx)
+    fa = R.from_transforms(cfg4_transforms(idx), (h, w), 's')
+    fb = R.from_transforms(cfg4_transforms(idx + 100000), (h, w), 's')
+    fam = rng.random((h, w)) > 0.02
+    fbm = rng.random((h, w)) > 0.02
+    return fa, fam, fb, fbm
+
+
 def cfg4_transforms(idx):
     """Per-frame rotation U(-10,10) deg about centre, scaling U(0.9,1.1), translation U(-20,20) px; seed 4+idx."""
     rng = np.random.default_rng(4 + idx)
