@@ -292,7 +292,8 @@ unsigned long long ofk_rt_launch_count(void);
  * (warp, tile) pairs fetched taps from global memory because the tile's box did not cover them (discontinuous or noisy
  * flows); read synchronously from the current device. which = 6..9: ofk_forward_s, pixels outside the regular mesh
  * since process start: 6 located in a bridging / pocket triangle, 7 found outside the hull by the search, 8 searches
- * that did not terminate (treated as outside; expected 0), 9 rejected by the per-frame hull polygon. */
+ * that did not terminate (treated as outside; expected 0), 9 rejected by the per-frame hull polygon, 10 pixels handed
+ * to the warp-cooperative pocket pass, 11 its work items. */
 unsigned long long ofk_rt_path_count(int which);
 
 #if defined(__GNUC__)

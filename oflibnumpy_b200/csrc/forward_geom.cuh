@@ -134,6 +134,58 @@ OFK_HD int cell_diagonal(const P2& a, const P2& b, const P2& c, const P2& d, dou
     return diag;
 }
 
+// Which triangle of the cell (split along `diag`) owns the point q: 0 / 1, or -1 when q belongs to another cell. The
+// fill rule: an edge traversed from its smaller-index endpoint to the larger one includes F == 0, the reverse
+// traversal excludes it, so a point on a shared edge or vertex has exactly one owner in the whole mesh.
+OFK_HD int owner_triangle(const P2& a, const P2& b, const P2& c, const P2& d, int diag, double qx, double qy) {
+    const double fab = edge_canon(a, b, qx, qy);
+    const double fbd = edge_canon(b, d, qx, qy);
+    const double fcd = edge_canon(c, d, qx, qy);
+    const double fac = edge_canon(a, c, qx, qy);
+    if (diag == 0) {
+        const double fad = edge_canon(a, d, qx, qy);
+        if (fab >= 0 && fbd >= 0 && fad < 0) return 0;     // (a, b, d): a->b, b->d canonical, d->a reversed
+        if (fad >= 0 && fcd < 0 && fac < 0) return 1;      // (a, d, c): a->d canonical, d->c, c->a reversed
+    } else {
+        const double fbc = edge_canon(b, c, qx, qy);
+        if (fab >= 0 && fbc >= 0 && fac < 0) return 0;     // (a, b, c): a->b, b->c canonical, c->a reversed
+        if (fbd >= 0 && fcd < 0 && fbc < 0) return 1;      // (b, d, c): b->d canonical, d->c, c->b reversed
+    }
+    return -1;
+}
+
+// Barycentric weights of q in triangle `tri` of the cell: corner codes (0..3 = a..d) k[3] and weights w[3].
+// area2 = twice the signed area of that triangle as cell_diagonal() returns it.
+OFK_HD void triangle_weights(const P2& a, const P2& b, const P2& c, const P2& d, int diag, int tri, double area2,
+                             double qx, double qy, int (&k)[3], double (&w)[3]) {
+    double e0, e1;
+    if (diag == 0) {
+        if (tri == 0) {           // (a, b, d)
+            e0 = edge_canon(b, d, qx, qy);
+            e1 = -edge_canon(a, d, qx, qy);
+            k[0] = 0; k[1] = 1; k[2] = 3;
+        } else {                  // (a, d, c)
+            e0 = -edge_canon(c, d, qx, qy);
+            e1 = -edge_canon(a, c, qx, qy);
+            k[0] = 0; k[1] = 3; k[2] = 2;
+        }
+    } else {
+        if (tri == 0) {           // (a, b, c)
+            e0 = edge_canon(b, c, qx, qy);
+            e1 = -edge_canon(a, c, qx, qy);
+            k[0] = 0; k[1] = 1; k[2] = 2;
+        } else {                  // (b, d, c)
+            e0 = -edge_canon(c, d, qx, qy);
+            e1 = -edge_canon(b, c, qx, qy);
+            k[0] = 1; k[1] = 3; k[2] = 2;
+        }
+    }
+    const double r = drcp(area2);
+    w[0] = dmul(e0, r);
+    w[1] = dmul(e1, r);
+    w[2] = dsub(dsub(1.0, w[0]), w[1]);
+}
+
 // Rasterises an intact cell: calls emit(x, y, k0, k1, k2, w0, w1, w2) once for every pixel the cell's two triangles
 // own (k = corner codes 0..3 = a..d, w = barycentric weights). W, H: frame size (candidates are clipped to it).
 template <class Emit>
@@ -147,30 +199,12 @@ OFK_HD void raster_cell(const P2& a, const P2& b, const P2& c, const P2& d, int 
     const int y0 = (int)ceil(fmax(ylo, 0.0)), y1 = (int)floor(fmin(yhi, (double)(H - 1)));
     for (int y = y0; y <= y1; ++y) {
         for (int x = x0; x <= x1; ++x) {
-            const double qx = x, qy = y;
-            const double fab = edge_canon(a, b, qx, qy);
-            const double fbd = edge_canon(b, d, qx, qy);
-            const double fcd = edge_canon(c, d, qx, qy);
-            const double fac = edge_canon(a, c, qx, qy);
-            if (diag == 0) {
-                const double fad = edge_canon(a, d, qx, qy);
-                if (fab >= 0 && fbd >= 0 && fad < 0) {          // (a, b, d): a->b, b->d canonical, d->a reversed
-                    const double r = drcp(area2[0]), w0 = dmul(fbd, r), w1 = dmul(-fad, r);
-                    emit(x, y, 0, 1, 3, w0, w1, dsub(dsub(1.0, w0), w1));
-                } else if (fad >= 0 && fcd < 0 && fac < 0) {    // (a, d, c): a->d canonical, d->c, c->a reversed
-                    const double r = drcp(area2[1]), w0 = dmul(-fcd, r), w1 = dmul(-fac, r);
-                    emit(x, y, 0, 3, 2, w0, w1, dsub(dsub(1.0, w0), w1));
-                }
-            } else {
-                const double fbc = edge_canon(b, c, qx, qy);
-                if (fab >= 0 && fbc >= 0 && fac < 0) {          // (a, b, c): a->b, b->c canonical, c->a reversed
-                    const double r = drcp(area2[0]), w0 = dmul(fbc, r), w1 = dmul(-fac, r);
-                    emit(x, y, 0, 1, 2, w0, w1, dsub(dsub(1.0, w0), w1));
-                } else if (fbd >= 0 && fcd < 0 && fbc < 0) {    // (b, d, c): b->d canonical, d->c, c->b reversed
-                    const double r = drcp(area2[1]), w0 = dmul(-fcd, r), w1 = dmul(-fbc, r);
-                    emit(x, y, 1, 3, 2, w0, w1, dsub(dsub(1.0, w0), w1));
-                }
-            }
+            const int tri = owner_triangle(a, b, c, d, diag, (double)x, (double)y);
+            if (tri < 0) continue;
+            int k[3];
+            double w[3];
+            triangle_weights(a, b, c, d, diag, tri, area2[tri], (double)x, (double)y, k, w);
+            emit(x, y, k[0], k[1], k[2], w[0], w[1], w[2]);
         }
     }
 }

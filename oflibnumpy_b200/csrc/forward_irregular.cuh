@@ -22,6 +22,15 @@
 namespace ofk {
 namespace fwd {
 
+#if defined(OFK_FWD_INSTR) && defined(__CUDACC__)   // profiling build only (OFK_FWD_INSTR=1 python -m oflibnumpy_b200.build)
+__device__ unsigned long long g_instr[8];
+#endif
+#if defined(OFK_FWD_INSTR) && defined(__CUDA_ARCH__)
+#define OFK_COUNT(i) atomicAdd(&g_instr[i], 1ull)
+#else
+#define OFK_COUNT(i)
+#endif
+
 constexpr int BIN_SHIFT = 2;               // fine bins of 4 x 4 pixels
 constexpr int BIN = 1 << BIN_SHIFT;
 constexpr int COARSE_SHIFT = 3;            // coarse bins of 8 x 8 fine bins (32 x 32 pixels), site counts only
@@ -144,12 +153,15 @@ struct ApexScan {
     P2 pa, pb, pbest;
     uint32_t a, b, best;
     Circle circ;
+    int visited;
     OFK_HD void take(uint32_t s, const P2& ps) {
         best = s;
         pbest = ps;
         circ = circumcircle(pa, pb, ps);
     }
     OFK_HD void operator()(uint32_t s) {
+        ++visited;
+        OFK_COUNT(3);   // sites looked at (all searches)
         if (s == a || s == b || s == best) return;
         const P2 ps = site_pos(g, s);
         if (!(orient(pa, pb, ps) > 0)) return;
@@ -203,13 +215,57 @@ OFK_HD void cap_bins(const SiteGrid& g, const P2& pa, const P2& pb, const Circle
     y1 = bin_coord(yhi, g.nby);
 }
 
+// A search can be shared by the lanes of a warp (device only): the bins of the cap sweep are dealt out by bin index,
+// every lane keeps the best candidate of its share (pruning with its own candidate stays valid: the overall best lies in
+// the cap of every other candidate) and the 32 candidates are reduced with the same in-circle comparison.
+// n == 1: a single thread does everything (host build; per-thread searches on the device).
+struct Coop {
+    int lane, n;
+};
+constexpr uint32_t OVER_BUDGET = 0xfffffffeu;   // apex_site gave up: more than `budget` sites looked at
+
+OFK_HD void coop_reduce(ApexScan& sc, const Coop& coop) {
+#if defined(__CUDA_ARCH__)
+    if (coop.n == 1) return;
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint32_t ob = __shfl_xor_sync(0xffffffffu, sc.best, o);
+        P2 op;
+        op.x = __shfl_xor_sync(0xffffffffu, sc.pbest.x, o);
+        op.y = __shfl_xor_sync(0xffffffffu, sc.pbest.y, o);
+        if (ob == NO_SITE || ob == sc.best) continue;
+        bool take = sc.best == NO_SITE;
+        if (!take) {
+            const double ic = incircle(sc.pa, sc.pb, sc.pbest, op);
+            take = ic > 0 || (ic == 0 && ob < sc.best);
+        }
+        if (take) {
+            sc.best = ob;
+            sc.pbest = op;
+        }
+    }
+    // rounding can make the comparison non-transitive in degenerate configurations: lane 0 has the last word
+    sc.best = __shfl_sync(0xffffffffu, sc.best, 0);
+    sc.pbest.x = __shfl_sync(0xffffffffu, sc.pbest.x, 0);
+    sc.pbest.y = __shfl_sync(0xffffffffu, sc.pbest.y, 0);
+#else
+    (void)sc;
+    (void)coop;
+#endif
+}
+
 // apex of the Delaunay triangle left of the directed edge a -> b, NO_SITE if there is no site on that side.
 // Every site that beats a candidate lies in that candidate's circle cap, and the cap only shrinks: a few rings of bins
 // around the edge midpoint give a first candidate (the final one for the small triangles that bridge holes); whatever
 // part of its cap they do not cover is swept through the two-level grid, skipping empty coarse bins and bins the
 // current cap does not reach (the long thin triangles of hull pockets).
-OFK_HD uint32_t apex_site(const SiteGrid& g, uint32_t a, uint32_t b, const P2& pa, const P2& pb) {
-    ApexScan sc{g, pa, pb, pa, a, b, NO_SITE, {0.0, 0.0, 0.0, false}};
+OFK_HD uint32_t apex_site_impl(const SiteGrid& g, uint32_t a, uint32_t b, const P2& pa, const P2& pb,
+                               const Coop& coop, int budget, int& visited) {
+    ApexScan sc{g, pa, pb, pa, a, b, NO_SITE, {0.0, 0.0, 0.0, false}, 0};
+    struct Tally {   // whatever way the search ends, the sites it looked at count against the caller's budget
+        int& total;
+        const int& mine;
+        OFK_HD ~Tally() { total += mine; }
+    } tally{visited, sc.visited};
     P2 mid;
     mid.x = 0.5 * (pa.x + pb.x);
     mid.y = 0.5 * (pa.y + pb.y);
@@ -222,10 +278,15 @@ OFK_HD uint32_t apex_site(const SiteGrid& g, uint32_t a, uint32_t b, const P2& p
         cap_bins(g, pa, pb, sc.circ, x0, x1, y0, y1);
         if (x0 >= cx - r && x1 <= cx + r && y0 >= cy - r && y1 <= cy + r) return sc.best;
     }
-    cap_bins(g, pa, pb, sc.circ, x0, x1, y0, y1);   // whole grid while there is no candidate
     const int cs = COARSE_SHIFT, cw = 1 << cs;
-    for (int gy = y0 >> cs; gy <= (y1 >> cs); ++gy) {
-        for (int gx = x0 >> cs; gx <= (x1 >> cs); ++gx) {
+    if (coop.n > 1) {
+        // a warp shares the search: the coarse bins under the cap of the first candidate (the whole grid without one)
+        // are dealt out to the lanes, every lane sweeps its share pruning with its own best candidate, one reduction
+        cap_bins(g, pa, pb, sc.circ, x0, x1, y0, y1);
+        const int gx0 = x0 >> cs, gx1 = x1 >> cs, gy0 = y0 >> cs, gy1 = y1 >> cs;
+        const int gw = gx1 - gx0 + 1, total = gw * (gy1 - gy0 + 1);
+        for (int t = coop.lane; t < total; t += coop.n) {
+            const int gy = gy0 + t / gw, gx = gx0 + t % gw;
             if (g.coarse[gy * g.ncx + gx] == 0u) continue;
             const int fx0 = (gx << cs) > x0 ? (gx << cs) : x0, fx1 = (gx << cs) + cw - 1 < x1 ? (gx << cs) + cw - 1 : x1;
             const int fy0 = (gy << cs) > y0 ? (gy << cs) : y0, fy1 = (gy << cs) + cw - 1 < y1 ? (gy << cs) + cw - 1 : y1;
@@ -234,42 +295,72 @@ OFK_HD uint32_t apex_site(const SiteGrid& g, uint32_t a, uint32_t b, const P2& p
                 for (int bx = fx0; bx <= fx1; ++bx) {
                     const int bi = by * g.nbx + bx;
                     if (g.bin_start[bi] == g.bin_start[bi + 1]) continue;
-                    if (bx >= cx - NEAR_RINGS && bx <= cx + NEAR_RINGS && by >= cy - NEAR_RINGS &&
-                        by <= cy + NEAR_RINGS)
+                    if (bx >= cx - NEAR_RINGS && bx <= cx + NEAR_RINGS && by >= cy - NEAR_RINGS && by <= cy + NEAR_RINGS)
                         continue;   // already scanned
                     if (!sc.may_hold_better(bx, bx, by, by)) continue;
                     scan_bin(g, bx, by, sc);
                 }
             }
         }
+        coop_reduce(sc, coop);
+        return sc.best;
+    }
+    // sweep the rest of the cap through the two-level grid, rings of coarse bins around the midpoint (near to far: a
+    // good candidate early shrinks the cap), until the rings cover the cap of the best candidate
+    const int ccx = cx >> cs, ccy = cy >> cs;
+    const int rcmax = (g.ncx > g.ncy ? g.ncx : g.ncy);
+    for (int rc = 0; rc <= rcmax; ++rc) {
+        if (sc.visited > budget) return OVER_BUDGET;
+        cap_bins(g, pa, pb, sc.circ, x0, x1, y0, y1);   // whole grid while there is no candidate
+        const int gx0 = x0 >> cs, gx1 = x1 >> cs, gy0 = y0 >> cs, gy1 = y1 >> cs;
+        if (rc > 0 && gx0 > ccx - rc && gx1 < ccx + rc && gy0 > ccy - rc && gy1 < ccy + rc) break;   // covered
+        for (int gy = ccy - rc; gy <= ccy + rc; ++gy) {
+            if (gy < gy0 || gy > gy1) continue;
+            const bool edge_row = (gy == ccy - rc || gy == ccy + rc);
+            for (int gx = ccx - rc; gx <= ccx + rc; gx += (edge_row || rc == 0) ? 1 : 2 * rc) {
+                if (gx < gx0 || gx > gx1) continue;
+                if (g.coarse[gy * g.ncx + gx] == 0u) continue;
+                const int fx0 = (gx << cs) > x0 ? (gx << cs) : x0, fx1 = (gx << cs) + cw - 1 < x1 ? (gx << cs) + cw - 1 : x1;
+                const int fy0 = (gy << cs) > y0 ? (gy << cs) : y0, fy1 = (gy << cs) + cw - 1 < y1 ? (gy << cs) + cw - 1 : y1;
+                if (!sc.may_hold_better(fx0, fx1, fy0, fy1)) continue;
+                for (int by = fy0; by <= fy1; ++by) {
+                    for (int bx = fx0; bx <= fx1; ++bx) {
+                        const int bi = by * g.nbx + bx;
+                        if (g.bin_start[bi] == g.bin_start[bi + 1]) continue;
+                        if (bx >= cx - NEAR_RINGS && bx <= cx + NEAR_RINGS && by >= cy - NEAR_RINGS &&
+                            by <= cy + NEAR_RINGS)
+                            continue;   // already scanned
+                        if (!sc.may_hold_better(bx, bx, by, by)) continue;
+                        scan_bin(g, bx, by, sc);
+                    }
+                }
+            }
+        }
+        if (ccx - rc <= 0 && ccy - rc <= 0 && ccx + rc >= g.ncx - 1 && ccy + rc >= g.ncy - 1) break;   // whole grid
     }
     return sc.best;
 }
 
-constexpr int LOC_FOUND = 0, LOC_OUTSIDE = 1, LOC_FAILED = 2;
+OFK_HD uint32_t apex_site(const SiteGrid& g, uint32_t a, uint32_t b, const P2& pa, const P2& pb, const Coop& coop,
+                          int& budget) {   // budget: sites the caller may still look at (decremented)
+    int visited = 0;
+    const uint32_t c = apex_site_impl(g, a, b, pa, pb, coop, budget, visited);
+    if (budget != 0x7fffffff) budget -= visited;
+    return (c != OVER_BUDGET && budget < 0) ? OVER_BUDGET : c;
+}
+
+constexpr int LOC_FOUND = 0, LOC_OUTSIDE = 1, LOC_FAILED = 2, LOC_HEAVY = 3;
+constexpr int NO_BUDGET = 0x7fffffff;
 constexpr int LOC_MAX_STEPS = 256;
 
-// Delaunay triangle of the boundary sites that contains q: vertex ids and barycentric weights
-OFK_HD int locate(const SiteGrid& g, const P2& q, uint32_t (&ids)[3], double (&w)[3]) {
-    uint32_t a = nearest_site(g, q, NO_SITE);
-    if (a == NO_SITE) return LOC_OUTSIDE;
-    P2 pa = site_pos(g, a);
-    if (pa.x == q.x && pa.y == q.y) {   // q is a site: its own value (barycentric weights 1, 0, 0)
-        ids[0] = ids[1] = ids[2] = a;
-        w[0] = 1.0;
-        w[1] = w[2] = 0.0;
-        return LOC_FOUND;
-    }
-    uint32_t b = nearest_site(g, pa, a);
-    if (b == NO_SITE) return LOC_OUTSIDE;
-    P2 pb = site_pos(g, b);
-    if (orient(pa, pb, q) < 0) {
-        const uint32_t t = a; a = b; b = t;
-        const P2 tp = pa; pa = pb; pb = tp;
-    }
+// The walk: from the Delaunay edge a -> b (q on its left or on its line) to the triangle that contains q.
+OFK_HD int locate_walk(const SiteGrid& g, const P2& q, uint32_t a, uint32_t b, P2 pa, P2 pb, uint32_t (&ids)[3],
+                       double (&w)[3], const Coop& coop, int budget) {   // budget: sites of the whole walk
     bool flipped = false;
     for (int step = 0; step < LOC_MAX_STEPS; ++step) {
-        const uint32_t c = apex_site(g, a, b, pa, pb);
+        if (coop.n > 1 && coop.lane == 0) OFK_COUNT(0);   // steps of cooperative walks
+        const uint32_t c = apex_site(g, a, b, pa, pb, coop, budget);
+        if (c == OVER_BUDGET) return LOC_HEAVY;
         if (c == NO_SITE) {
             if (!flipped && orient(pa, pb, q) == 0) {   // q on the line through a hull edge: look on the other side
                 const uint32_t t = a; a = b; b = t;
@@ -297,6 +388,50 @@ OFK_HD int locate(const SiteGrid& g, const P2& q, uint32_t (&ids)[3], double (&w
         }
     }
     return LOC_FAILED;
+}
+
+// Delaunay triangle of the boundary sites that contains q: vertex ids and barycentric weights
+OFK_HD int locate(const SiteGrid& g, const P2& q, uint32_t (&ids)[3], double (&w)[3], const Coop& coop = Coop{0, 1},
+                  int budget = NO_BUDGET) {
+    uint32_t a = nearest_site(g, q, NO_SITE);
+    if (a == NO_SITE) return LOC_OUTSIDE;
+    P2 pa = site_pos(g, a);
+    if (pa.x == q.x && pa.y == q.y) {   // q is a site: its own value (barycentric weights 1, 0, 0)
+        ids[0] = ids[1] = ids[2] = a;
+        w[0] = 1.0;
+        w[1] = w[2] = 0.0;
+        return LOC_FOUND;
+    }
+    uint32_t b = nearest_site(g, pa, a);
+    if (b == NO_SITE) return LOC_OUTSIDE;
+    P2 pb = site_pos(g, b);
+    if (orient(pa, pb, q) < 0) {
+        const uint32_t t = a; a = b; b = t;
+        const P2 tp = pa; pa = pb; pb = tp;
+    }
+    return locate_walk(g, q, a, b, pa, pb, ids, w, coop, budget);
+}
+
+// The same with a hint: a Delaunay triangle (ids of a previous, nearby query, positively oriented). q inside it costs
+// three orientation tests; otherwise the walk starts across the edge that separates q from it. Pocket triangles are
+// long fans: a walk from the nearest site crosses dozens of them, from the neighbouring pixel's triangle one or two.
+OFK_HD int locate_hinted(const SiteGrid& g, const P2& q, const uint32_t (&hint)[3], uint32_t (&ids)[3],
+                         double (&w)[3], const Coop& coop = Coop{0, 1}, int budget = NO_BUDGET) {
+    if (hint[0] == hint[1]) return locate(g, q, ids, w, coop, budget);   // the hint is a site hit, not a triangle
+    const P2 p0 = site_pos(g, hint[0]), p1 = site_pos(g, hint[1]), p2 = site_pos(g, hint[2]);
+    const double o0 = orient(p1, p2, q), o1 = orient(p2, p0, q), o2 = orient(p0, p1, q);
+    if (o0 >= 0 && o1 >= 0 && o2 >= 0) {
+        const double r = drcp(orient(p0, p1, p2));
+        ids[0] = hint[0]; ids[1] = hint[1]; ids[2] = hint[2];
+        w[0] = dmul(o0, r);
+        w[1] = dmul(o1, r);
+        w[2] = dsub(dsub(1.0, w[0]), w[1]);
+        return LOC_FOUND;
+    }
+    // leave through the most violated edge, reversed so that q is on its left
+    if (o0 <= o1 && o0 <= o2) return locate_walk(g, q, hint[2], hint[1], p2, p1, ids, w, coop, budget);
+    if (o1 <= o2) return locate_walk(g, q, hint[0], hint[2], p0, p2, ids, w, coop, budget);
+    return locate_walk(g, q, hint[1], hint[0], p1, p0, ids, w, coop, budget);
 }
 
 // ---------------------------------------------------------------------------------------------- hull pre-filter

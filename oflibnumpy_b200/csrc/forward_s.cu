@@ -23,6 +23,8 @@
 //
 // Deviation left: cells whose four corners are co-circular to within rounding have no unique Delaunay
 // diagonal (similarity transforms of the pixel grid); Qhull's pick there is an artefact of its facet merging.
+#include <algorithm>
+
 #include "ofk_common.cuh"
 #include "forward_irregular.cuh"
 
@@ -82,14 +84,11 @@ __device__ __forceinline__ double edge_fn(const P2& u, int iu, const P2& v, int 
     return -((u.x - v.x) * (qy - v.y) - (u.y - v.y) * (qx - v.x));
 }
 
-__global__ void __launch_bounds__(256, 4) fwd_scatter(const float* __restrict__ flow, float sign,
-                                                   const uint8_t* __restrict__ point_mask,
-                                                   unsigned int* __restrict__ winner, int H, int W,
-                                                   const int* __restrict__ folded) {
-    const int j = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int i = blockIdx.y * 8 + (threadIdx.x >> 5);
-    const int n = blockIdx.z;
-    if (!folded[n]) return;
+__device__ __forceinline__ void scatter_tile(const float* __restrict__ flow, float sign,
+                                             const uint8_t* __restrict__ point_mask,
+                                             unsigned int* __restrict__ winner, int H, int W, int bx, int by, int n) {
+    const int j = bx * 32 + (threadIdx.x & 31);
+    const int i = by * 8 + (threadIdx.x >> 5);
     if (i >= H - 1 || j >= W - 1) return;
     const size_t fbase = (size_t)n * H * W;
     const float2* fl = reinterpret_cast<const float2*>(flow) + fbase;
@@ -136,17 +135,26 @@ __global__ void __launch_bounds__(256, 4) fwd_scatter(const float* __restrict__ 
     }
 }
 
-__global__ void __launch_bounds__(256) fwd_gather(const float* __restrict__ payload, int C,
-                                                  const float* __restrict__ flow, float sign,
-                                                  const uint8_t* __restrict__ payload_mask,
-                                                  const unsigned int* __restrict__ winner, float* __restrict__ out,
-                                                  uint8_t* __restrict__ out_mask, int rule, int H, int W,
-                                                  unsigned long long inv_w /* ceil(2^64 / W) */,
-                                                  const int* __restrict__ folded) {
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    const int n = blockIdx.z;
+// The resolve kernels run on small grids that loop over the tiles of the frames flagged as folded: for every other
+// frame (the normal case) a launch costs a few hundred empty CTAs instead of one per tile.
+__global__ void __launch_bounds__(256, 4) fwd_scatter(const float* __restrict__ flow, float sign,
+                                                   const uint8_t* __restrict__ point_mask,
+                                                   unsigned int* __restrict__ winner, int H, int W,
+                                                   const int* __restrict__ folded) {
+    const int n = blockIdx.y;
     if (!folded[n]) return;
+    const int tx = (W - 1 + 31) / 32, ty = (H - 1 + 7) / 8;
+    for (int t = blockIdx.x; t < tx * ty; t += gridDim.x) scatter_tile(flow, sign, point_mask, winner, H, W, t % tx, t / tx, n);
+}
+
+__device__ __forceinline__ void gather_tile(const float* __restrict__ payload, int C,
+                                            const float* __restrict__ flow, float sign,
+                                            const uint8_t* __restrict__ payload_mask,
+                                            const unsigned int* __restrict__ winner, float* __restrict__ out,
+                                            uint8_t* __restrict__ out_mask, int rule, int H, int W,
+                                            unsigned long long inv_w /* ceil(2^64 / W) */, int bx, int by, int n) {
+    const int x = bx * 32 + (threadIdx.x & 31);
+    const int y = by * 8 + (threadIdx.x >> 5);
     if (x >= W || y >= H) return;
     const size_t fbase = (size_t)n * H * W;
     const int pix = y * W + x;
@@ -198,13 +206,25 @@ __global__ void __launch_bounds__(256) fwd_gather(const float* __restrict__ payl
 }
 
 
+__global__ void __launch_bounds__(256) fwd_gather(const float* __restrict__ payload, int C,
+                                                  const float* __restrict__ flow, float sign,
+                                                  const uint8_t* __restrict__ payload_mask,
+                                                  const unsigned int* __restrict__ winner, float* __restrict__ out,
+                                                  uint8_t* __restrict__ out_mask, int rule, int H, int W,
+                                                  unsigned long long inv_w, const int* __restrict__ folded) {
+    const int n = blockIdx.y;
+    if (!folded[n]) return;
+    const int tx = (W + 31) / 32, ty = (H + 7) / 8;
+    for (int t = blockIdx.x; t < tx * ty; t += gridDim.x)
+        gather_tile(payload, C, flow, sign, payload_mask, winner, out, out_mask, rule, H, W, inv_w, t % tx, t / tx, n);
+}
+
 __global__ void __launch_bounds__(256) fwd_clear(unsigned int* __restrict__ winner, size_t frame_px,
                                                  const int* __restrict__ folded) {
     const int n = blockIdx.y;
     if (!folded[n]) return;
-    const size_t t = ((size_t)blockIdx.x * 256 + threadIdx.x) * 4;
-    for (int k = 0; k < 4; ++k)
-        if (t + k < frame_px) winner[(size_t)n * frame_px + t + k] = 0u;
+    for (size_t t = (size_t)blockIdx.x * 256 + threadIdx.x; t < frame_px; t += (size_t)gridDim.x * 256)
+        winner[(size_t)n * frame_px + t] = 0u;
 }
 
 }  // namespace legacy
@@ -215,7 +235,8 @@ namespace ofk {
 namespace fwdk {
 using namespace fwd;
 
-__device__ unsigned long long g_stats[4];   // located, outside (by search), failed walks, rejected by the hull filter
+__device__ unsigned long long g_stats[8];   // located, outside (by search), failed walks, rejected by the hull filter,
+                                            // pixels handed to the pocket pass, its work items
 
 constexpr int TW = 64, TH = 16, SW = TW + 1, SH = TH + 1, NV = SW * SH;
 constexpr uint8_t UNCOVERED = 0xFF;
@@ -263,56 +284,223 @@ struct EmitDev {
     }
 };
 
+// ---- float32 helpers of the raster kernel (filters only: every decision they cannot take with a safety margin is
+// ---- taken by the float64 predicates of forward_geom.cuh, so the result is the one of the host build)
+__device__ __forceinline__ float edgef(const float2& u, const float2& v, float qx, float qy) {
+    return (v.x - u.x) * (qy - u.y) - (v.y - u.y) * (qx - u.x);
+}
+__device__ __forceinline__ float orientf(const float2& a, const float2& b, const float2& c) {
+    return (b.x - a.x) * (c.y - a.y) - (b.y - a.y) * (c.x - a.x);
+}
+// round-to-nearest integer of |v| < 2^22 without the conversion pipe
+__device__ __forceinline__ int rint_magic(float v) { return __float_as_int(v + 12582912.0f) - 0x4B400000; }
+__device__ __forceinline__ float int_to_float_magic(int i) { return __int_as_float(i + 0x4B400000) - 12582912.0f; }
+__device__ __forceinline__ int floor_magic(float v) {
+    const int r = rint_magic(v);
+    return r - (int_to_float_magic(r) > v ? 1 : 0);
+}
+__device__ __forceinline__ int ceil_magic(float v) {
+    const int r = rint_magic(v);
+    return r + (int_to_float_magic(r) < v ? 1 : 0);
+}
+
+constexpr int QCAP = 256;          // candidate ring per warp (records), power of two
+constexpr int REC_OK = 1 << 15;    // record flag: the cell is a positively oriented convex quadrilateral (float32 proof)
+
+// Tile kernel. Phase 1 (one thread per cell column, rows of the warp's strip in turn): float32 bounding box of the
+// displaced cell -> the candidate pixels (1.3 per cell for rotation-like fields) go into the warp's ring; a folded cell
+// sets the frame's flag. Phase 2 (whenever 32 candidates are queued): one candidate per lane -- float32 edge functions
+// reject or accept it (exact float64 evaluation only inside a rounding margin), the Delaunay diagonal by the float64
+// in-circle determinant, weights and payload in float64. Without the queue the 1..4 candidates of a cell are a
+// divergent loop that runs its longest trip count on every warp (measured: 765 thread instructions per pixel).
 template <int CT>
 __global__ void __launch_bounds__(256) fwd_raster_kernel(const RasterArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int PC = CT > 0 ? CT : 0;
     P2* s_pos = reinterpret_cast<P2*>(smem);
-    float* s_pay = reinterpret_cast<float*>(s_pos + NV);
-    uint8_t* s_pm = reinterpret_cast<uint8_t*>(s_pay + NV * PC);
+    float2* s_posf = reinterpret_cast<float2*>(s_pos + NV);
+    float* s_pay = reinterpret_cast<float*>(s_posf + NV);
+    uint2* s_q = reinterpret_cast<uint2*>(s_pay + NV * PC + ((NV * PC) & 1));
+    uint8_t* s_pm = reinterpret_cast<uint8_t*>(s_q + 8 * QCAP);
     uint8_t* s_pt = s_pm + NV;
     const int n = blockIdx.z, i0 = blockIdx.y * TH, j0 = blockIdx.x * TW;
     const size_t frame = (size_t)n * A.H * A.W;
     const float2* fl = reinterpret_cast<const float2*>(A.flow) + frame;
+    // pixel origin of the tile's local float32 coordinates: the displaced centre vertex
+    int ox, oy;
+    {
+        const int gi = min(i0 + TH / 2, A.H - 1), gj = min(j0 + TW / 2, A.W - 1);
+        const float2 f = __ldg(fl + (size_t)gi * A.W + gj);
+        const P2 pc = displaced(f.x, f.y, gi, gj, A.sign);
+        ox = (int)fmin(fmax(rint(pc.x), -1048576.0), 1048576.0);
+        oy = (int)fmin(fmax(rint(pc.y), -1048576.0), 1048576.0);
+    }
     for (int v = threadIdx.x; v < NV; v += 256) {
         const int r = v / SW, c = v - r * SW;
         const int gi = min(i0 + r, A.H - 1), gj = min(j0 + c, A.W - 1);
         const size_t g = (size_t)gi * A.W + gj;
         const float2 f = __ldg(fl + g);
-        s_pos[v] = displaced(f.x, f.y, gi, gj, A.sign);
+        const P2 p = displaced(f.x, f.y, gi, gj, A.sign);
+        s_pos[v] = p;
+        s_posf[v] = make_float2((float)(p.x - (double)ox), (float)(p.y - (double)oy));
 #pragma unroll
         for (int k = 0; k < PC; ++k) s_pay[v * PC + k] = __ldg(A.payload + (frame + g) * PC + k);
         s_pm[v] = A.payload_mask ? A.payload_mask[frame + g] : (uint8_t)1;
         s_pt[v] = A.point_mask ? A.point_mask[frame + g] : (uint8_t)1;
     }
     __syncthreads();
-    const int jl = threadIdx.x & (TW - 1), strip = threadIdx.x / TW;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // warp w: columns (w & 1) * 32 .. + 31, rows (w >> 1) * 4 .. + 3 of the tile
+    const int jl = (warp & 1) * 32 + lane, ilbase = (warp >> 1) * (TH / 4);
     const int gj = j0 + jl;
-    if (gj >= A.W - 1) return;
-    constexpr int ROWS = TH / (256 / TW);
-    int il = strip * ROWS;
-    P2 a = s_pos[il * SW + jl], b = s_pos[il * SW + jl + 1];
-    bool vab = s_pt[il * SW + jl] && s_pt[il * SW + jl + 1];
-    for (int k = 0; k < ROWS; ++k, ++il) {
-        const int gi = i0 + il;
-        if (gi >= A.H - 1) break;
-        const int sb = il * SW + jl;
-        const P2 c = s_pos[sb + SW], d = s_pos[sb + SW + 1];
-        const bool vcd = s_pt[sb + SW] && s_pt[sb + SW + 1];
-        if (vab && vcd) {
-            double area2[2];
-            const int diag = cell_diagonal(a, b, c, d, area2, A.flip_tol);
-            if (diag < 0) {
-                A.folded[n] = 1;
+    uint2* q = s_q + warp * QCAP;
+    unsigned head = 0, tail = 0;
+    const float lxmin = (float)(0 - ox), lxmax = (float)(A.W - 1 - ox), lymin = (float)(0 - oy),
+                lymax = (float)(A.H - 1 - oy);
+
+    // ---------------------------------------------------------------- phase 2: one queued candidate per lane
+    auto drain = [&](unsigned count) {
+        const bool have = lane < count;
+        const uint2 rec = have ? q[(head + lane) & (QCAP - 1)] : make_uint2(0u, 0u);
+        head += count;
+        if (!have) return;
+        const int sb = rec.x & 0x7fff;
+        const bool convex_ok = (rec.x & REC_OK) != 0;
+        const int x = rec.y & 0xffff, y = rec.y >> 16;
+        const float qxf = int_to_float_magic(x - ox), qyf = int_to_float_magic(y - oy);
+        const float2 af = s_posf[sb], bf = s_posf[sb + 1], cf = s_posf[sb + SW], df = s_posf[sb + SW + 1];
+        const float fab = edgef(af, bf, qxf, qyf), fbd = edgef(bf, df, qxf, qyf), fcd = edgef(cf, df, qxf, qyf),
+                    fac = edgef(af, cf, qxf, qyf);
+        // rounding margin of a float32 edge function: positions carry half an ulp of their magnitude
+        const float mag = fmaxf(fmaxf(fabsf(af.x), fabsf(af.y)), fmaxf(fabsf(df.x), fabsf(df.y))) + 4.0f;
+        const float ext = fabsf(df.x - af.x) + fabsf(df.y - af.y) + fabsf(bf.x - cf.x) + fabsf(bf.y - cf.y) + 2.0f;
+        const float m = 1e-6f * mag * ext;
+        bool decided = convex_ok && fabsf(fab) > m && fabsf(fbd) > m && fabsf(fcd) > m && fabsf(fac) > m;
+        if (decided && !(fab > 0 && fbd > 0 && fcd < 0 && fac < 0)) return;   // outside the cell
+        const P2 a = s_pos[sb], b = s_pos[sb + 1], c = s_pos[sb + SW], d = s_pos[sb + SW + 1];
+        const double qx = (double)x, qy = (double)y;
+        int diag, tri;
+        double area2;
+        if (convex_ok) {
+            const double ic = incircle(a, b, d, c);
+            diag = ic > 0 ? 1 : 0;
+            if (fabs(ic) <= A.flip_tol) diag ^= 1;
+            const float fdg = diag == 0 ? edgef(af, df, qxf, qyf) : edgef(bf, cf, qxf, qyf);
+            decided = decided && fabsf(fdg) > m;
+            if (decided) {
+                tri = diag == 0 ? (fdg < 0 ? 0 : 1) : (fdg > 0 ? 0 : 1);
             } else {
-                EmitDev<CT> e{A, s_pay, s_pm, sb, frame, gi, gj};
-                raster_cell(a, b, c, d, diag, area2, A.W, A.H, e);
+                tri = owner_triangle(a, b, c, d, diag, qx, qy);
+                if (tri < 0) return;
+            }
+            area2 = diag == 0 ? (tri == 0 ? orient(a, b, d) : orient(a, d, c))
+                              : (tri == 0 ? orient(a, b, c) : orient(b, d, c));
+        } else {
+            double ar[2];
+            diag = cell_diagonal(a, b, c, d, ar, A.flip_tol);
+            if (diag < 0) return;   // folded: the frame is redone by the resolve kernels
+            tri = owner_triangle(a, b, c, d, diag, qx, qy);
+            if (tri < 0) return;
+            area2 = ar[tri];
+        }
+        int k[3];
+        double w[3];
+        triangle_weights(a, b, c, d, diag, tri, area2, qx, qy, k, w);
+        const int v0 = sb + (k[0] >> 1) * SW + (k[0] & 1), v1 = sb + (k[1] >> 1) * SW + (k[1] & 1),
+                  v2 = sb + (k[2] >> 1) * SW + (k[2] & 1);
+        const size_t px = frame + (size_t)y * A.W + x;
+        const bool m0 = s_pm[v0] != 0, m1 = s_pm[v1] != 0, m2 = s_pm[v2] != 0;
+        if (CT >= 0) {
+            interp_store(s_pay + v0 * PC, s_pay + v1 * PC, s_pay + v2 * PC, m0, m1, m2, w[0], w[1], w[2], PC,
+                         A.out + px * PC, A.out_mask ? A.out_mask + px : nullptr, A.rule_strict);
+        } else {
+            const int il = sb / SW, jc = sb - il * SW;
+            const size_t ga = frame + (size_t)(i0 + il) * A.W + j0 + jc;
+            const size_t g0 = ga + (size_t)(k[0] >> 1) * A.W + (k[0] & 1), g1 = ga + (size_t)(k[1] >> 1) * A.W + (k[1] & 1),
+                         g2 = ga + (size_t)(k[2] >> 1) * A.W + (k[2] & 1);
+            interp_store(A.payload + g0 * A.C, A.payload + g1 * A.C, A.payload + g2 * A.C, m0, m1, m2, w[0], w[1], w[2],
+                         A.C, A.out + px * A.C, A.out_mask ? A.out_mask + px : nullptr, A.rule_strict);
+        }
+        if (A.out_mask == nullptr) A.cover[px] = 1;
+    };
+
+    // ---------------------------------------------------------------- phase 1: cells -> candidates
+    const bool col_ok = gj < A.W - 1;
+    int il = ilbase;
+    float2 af = s_posf[il * SW + jl], bf = s_posf[il * SW + jl + 1];
+    bool vab = s_pt[il * SW + jl] && s_pt[il * SW + jl + 1];
+    for (int kr = 0; kr < TH / 4; ++kr, ++il) {
+        const int sb = il * SW + jl;
+        const float2 cf = s_posf[sb + SW], df = s_posf[sb + SW + 1];
+        const bool vcd = s_pt[sb + SW] && s_pt[sb + SW + 1];
+        int ncand = 0, x0 = 0, y0 = 0, nx = 1;
+        unsigned flag = 0;
+        if (col_ok && i0 + il < A.H - 1 && vab && vcd) {
+            float xlo = fminf(fminf(af.x, bf.x), fminf(cf.x, df.x)), xhi = fmaxf(fmaxf(af.x, bf.x), fmaxf(cf.x, df.x));
+            float ylo = fminf(fminf(af.y, bf.y), fminf(cf.y, df.y)), yhi = fmaxf(fmaxf(af.y, bf.y), fmaxf(cf.y, df.y));
+            const float mag = fmaxf(fmaxf(fabsf(xlo), fabsf(xhi)), fmaxf(fabsf(ylo), fabsf(yhi)));
+            const float eps = mag * 2.4e-7f + 1e-6f;        // the float32 positions are within half an ulp
+            const float ext = (xhi - xlo) + (yhi - ylo) + 1.0f;
+            xlo = fmaxf(xlo - eps, lxmin - 1.0f);
+            xhi = fminf(xhi + eps, lxmax + 1.0f);
+            ylo = fmaxf(ylo - eps, lymin - 1.0f);
+            yhi = fminf(yhi + eps, lymax + 1.0f);
+            if (xlo <= xhi && ylo <= yhi) {
+                x0 = max(ceil_magic(xlo), 0 - ox);
+                y0 = max(ceil_magic(ylo), 0 - oy);
+                const int x1 = min(floor_magic(xhi), A.W - 1 - ox), y1 = min(floor_magic(yhi), A.H - 1 - oy);
+                nx = x1 - x0 + 1;
+                const int ny = y1 - y0 + 1;
+                if (nx > 0 && ny > 0) ncand = nx * ny;
+            }
+            if (ncand > 0) {
+                const float mo = 16.0f * eps * ext;
+                const bool ok = orientf(af, bf, df) > mo && orientf(af, df, cf) > mo && orientf(af, bf, cf) > mo &&
+                                orientf(bf, df, cf) > mo;
+                if (ok) {
+                    flag = REC_OK;
+                } else {
+                    const P2 a = s_pos[sb], b = s_pos[sb + 1], c = s_pos[sb + SW], d = s_pos[sb + SW + 1];
+                    double ar[2];
+                    if (cell_diagonal(a, b, c, d, ar, A.flip_tol) < 0) {
+                        A.folded[n] = 1;
+                        ncand = 0;
+                    }
+                }
+            }
+            if (ncand > 4) {   // a stretched cell: rasterised on the spot by the generic float64 loop
+                const P2 a = s_pos[sb], b = s_pos[sb + 1], c = s_pos[sb + SW], d = s_pos[sb + SW + 1];
+                double ar[2];
+                const int diag = cell_diagonal(a, b, c, d, ar, A.flip_tol);
+                if (diag >= 0) {
+                    EmitDev<CT> e{A, s_pay, s_pm, sb, frame, i0 + il, gj};
+                    raster_cell(a, b, c, d, diag, ar, A.W, A.H, e);
+                }
+                ncand = 0;
             }
         }
-        a = c;
-        b = d;
+        // push: slot s of every cell that has one, compacted over the warp
+        int most = ncand;
+        for (int o = 16; o > 0; o >>= 1) most = max(most, __shfl_xor_sync(0xffffffffu, most, o));
+        for (int sl = 0; sl < most; ++sl) {
+            const bool act = sl < ncand;
+            const unsigned bal = __ballot_sync(0xffffffffu, act);
+            if (act) {
+                const int dy = (sl >= nx) + (sl >= 2 * nx) + (sl >= 3 * nx), dx = sl - dy * nx;
+                const unsigned rank = __popc(bal & ((1u << lane) - 1u));
+                q[(tail + rank) & (QCAP - 1)] =
+                    make_uint2((unsigned)sb | flag, (unsigned)(x0 + dx + ox) | ((unsigned)(y0 + dy + oy) << 16));
+            }
+            tail += __popc(bal);
+        }
+        __syncwarp();
+        while (tail - head >= 32u) drain(32u);
+        __syncwarp();
+        af = cf;
+        bf = df;
         vab = vcd;
     }
+    if (tail != head) drain(tail - head);
 }
 
 // ------------------------------------------------------------------------------------------- boundary sites -> bins
@@ -373,28 +561,69 @@ __global__ void __launch_bounds__(256) irr_sites_kernel(const IrrArgs A) {
     }
 }
 
-// counts -> inclusive end offsets, one CTA per frame; bins[nb] = number of sites
-__global__ void __launch_bounds__(1024) irr_scan_kernel(uint32_t* bins_all, int nb) {
-    uint32_t* a = bins_all + (size_t)blockIdx.x * (nb + 1);
-    const int per = (nb + 1023) / 1024;
-    const int b0 = min(threadIdx.x * per, nb), b1 = min(b0 + per, nb);
+// counts -> inclusive end offsets; bins[nb] = number of sites. Three small launches (chunk sums, scan of the chunk
+// sums, scan inside the chunks): a single CTA per frame took 100 us for the 130 k bins of a 1080p frame.
+constexpr int SCAN_CHUNK = 2048;   // bins per CTA, 8 per thread
+
+__global__ void __launch_bounds__(256) irr_scan_sums_kernel(const uint32_t* bins_all, int nb, uint32_t* chunk_sums,
+                                                            int chunks) {
+    const uint32_t* a = bins_all + (size_t)blockIdx.y * (nb + 1);
+    const int b0 = blockIdx.x * SCAN_CHUNK + threadIdx.x * 8;
     uint32_t sum = 0;
-    for (int b = b0; b < b1; ++b) sum += a[b];
-    __shared__ uint32_t part[1024];
-    part[threadIdx.x] = sum;
+    for (int k = 0; k < 8; ++k)
+        if (b0 + k < nb) sum += a[b0 + k];
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __shared__ uint32_t part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = sum;
     __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-        const uint32_t v = threadIdx.x >= off ? part[threadIdx.x - off] : 0u;
-        __syncthreads();
-        part[threadIdx.x] += v;
-        __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int k = 0; k < 8; ++k) t += part[k];
+        chunk_sums[(size_t)blockIdx.y * chunks + blockIdx.x] = t;
     }
-    uint32_t run = part[threadIdx.x] - sum;
-    for (int b = b0; b < b1; ++b) {
-        run += a[b];
-        a[b] = run;
+}
+
+__global__ void irr_scan_chunks_kernel(uint32_t* chunk_sums, int chunks) {   // exclusive, in place; one warp per frame
+    uint32_t* c = chunk_sums + (size_t)blockIdx.x * chunks;
+    uint32_t carry = 0;
+    for (int base = 0; base < chunks; base += 32) {
+        const int i = base + threadIdx.x;
+        const uint32_t v = i < chunks ? c[i] : 0u;
+        uint32_t inc = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if ((int)threadIdx.x >= o) inc += t;
+        }
+        if (i < chunks) c[i] = carry + inc - v;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
     }
-    if (threadIdx.x == 1023) a[nb] = part[1023];
+}
+
+__global__ void __launch_bounds__(256) irr_scan_final_kernel(uint32_t* bins_all, int nb, const uint32_t* chunk_sums,
+                                                             int chunks) {
+    uint32_t* a = bins_all + (size_t)blockIdx.y * (nb + 1);
+    const int b0 = blockIdx.x * SCAN_CHUNK + threadIdx.x * 8;
+    uint32_t v[8], sum = 0;
+    for (int k = 0; k < 8; ++k) {
+        v[k] = b0 + k < nb ? a[b0 + k] : 0u;
+        sum += v[k];
+    }
+    uint32_t inc = sum;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    __shared__ uint32_t part[8];
+    if (lane == 31) part[warp] = inc;
+    __syncthreads();
+    uint32_t run = chunk_sums[(size_t)blockIdx.y * chunks + blockIdx.x] + inc - sum;
+    for (int k = 0; k < warp; ++k) run += part[k];
+    for (int k = 0; k < 8; ++k) {
+        run += v[k];
+        if (b0 + k < nb) a[b0 + k] = run;
+    }
+    if (blockIdx.x == chunks - 1 && threadIdx.x == 255) a[nb] = run;
 }
 
 // ------------------------------------------------------------------------------------------------- hull pre-filter
@@ -515,24 +744,95 @@ struct SolveArgs {
     float* out;
     uint8_t* out_mask;
     const uint8_t* cover;
+    unsigned long long* heavy;       // work items of the pocket pass: frame << 40 | 8-pixel block << 8 | pixel bits
+    unsigned int* heavy_count;
     float sign;
     int C, rule_strict, H, W, nbx, nby, ncx, ncy;
 };
 
+constexpr int SOLVE_SPAN = 4096;          // pixels per CTA, 16 per thread
+constexpr int THREAD_BUDGET = 320;        // sites one thread looks at per apex search before the pixel goes to a warp
+
+__device__ __forceinline__ void solve_store(const SolveArgs& A, size_t frame, uint32_t p, int st, const uint32_t (&vid)[3],
+                                            const double (&w)[3]) {
+    const size_t px = frame + p;
+    if (st == LOC_FOUND) {
+        const uint8_t* pm = A.payload_mask ? A.payload_mask + frame : nullptr;
+        const float* pay = A.payload + frame * A.C;
+        interp_store(pay + (size_t)vid[0] * A.C, pay + (size_t)vid[1] * A.C, pay + (size_t)vid[2] * A.C,
+                     pm ? pm[vid[0]] != 0 : true, pm ? pm[vid[1]] != 0 : true, pm ? pm[vid[2]] != 0 : true, w[0], w[1],
+                     w[2], A.C, A.out + px * A.C, A.out_mask ? A.out_mask + px : nullptr, A.rule_strict);
+    } else {
+        for (int c = 0; c < A.C; ++c) A.out[px * A.C + c] = 0.f;
+        if (A.out_mask) A.out_mask[px] = 0;
+    }
+}
+
+// A CTA reads the marker bytes of a span of 4096 pixels (16 bytes per thread) and lists the uncovered ones in shared
+// memory, then works through the list one pixel per thread (the searches are long and the uncovered pixels scattered:
+// with 2 % of the points removed 8 % of the pixels are bridged; pixel-to-lane mapping would leave most lanes idle). A
+// search that looks at more than THREAD_BUDGET sites is abandoned: these are the pixels of hull pockets, whose long
+// thin triangles have circles that graze hundreds of border points. They are handed, in blocks of 8 neighbouring
+// pixels, to irr_heavy_kernel.
 __global__ void __launch_bounds__(256) irr_solve_kernel(const SolveArgs A) {
-    const int n = blockIdx.z;
+    const int n = blockIdx.y;
     if (A.folded[n]) return;
     __shared__ HullInfo s_hull;
+    __shared__ uint32_t s_list[SOLVE_SPAN];
+    __shared__ uint32_t s_blocks[SOLVE_SPAN / 8];
+    __shared__ uint32_t s_warp[8];
+    const size_t frame_px = (size_t)A.H * A.W, frame = (size_t)n * frame_px;
+    const size_t p0 = (size_t)blockIdx.x * SOLVE_SPAN + (size_t)threadIdx.x * 16;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t hits[4] = {0, 0, 0, 0};
+    int mine = 0;
+    for (int b = threadIdx.x; b < SOLVE_SPAN / 8; b += 256) s_blocks[b] = 0;
+    if (p0 < frame_px) {
+        const uint8_t* cv = A.cover + frame + p0;
+        uint32_t wds[4];
+        if (p0 + 16 <= frame_px && (reinterpret_cast<uintptr_t>(cv) & 15) == 0) {
+            const uint4 v = *reinterpret_cast<const uint4*>(cv);
+            wds[0] = v.x; wds[1] = v.y; wds[2] = v.z; wds[3] = v.w;
+        } else {
+            for (int k = 0; k < 4; ++k) {
+                wds[k] = 0;
+                for (int b = 0; b < 4; ++b)
+                    if (p0 + 4 * k + b < frame_px) wds[k] |= (uint32_t)cv[4 * k + b] << (8 * b);
+            }
+        }
+        for (int k = 0; k < 4; ++k) {
+            hits[k] = ((wds[k] & 0x7f7f7f7fu) + 0x01010101u) & wds[k] & 0x80808080u;   // bytes equal to 0xFF
+            mine += __popc(hits[k]);
+        }
+    }
+    // ordered compaction: exclusive scan of the per-thread counts
+    int inc = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = (uint32_t)inc;
+    __syncthreads();
+    unsigned count = 0, base = (unsigned)(inc - mine);
+    for (int k = 0; k < 8; ++k) {
+        if (k < warp) base += s_warp[k];
+        count += s_warp[k];
+    }
+    if (count == 0) return;
+    for (int k = 0; k < 4; ++k) {
+        uint32_t hit = hits[k];
+        while (hit) {
+            const int b = (__ffs(hit) - 1) >> 3;
+            hit &= hit - 1;
+            s_list[base++] = (uint32_t)(p0 + 4 * k + b);
+        }
+    }
     {
         const int words = sizeof(HullInfo) / 4;
         const uint32_t* src = reinterpret_cast<const uint32_t*>(A.info + n);
         for (int k = threadIdx.x; k < words; k += 256) reinterpret_cast<uint32_t*>(&s_hull)[k] = src[k];
     }
     __syncthreads();
-    const int y = blockIdx.y;
-    const size_t frame = (size_t)n * A.H * A.W;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int xbase = (blockIdx.x * 8 + warp) * 128;
     SiteGrid g;
     g.H = A.H;
     g.W = A.W;
@@ -546,11 +846,12 @@ __global__ void __launch_bounds__(256) irr_solve_kernel(const SolveArgs A) {
     g.sites = A.sites + frame;
     g.flow = A.flow + 2 * frame;
     g.sign = A.sign;
-    for (int k = 0; k < 4; ++k) {
-        const int x = xbase + k * 32 + lane;
-        if (x >= A.W) break;
-        const size_t px = frame + (size_t)y * A.W + x;
-        if (A.cover[px] != UNCOVERED) continue;
+    unsigned long long tally[4] = {0, 0, 0, 0};
+    bool any_heavy = false;
+    // ---- pass 1: one pixel per thread
+    for (unsigned e = threadIdx.x; e < count; e += 256) {
+        const uint32_t p = s_list[e];
+        const int y = (int)(p / (uint32_t)A.W), x = (int)(p - (uint32_t)y * (uint32_t)A.W);
         P2 q;
         q.x = x;
         q.y = y;
@@ -559,27 +860,101 @@ __global__ void __launch_bounds__(256) irr_solve_kernel(const SolveArgs A) {
         int st;
         if (hull_rejects(s_hull, q)) {
             st = LOC_OUTSIDE;
-            atomicAdd(&g_stats[3], 1ull);
+            ++tally[3];
         } else {
-            st = locate(g, q, vid, w);
-            atomicAdd(&g_stats[st == LOC_FOUND ? 0 : (st == LOC_OUTSIDE ? 1 : 2)], 1ull);
+            st = locate(g, q, vid, w, Coop{0, 1}, THREAD_BUDGET);
+            if (st == LOC_HEAVY) {
+                atomicOr(&s_blocks[(p >> 3) - blockIdx.x * (SOLVE_SPAN / 8)], 1u << (p & 7));
+                any_heavy = true;
+                continue;
+            }
+            ++tally[st == LOC_FOUND ? 0 : (st == LOC_OUTSIDE ? 1 : 2)];
         }
-        if (st == LOC_FOUND) {
-            const uint8_t* pm = A.payload_mask ? A.payload_mask + frame : nullptr;
-            const float* pay = A.payload + frame * A.C;
-            interp_store(pay + (size_t)vid[0] * A.C, pay + (size_t)vid[1] * A.C, pay + (size_t)vid[2] * A.C,
-                         pm ? pm[vid[0]] != 0 : true, pm ? pm[vid[1]] != 0 : true, pm ? pm[vid[2]] != 0 : true, w[0],
-                         w[1], w[2], A.C, A.out + px * A.C, A.out_mask ? A.out_mask + px : nullptr, A.rule_strict);
-        } else {
-            for (int c = 0; c < A.C; ++c) A.out[px * A.C + c] = 0.f;
-            if (A.out_mask) A.out_mask[px] = 0;
+        solve_store(A, frame, p, st, vid, w);
+    }
+    // ---- the abandoned searches become work items of the pocket pass
+    if (__syncthreads_or(any_heavy ? 1 : 0)) {
+        for (unsigned b = threadIdx.x; b < SOLVE_SPAN / 8; b += 256) {
+            const uint32_t bits = s_blocks[b];
+            if (bits == 0) continue;
+            const unsigned slot = atomicAdd(A.heavy_count, 1u);
+            A.heavy[slot] = ((unsigned long long)n << 40) |
+                            ((unsigned long long)(blockIdx.x * (SOLVE_SPAN / 8) + b) << 8) | bits;
         }
+    }
+    for (int k = 0; k < 4; ++k)
+        if (tally[k]) atomicAdd(&g_stats[k], tally[k]);
+}
+
+// The pocket pass: one warp per work item (up to 8 neighbouring pixels of a row), all 32 lanes scanning the bins of
+// every search. The first pixel of a block is located from scratch, the others start from the triangle of their left
+// neighbour: a walk from the nearest site crosses dozens of the fan triangles that fill a pocket, from the neighbouring
+// pixel's triangle one or two. Items are independent of each other and of the order they were queued in.
+__global__ void __launch_bounds__(256) irr_heavy_kernel(const SolveArgs A) {
+    const unsigned count = *A.heavy_count;
+    const int lane = threadIdx.x & 31;
+    const unsigned nwarps = gridDim.x * 8, gwarp = blockIdx.x * 8 + (threadIdx.x >> 5);
+    unsigned long long tally[5] = {0, 0, 0, 0, 0};
+    for (unsigned it = gwarp; it < count; it += nwarps) {
+        ++tally[4];
+        const unsigned long long item = A.heavy[it];
+        const int n = (int)(item >> 40);
+        const uint32_t block = (uint32_t)((item >> 8) & 0xffffffffu), bits = (uint32_t)(item & 0xffu);
+        const size_t frame = (size_t)n * A.H * A.W;
+        SiteGrid g;
+        g.H = A.H;
+        g.W = A.W;
+        g.nbx = A.nbx;
+        g.nby = A.nby;
+        g.ncx = A.ncx;
+        g.ncy = A.ncy;
+        const int nb = A.nbx * A.nby;
+        g.bin_start = A.bins + (size_t)n * (nb + 1);
+        g.coarse = A.coarse + (size_t)n * A.ncx * A.ncy;
+        g.sites = A.sites + frame;
+        g.flow = A.flow + 2 * frame;
+        g.sign = A.sign;
+        uint32_t hint[3] = {0, 0, 0};
+        bool have_hint = false;
+        for (int k = 0; k < 8; ++k) {
+            if (!((bits >> k) & 1u)) {
+                have_hint = false;
+                continue;
+            }
+            const uint32_t p = block * 8 + k;
+            const int y = (int)(p / (uint32_t)A.W), x = (int)(p - (uint32_t)y * (uint32_t)A.W);
+            P2 q;
+            q.x = x;
+            q.y = y;
+            uint32_t vid[3];
+            double w[3];
+            const Coop coop{lane, 32};
+            const int st = (have_hint && x > 0) ? locate_hinted(g, q, hint, vid, w, coop, NO_BUDGET)
+                                                : locate(g, q, vid, w, coop, NO_BUDGET);
+            have_hint = st == LOC_FOUND;
+            if (have_hint) {
+                hint[0] = vid[0];
+                hint[1] = vid[1];
+                hint[2] = vid[2];
+            }
+            if (lane == 0) {
+                ++tally[st == LOC_FOUND ? 0 : (st == LOC_OUTSIDE ? 1 : 2)];
+                ++tally[3];
+                solve_store(A, frame, p, st, vid, w);
+            }
+        }
+    }
+    if (lane == 0) {
+        for (int k = 0; k < 3; ++k)
+            if (tally[k]) atomicAdd(&g_stats[k], tally[k]);
+        if (tally[3]) atomicAdd(&g_stats[4], tally[3]);
+        if (tally[4]) atomicAdd(&g_stats[5], tally[4]);
     }
 }
 
 // ------------------------------------------------------------------------------------------------- workspace layout
 struct WsLayout {
-    size_t sites, cover, bins, coarse, hullws, hullinfo, folded, total;
+    size_t sites, cover, heavy, heavy_count, bins, coarse, hullws, hullinfo, folded, chunks, total;
     size_t zero_begin, zero_bytes;   // region cleared before every call (bins, coarse, hull keys, folded flags)
     int nbx, nby, ncx, ncy, nb, nc;
 };
@@ -600,6 +975,8 @@ static WsLayout ws_layout(int N, int H, int W) {
     o = align_up(o + px * 4, 256);
     L.cover = o;
     o = align_up(o + px, 256);
+    L.heavy = o;            // at most one item per 8 pixels
+    o = align_up(o + px + 8, 256);
     L.hullinfo = o;
     o = align_up(o + (size_t)N * sizeof(HullInfo), 256);
     L.zero_begin = o;
@@ -611,6 +988,10 @@ static WsLayout ws_layout(int N, int H, int W) {
     o = align_up(o + (size_t)N * sizeof(HullWs), 256);
     L.folded = o;
     o = align_up(o + (size_t)N * 4, 256);
+    L.chunks = o;
+    o = align_up(o + (size_t)N * ((L.nb + SCAN_CHUNK - 1) / SCAN_CHUNK) * 4, 256);
+    L.heavy_count = o;
+    o = align_up(o + 4, 256);
     L.zero_bytes = o - L.zero_begin;
     L.total = o;
     return L;
@@ -622,9 +1003,16 @@ __global__ void hull_ws_init_kernel(HullWs* ws, int N) {
 }
 
 unsigned long long stat(int which) {
-    unsigned long long v[4] = {0, 0, 0, 0};
+#if defined(OFK_FWD_INSTR)
+    if (which >= 8 && which < 16) {
+        unsigned long long c[8];
+        if (cudaMemcpyFromSymbol(c, fwd::g_instr, sizeof(c)) != cudaSuccess) cudaGetLastError();
+        return c[which - 8];
+    }
+#endif
+    unsigned long long v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (cudaMemcpyFromSymbol(v, g_stats, sizeof(v)) != cudaSuccess) cudaGetLastError();
-    return which >= 0 && which < 4 ? v[which] : 0ull;
+    return which >= 0 && which < 8 ? v[which] : 0ull;
 }
 
 }  // namespace fwdk
@@ -651,7 +1039,9 @@ template <int CT>
 static void launch_raster(const fwdk::RasterArgs& A, int N, cudaStream_t st) {
     using namespace fwdk;
     constexpr int PC = CT > 0 ? CT : 0;
-    const size_t smem = (size_t)NV * (sizeof(fwd::P2) + 4 * PC + 2);
+    const size_t smem = (size_t)NV * (sizeof(fwd::P2) + 8 + 2) + 4 * (size_t)(NV * PC + ((NV * PC) & 1)) + 8 * QCAP * 8;
+    // > 48 KB of dynamic shared memory needs the opt-in (per device)
+    cudaFuncSetAttribute(fwd_raster_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     dim3 grid((A.W - 1 + TW - 1) / TW, (A.H - 1 + TH - 1) / TH, N);
     fwd_raster_kernel<CT><<<grid, 256, smem, st>>>(A);
 }
@@ -668,7 +1058,7 @@ extern "C" int ofk_forward_s(const float* payload, int C, const float* flow, flo
     OFK_CHECK_ARG(mask_rule == OFK_RULE_STRICT || mask_rule == OFK_RULE_GT_HALF,
                   "ofk_forward_s: mask rule must be STRICT or GT_HALF");
     OFK_CHECK_ARG((size_t)H * W < ((size_t)1 << 29), "ofk_forward_s: frame too large for 32-bit triangle ids");
-    OFK_CHECK_ARG(H <= 65535, "ofk_forward_s: H=%d exceeds 65535", H);
+    OFK_CHECK_ARG(H <= 65535 && W <= 65535, "ofk_forward_s: H=%d / W=%d exceed 65535", H, W);
     OFK_CHECK_ARG((reinterpret_cast<uintptr_t>(flow) & 7) == 0, "ofk_forward_s: flow must be 8-byte aligned");
     if (N == 0) return OFK_OK;
     OFK_CHECK_ARG(N <= 65535, "ofk_forward_s: N=%d exceeds 65535", N);
@@ -714,7 +1104,13 @@ extern "C" int ofk_forward_s(const float* payload, int C, const float* flow, flo
     dim3 sgrid((unsigned)((cand + 255) / 256), N);
     irr_sites_kernel<0><<<sgrid, 256, 0, st>>>(I);
     OFK_LAUNCHED();
-    irr_scan_kernel<<<N, 1024, 0, st>>>(d_bins, L.nb);
+    const int chunks = (L.nb + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    uint32_t* d_chunks = reinterpret_cast<uint32_t*>(base + L.chunks);
+    irr_scan_sums_kernel<<<dim3(chunks, N), 256, 0, st>>>(d_bins, L.nb, d_chunks, chunks);
+    OFK_LAUNCHED();
+    irr_scan_chunks_kernel<<<N, 32, 0, st>>>(d_chunks, chunks);
+    OFK_LAUNCHED();
+    irr_scan_final_kernel<<<dim3(chunks, N), 256, 0, st>>>(d_bins, L.nb, d_chunks, chunks);
     OFK_LAUNCHED();
     irr_sites_kernel<1><<<sgrid, 256, 0, st>>>(I);
     OFK_LAUNCHED();
@@ -747,23 +1143,26 @@ extern "C" int ofk_forward_s(const float* payload, int C, const float* flow, flo
     OFK_LAUNCHED();
 
     SolveArgs S{payload, flow, payload_mask, d_folded, d_bins, d_coarse, d_sites, d_info, out, out_mask, d_cover,
-                flow_sign, C, strict, H, W, L.nbx, L.nby, L.ncx, L.ncy};
-    dim3 vgrid((W + 1023) / 1024, H, N);
+                reinterpret_cast<unsigned long long*>(base + L.heavy),
+                reinterpret_cast<unsigned int*>(base + L.heavy_count), flow_sign, C, strict, H, W, L.nbx, L.nby, L.ncx,
+                L.ncy};
+    dim3 vgrid((unsigned)(((size_t)H * W + SOLVE_SPAN - 1) / SOLVE_SPAN), N);
     irr_solve_kernel<<<vgrid, 256, 0, st>>>(S);
+    OFK_LAUNCHED();
+    irr_heavy_kernel<<<sm_count() * 4, 256, 0, st>>>(S);
     OFK_LAUNCHED();
 
     // ---- folding frames: redone by the order-independent resolve (no-ops for all other frames)
     if (H > 1 && W > 1) {
         unsigned int* winner = reinterpret_cast<unsigned int*>(d_sites);
-        dim3 cgrid((unsigned)(((size_t)H * W + 1023) / 1024), N);
-        legacy::fwd_clear<<<cgrid, 256, 0, st>>>(winner, (size_t)H * W, d_folded);
+        const int per_frame = std::max(8, std::min(1184, 4736 / N));   // ~ 8 CTAs per SM over the whole batch
+        dim3 lgrid(per_frame, N);
+        legacy::fwd_clear<<<lgrid, 256, 0, st>>>(winner, (size_t)H * W, d_folded);
         OFK_LAUNCHED();
-        dim3 grid((W - 1 + 31) / 32, (H - 1 + 7) / 8, N);
-        legacy::fwd_scatter<<<grid, 256, 0, st>>>(flow, flow_sign, point_mask, winner, H, W, d_folded);
+        legacy::fwd_scatter<<<lgrid, 256, 0, st>>>(flow, flow_sign, point_mask, winner, H, W, d_folded);
         OFK_LAUNCHED();
-        dim3 ggrid((W + 31) / 32, (H + 7) / 8, N);
         const unsigned long long inv_w = ~0ull / (unsigned long long)W + 1ull;   // ceil(2^64 / W), W >= 2
-        legacy::fwd_gather<<<ggrid, 256, 0, st>>>(payload, C, flow, flow_sign, payload_mask, winner, out, out_mask,
+        legacy::fwd_gather<<<lgrid, 256, 0, st>>>(payload, C, flow, flow_sign, payload_mask, winner, out, out_mask,
                                                  mask_rule, H, W, inv_w, d_folded);
         OFK_LAUNCHED();
     }

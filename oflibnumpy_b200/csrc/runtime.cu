@@ -44,7 +44,7 @@ extern "C" unsigned long long ofk_rt_path_count(int which) {
     if (which >= 0 && which < 4) return g_paths[which].load();
     if (which == 4) return c3_ws_mixed_count();      // synchronous reads of device counters (current device)
     if (which == 5) return warp_ws_mixed_count();
-    if (which >= 6 && which <= 9) return forward_s_stat(which - 6);
+    if (which >= 6 && which <= 21) return forward_s_stat(which - 6);
     return 0ull;
 }
 

@@ -53,6 +53,8 @@ struct EmitHost {
 extern "C" int fwd_hostsim(const float* payload, int C, const float* flow, float sign, const uint8_t* payload_mask,
                            const uint8_t* point_mask, float* out, uint8_t* out_mask, int rule_strict, int H, int W,
                            int use_prefilter, double flip_tol, long long* stats) {
+    const int use_hints = (use_prefilter & 2) != 0;
+    use_prefilter &= 1;
     std::vector<uint8_t> cover((size_t)H * W, 0);
     Frame f{payload, C, flow, sign, payload_mask, point_mask, out, out_mask, rule_strict, H, W, cover.data()};
     memset(stats, 0, 8 * sizeof(long long));
@@ -126,6 +128,8 @@ extern "C" int fwd_hostsim(const float* payload, int C, const float* flow, float
     if (!use_prefilter) hull.m = 0;
     // ---- irregular part
     for (int y = 0; y < H; ++y) {
+        uint32_t hint[3] = {0, 0, 0};
+        int hint_x = -2;
         for (int x = 0; x < W; ++x) {
             const size_t px = (size_t)y * W + x;
             if (cover[px]) continue;
@@ -139,7 +143,11 @@ extern "C" int fwd_hostsim(const float* payload, int C, const float* flow, float
                 st = LOC_OUTSIDE;
                 ++stats[4];
             } else {
-                st = locate(g, q, vid, w);
+                st = (use_hints && hint_x == x - 1) ? locate_hinted(g, q, hint, vid, w) : locate(g, q, vid, w);
+                if (st == LOC_FOUND) {
+                    hint[0] = vid[0]; hint[1] = vid[1]; hint[2] = vid[2];
+                    hint_x = x;
+                }
                 if (st == LOC_OUTSIDE) ++stats[2];
                 if (st == LOC_FAILED) ++stats[3];
                 if (st == LOC_FOUND) ++stats[1];
