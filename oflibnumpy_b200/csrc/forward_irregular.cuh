@@ -443,6 +443,7 @@ struct HullInfo {
     int m;                         // number of polygon vertices (0: no filter)
     int pad_;
     double vx[HULL_DIRS], vy[HULL_DIRS], slack[HULL_DIRS];
+    double la[HULL_DIRS], lb[HULL_DIRS], lc[HULL_DIRS];   // edge i rejects q when la * qx + lb * qy + lc < 0
 };
 
 // direction k of the pre-filter (the table is computed once on the host and handed to the device, so both builds
@@ -485,13 +486,20 @@ OFK_HD double hull_edge_orient(const HullInfo& h, int i, const P2& p) {
     return orient(u, v, p);
 }
 
+// line form of edge i once its slack is known: orient(v_i, v_i+1, q) < slack_i - tolerance, written as a linear
+// function of q (the tolerance covers the rounding of either form)
+OFK_HD void hull_edge_line(HullInfo& h, int i) {
+    const int k = i + 1 == h.m ? 0 : i + 1;
+    const double dx = h.vx[k] - h.vx[i], dy = h.vy[k] - h.vy[i];
+    const double scale = fabs(dx) + fabs(dy) + fabs(h.vx[i]) + fabs(h.vy[i]) + 1.0;
+    h.la[i] = -dy;
+    h.lb[i] = dx;
+    h.lc[i] = dy * h.vx[i] - dx * h.vy[i] - h.slack[i] + 1e-8 * scale * scale;
+}
+
 OFK_HD bool hull_rejects(const HullInfo& h, const P2& q) {
-    for (int i = 0; i < h.m; ++i) {
-        const int k = i + 1 == h.m ? 0 : i + 1;
-        const double o = hull_edge_orient(h, i, q);
-        const double scale = fabs(h.vx[k] - h.vx[i]) + fabs(h.vy[k] - h.vy[i]);
-        if (o < h.slack[i] - 1e-9 * (scale + 1.0) * (scale + 1.0)) return true;
-    }
+    for (int i = 0; i < h.m; ++i)
+        if (dfma(h.la[i], q.x, dfma(h.lb[i], q.y, h.lc[i])) < 0) return true;
     return false;
 }
 
@@ -520,6 +528,7 @@ inline void hull_build_serial(const SiteGrid& g, uint32_t nsites, const HullDirs
         const P2 p = site_pos(g, g.sites[s]);
         for (int i = 0; i < h.m; ++i) h.slack[i] = fmin(h.slack[i], hull_edge_orient(h, i, p));
     }
+    for (int i = 0; i < h.m; ++i) hull_edge_line(h, i);
 }
 
 // a valid site is a boundary site when it sits on the frame border or one of its 8 neighbours has been removed

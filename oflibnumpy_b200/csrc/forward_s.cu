@@ -314,7 +314,7 @@ constexpr int REC_OK = 1 << 15;    // record flag: the cell is a positively orie
 // in-circle determinant, weights and payload in float64. Without the queue the 1..4 candidates of a cell are a
 // divergent loop that runs its longest trip count on every warp (measured: 765 thread instructions per pixel).
 template <int CT>
-__global__ void __launch_bounds__(256) fwd_raster_kernel(const RasterArgs A) {
+__global__ void __launch_bounds__(256, 3) fwd_raster_kernel(const RasterArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int PC = CT > 0 ? CT : 0;
     P2* s_pos = reinterpret_cast<P2*>(smem);
@@ -728,6 +728,7 @@ __global__ void hull_frame_kernel(const HullArgs A) {
         if (threadIdx.x < HULL_DIRS) ws.slackkey[threadIdx.x] = order_key(0.0);
     } else if (threadIdx.x < HULL_DIRS) {
         info.slack[threadIdx.x] = order_value(ws.slackkey[threadIdx.x]);
+        if ((int)threadIdx.x < info.m) hull_edge_line(info, threadIdx.x);
     }
 }
 
@@ -1042,6 +1043,8 @@ static void launch_raster(const fwdk::RasterArgs& A, int N, cudaStream_t st) {
     const size_t smem = (size_t)NV * (sizeof(fwd::P2) + 8 + 2) + 4 * (size_t)(NV * PC + ((NV * PC) & 1)) + 8 * QCAP * 8;
     // > 48 KB of dynamic shared memory needs the opt-in (per device)
     cudaFuncSetAttribute(fwd_raster_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(fwd_raster_kernel<CT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
     dim3 grid((A.W - 1 + TW - 1) / TW, (A.H - 1 + TH - 1) / TH, N);
     fwd_raster_kernel<CT><<<grid, 256, smem, st>>>(A);
 }
