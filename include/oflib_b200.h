@@ -155,6 +155,11 @@ int ofk_check_finite(const float* data, size_t n, int* flag, ofk_stream_t stream
 int ofk_pad(const float* vecs, const uint8_t* mask, float* out_vecs, uint8_t* out_mask, int mode, int N, int H, int W,
             int top, int bottom, int left, int right, ofk_stream_t stream);
 
+/* Payload dtype conversion around the float32 forward resampler (utils.py:256-258): exactly one of in_dtype /
+ * out_dtype is OFK_F32, the other one of OFK_U8 / OFK_I16 / OFK_U16 / OFK_F64. From float32 to an integer type:
+ * round-half-even (numpy.round) and saturate. */
+int ofk_cast(const void* in, int in_dtype, void* out, int out_dtype, size_t n, ofk_stream_t stream);
+
 /* out = a & b for 0/1 masks (the `target_mask & self.mask` of Flow.apply for 's' flows, flow_class.py:634-643). */
 int ofk_mask_and(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n, ofk_stream_t stream);
 
@@ -212,17 +217,29 @@ int ofk_decode_sintel_mask(const uint8_t* invalid, uint8_t* mask, size_t n_pixel
 /* ------------------------------------------------------------------------------- source-referenced path, device */
 
 /* Source-referenced (forward) resampling: replaces `griddata(grid + flow, payload, grid, 'linear')` + nan_to_num in
- * apply_flow (utils.py:237-258) with a rasterisation of the displaced pixel grid (two triangles per cell, Delaunay
- * diagonal, float64 geometry). payload is float32 [N,H,W,C]; payload_mask (or NULL = all valid) is resampled with it
- * and turned into out_mask by mask_rule: OFK_RULE_STRICT (float payloads: interpolated mask == 1 after the float32
- * cast) or OFK_RULE_GT_HALF (integer payloads: numpy.round(interpolated mask) == 1). point_mask (consider_mask, or
- * NULL) removes invalid source points: cells touching a removed point are not rasterised (documented deviation from
- * Qhull's gap bridging). Sample positions are p + flow_sign * flow[p].
- * ws: device workspace of ofk_forward_s_workspace(N,H,W) bytes. payload/out may be NULL with C = 0 (mask only). */
+ * apply_flow (utils.py:237-258): the Delaunay triangulation of the displaced pixel positions p + flow_sign * flow[p]
+ * with barycentric interpolation (float64 geometry) and 0 outside the convex hull. Cells of the displaced grid with
+ * four valid corners are rasterised directly (each split along its Delaunay diagonal); everything else -- holes left
+ * by removed points, the pockets between the displaced frame border and its convex hull -- is located per pixel in
+ * the Delaunay triangulation of the boundary points, exactly as Qhull bridges them.
+ *   payload       float32 [N,H,W,C]; payload_mask [N,H,W] (or NULL = all valid) is resampled with it and turned into
+ *                 out_mask by mask_rule: OFK_RULE_STRICT (float payloads: interpolated mask == 1 after the float32
+ *                 cast) or OFK_RULE_GT_HALF (integer payloads: numpy.round(interpolated mask) == 1)
+ *   point_mask    [N,H,W] or NULL: `consider_mask`, the points with 0 are removed before triangulating (utils.py:249-251)
+ *   mask bytes    must be 0 or 1
+ *   ws            device workspace of ofk_forward_s_workspace(N,H,W) bytes; payload/out may be NULL with C = 0
+ * Folding fields (a displaced cell with a non-positive triangle) have no defined result in the reference; such frames
+ * are resolved deterministically (largest source index wins, cells with a removed corner left empty).
+ * ofk_forward_s_ex: flow_nonzero (int32 [N], device, e.g. from ofk_nonzero_flags(flow, NULL, 1e-3)) or NULL; frames
+ * with 0 are passed through (out = payload, out_mask = payload_mask) like apply_flow's early return for a flow that is
+ * zero below the threshold (utils.py:215-216). */
 size_t ofk_forward_s_workspace(int N, int H, int W);
 int ofk_forward_s(const float* payload, int C, const float* flow, float flow_sign, const uint8_t* payload_mask,
                   const uint8_t* point_mask, float* out, uint8_t* out_mask, int mask_rule, int N, int H, int W,
                   void* ws, size_t ws_bytes, ofk_stream_t stream);
+int ofk_forward_s_ex(const float* payload, int C, const float* flow, float flow_sign, const uint8_t* payload_mask,
+                     const uint8_t* point_mask, const int* flow_nonzero, float* out, uint8_t* out_mask, int mask_rule,
+                     int N, int H, int W, void* ws, size_t ws_bytes, ofk_stream_t stream);
 
 /* Test hook: cells of the displaced grid whose in-circle determinant is within +-tol take the OTHER diagonal in
  * subsequent ofk_forward_s calls of this process (0 = production behaviour). Similarity transforms leave the four
@@ -242,6 +259,21 @@ int ofk_forward_s_set_flip_tol(double tol);
 int ofk_mesh_sample(const float* mesh_flow, float mesh_sign, int pos_f32, const float* payload, int C,
                     const uint8_t* payload_mask, const float* query_flow, float query_sign, const double* query_pts,
                     int Q, float* out, float* out_maskval, uint8_t* found, int N, int H, int W, ofk_stream_t stream);
+
+/* Flow composition, modes 1 and 2 (flow_class.py:1357-1410), frame-wise on a batch: the chains of forward / backward
+ * warps, additions and mask-ANDs the reference writes as Flow methods, run on the device behind one call.
+ *   mode 1: flow_1 such that flow_1 (+) A = B;   mode 2: flow_2 such that A (+) flow_2 = B;   ref 's' or 't' (both
+ *   operands and the result). Am / Bm may be NULL (all valid); mask bytes must be 0 or 1.
+ * The zero-flow tests INSIDE the chains (switch_ref relabels an exactly-zero flow, apply_flow passes its target through
+ * for a flow below the threshold) are evaluated per frame on the device. The early exits of combine_with itself
+ * (:1338-1354: A zero -> B, B zero -> A.invert()) return operand objects and stay with the caller
+ * (ofk_nonzero_flags). ws: device workspace of ofk_combine12_workspace(mode, ref, N, H, W) bytes.
+ * ofk_combine2_t is mode 2 / ref 't' alone (one launch, no workspace): B - resample(A, grid - A -> grid - B). */
+size_t ofk_combine12_workspace(int mode, int ref, int N, int H, int W);
+int ofk_combine12(int mode, int ref, const float* A, const uint8_t* Am, const float* B, const uint8_t* Bm, float* out,
+                  uint8_t* out_mask, int N, int H, int W, void* ws, size_t ws_bytes, ofk_stream_t stream);
+int ofk_combine2_t(const float* A, const uint8_t* Am, const float* B, const uint8_t* Bm, float* out, uint8_t* out_mask,
+                   int N, int H, int W, ofk_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------ host-buffer API */
 

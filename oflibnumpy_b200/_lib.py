@@ -48,7 +48,12 @@ _SIGNATURES = {
     'ofk_points_inside_area': (_i, [_vp, _sz, _i, _i, _vp, _vp]),
     'ofk_forward_s_workspace': (_sz, [_i, _i, _i]),
     'ofk_forward_s': (_i, [_vp, _i, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    'ofk_cast': (_i, [_vp, _i, _vp, _i, _sz, _vp]),
     'ofk_forward_s_set_flip_tol': (_i, [C.c_double]),
+    'ofk_forward_s_ex': (_i, [_vp, _i, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    'ofk_combine12_workspace': (_sz, [_i, _i, _i, _i, _i]),
+    'ofk_combine12': (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    'ofk_combine2_t': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'ofk_mesh_sample': (_i, [_vp, _f, _i, _vp, _i, _vp, _vp, _f, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'ofh_warp_t': (_i, [_vp, _i, _i, _i, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i]),
     'ofh_combine3': (_i, [_vp, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _i, _i, _i, _i]),
@@ -80,7 +85,7 @@ _SIGNATURES = {
     'ofk_rt_path_count': (C.c_ulonglong, [C.c_int]),
 }
 
-_NO_CHECK = {'ofk_last_error', 'ofk_version', 'ofk_forward_s_workspace', 'ofk_kth_smallest_workspace', 'ofk_rt_launch_count', 'ofk_rt_path_count'}
+_NO_CHECK = {'ofk_last_error', 'ofk_version', 'ofk_forward_s_workspace', 'ofk_combine12_workspace', 'ofk_kth_smallest_workspace', 'ofk_rt_launch_count', 'ofk_rt_path_count'}
 
 _lib = None
 

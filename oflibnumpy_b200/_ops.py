@@ -236,16 +236,53 @@ def points_inside_area(pts, shape):
     return out.numpy().astype(bool)
 
 
-def forward_s(flow, sign, payload, payload_mask=None, point_mask=None, want_mask=True, rule=_lib.RULE_STRICT):
-    """Forward (source-referenced) resampling of a float32 payload [N,H,W,C] (ofk_forward_s)."""
+def cast(arr, dtype, round_ints=True):
+    """Device dtype conversion to / from float32 (ofk_cast)."""
+    dtype = np.dtype(dtype)
+    out = DeviceArray.empty(arr.shape, dtype)
+    _lib.call('ofk_cast', arr.ptr, dtype_code(arr.dtype), out.ptr, dtype_code(dtype), arr.size, dev.current_stream())
+    return out
+
+
+def and_flags(a, b):
+    """Element-wise AND of two device int32 0/1 flag arrays."""
+    out = DeviceArray.empty(a.shape, np.int32)
+    _lib.call('ofk_mask_and', a.ptr, b.ptr, out.ptr, a.nbytes, dev.current_stream())
+    return out
+
+
+def nonzero_flags_device(flow, mask, thr):
+    """Device int32 [N] version of nonzero_flags (no synchronisation)."""
+    n, h, w = flow.shape[:3]
+    flags = DeviceArray.empty((n,), np.int32)
+    _lib.call('ofk_nonzero_flags', flow.ptr, _p(mask), float(thr), flags.ptr, n, h, w, dev.current_stream())
+    return flags
+
+
+def forward_s(flow, sign, payload, payload_mask=None, point_mask=None, want_mask=True, rule=_lib.RULE_STRICT,
+              flow_nonzero=None):
+    """Forward (source-referenced) resampling of a float32 payload [N,H,W,C] (ofk_forward_s_ex). flow_nonzero: device
+    int32 [N]; frames with 0 are passed through (apply_flow's early return for a thresholded-zero flow)."""
     n, h, w = flow.shape[:3]
     c = payload.shape[3] if payload is not None else 0
     out = DeviceArray.empty((n, h, w, c), np.float32) if c else None
     omask = DeviceArray.empty((n, h, w), np.uint8) if want_mask else None
     ws_bytes = _lib.call('ofk_forward_s_workspace', n, h, w)
     ws = DeviceArray.empty((max(ws_bytes, 16),), np.uint8)
-    _lib.call('ofk_forward_s', _p(payload), c, flow.ptr, float(sign), _p(payload_mask), _p(point_mask), _p(out),
-              _p(omask), rule, n, h, w, ws.ptr, ws_bytes, dev.current_stream())
+    _lib.call('ofk_forward_s_ex', _p(payload), c, flow.ptr, float(sign), _p(payload_mask), _p(point_mask),
+              _p(flow_nonzero), _p(out), _p(omask), rule, n, h, w, ws.ptr, ws_bytes, dev.current_stream())
+    return out, omask
+
+
+def combine12(mode, ref, a, am, b, bm):
+    """combine_with modes 1 / 2 as one device-resident chain (ofk_combine12): flows [N,H,W,2], masks [N,H,W]."""
+    n, h, w = a.shape[:3]
+    out = DeviceArray.empty((n, h, w, 2), np.float32)
+    omask = DeviceArray.empty((n, h, w), np.uint8)
+    ws_bytes = _lib.call('ofk_combine12_workspace', mode, ord(ref), n, h, w)
+    ws = DeviceArray.empty((max(ws_bytes, 16),), np.uint8)
+    _lib.call('ofk_combine12', mode, ord(ref), a.ptr, _p(am), b.ptr, _p(bm), out.ptr, omask.ptr, n, h, w, ws.ptr,
+              ws_bytes, dev.current_stream())
     return out, omask
 
 

@@ -116,16 +116,18 @@ class FlowBatch(object):
         return b
 
     # ------------------------------------------------------------------------------------------------ hot path
-    def apply(self, targets, target_masks=None, return_valid_area=False):
-        """Warp images (N,H,W,C) [numpy or device] frame by frame with this batch (ref 't'), like ``Flow.apply``.
-        Returns device arrays (``.numpy()`` to download): images, and the valid areas if requested."""
-        if self.ref != 't':
-            raise NotImplementedError("FlowBatch.apply: batched warping is built for ref 't' flows")
+    def apply(self, targets, target_masks=None, return_valid_area=False, consider_mask=True):
+        """Warp images (N,H,W,C) [numpy or device] frame by frame with this batch, like ``Flow.apply`` (ref 't':
+        ofk_warp_t, ref 's': ofk_forward_s). Returns device arrays (``.numpy()`` to download): images in the dtype of
+        the targets (ref 's' resamples in float32 and rounds integer targets like the reference), and the valid areas
+        if requested."""
         payload = _to_device(targets)
         if payload.ndim == 3:
             payload = payload.reshape(payload.shape + (1,))
         if payload.shape[:3] != self.vecs.shape[:3]:
             raise ValueError("Error applying flow: Flow shape does not match target shape")
+        if self.ref == 's':
+            return self._apply_s(payload, target_masks, return_valid_area, consider_mask)
         pmask = None
         if return_valid_area:
             arith, rule = _ops.promoted_rule(payload.dtype, target_masks is not None)
@@ -138,10 +140,34 @@ class FlowBatch(object):
                                  return_valid_area, arith, rule)
         return (out, omask) if return_valid_area else out
 
-    def apply_to_flows(self, other):
+    def _zero_flags(self):
+        """Device int32 [N]: 0 where the flow is zero below the threshold (apply_flow passes its target through)."""
+        return _ops.nonzero_flags_device(self.vecs, None, DEFAULT_THRESHOLD)
+
+    def _apply_s(self, payload, target_masks, return_valid_area, consider_mask):
+        out_dtype = payload.dtype
+        is_int = np.issubdtype(out_dtype, np.integer)
+        pay32 = payload if out_dtype == np.float32 else _ops.cast(payload, np.float32)
+        pmask = None
+        if return_valid_area:
+            pmask = self.masks
+            if target_masks is not None:
+                tm = _to_device(target_masks.view(np.uint8) if isinstance(target_masks, np.ndarray) else target_masks)
+                pmask = _ops.mask_and(DeviceArray(tm.ptr, tm.shape, np.uint8, owner=tm), self.masks)
+        rule = _lib.RULE_GT_HALF if is_int else _lib.RULE_STRICT
+        out, omask = _ops.forward_s(self.vecs, 1.0, pay32, pmask, self.masks if consider_mask else None,
+                                    return_valid_area, rule, flow_nonzero=self._zero_flags())
+        if out_dtype != np.float32:
+            out = _ops.cast(out, out_dtype, round_ints=True)
+        return (out, omask) if return_valid_area else out
+
+    def apply_to_flows(self, other, consider_mask=True):
         """``self[i].apply(other[i])`` for every frame: warp a batch of flows (vectors and masks) with this batch."""
         if self.ref != 't':
-            raise NotImplementedError("FlowBatch.apply_to_flows: built for ref 't' flows")
+            pm = _ops.mask_and(other.masks, self.masks)
+            out, omask = _ops.forward_s(self.vecs, 1.0, other.vecs, pm, self.masks if consider_mask else None, True,
+                                        _lib.RULE_STRICT, flow_nonzero=self._zero_flags())
+            return FlowBatch._wrap(out, other.ref, omask)
         out, omask = _ops.warp_t(self.vecs, -1.0, other.vecs, other.masks, self.masks, True, _lib.ARITH_NATIVE,
                                  _lib.RULE_STRICT)
         return FlowBatch._wrap(out, other.ref, omask)
@@ -155,34 +181,84 @@ class FlowBatch(object):
             raise ValueError("Error combining flows: Flow fields need to have the same shape")
         if self.ref != other.ref:
             raise ValueError("Error combining flows: Flow fields need to have the same reference")
-        if mode != 3:
-            raise NotImplementedError("FlowBatch.combine_with: batched combination is built for mode 3")
+        if mode not in (1, 2, 3):
+            raise ValueError("Error combining flows: Mode needs to be 1, 2 or 3")
         thr = DEFAULT_THRESHOLD if thresholded else 0.0
-        v, m, flags = _ops.combine3(self.vecs, self.masks, other.vecs, other.masks, self.ref, thr)
+        if mode == 3:
+            v, m, flags = _ops.combine3(self.vecs, self.masks, other.vecs, other.masks, self.ref, thr)
+            res = FlowBatch._wrap(v, self.ref, m)
+            return (res, flags) if return_flags else res
+        # modes 1 and 2: one device-resident chain for the whole batch (ofk_combine12). The reference's early exits
+        # (self zero -> flow, flow zero -> self.invert(); flow_class.py:1338-1354) are rare: the two zero tests are
+        # read back once and those frames redone through the single-frame path
+        v, m = _ops.combine12(mode, self.ref, self.vecs, self.masks, other.vecs, other.masks)
+        a_nz = _ops.nonzero_flags(self.vecs, self.masks, thr)
+        b_nz = _ops.nonzero_flags(other.vecs, other.masks, thr)
         res = FlowBatch._wrap(v, self.ref, m)
+        for i in np.flatnonzero((a_nz == 0) | (b_nz == 0)):
+            one = self[int(i)].combine_with(other[int(i)], mode, thresholded)
+            res.vecs.frames(int(i), int(i) + 1).copy_from(one._vd())
+            res.masks.frames(int(i), int(i) + 1).copy_from(one._md())
+        flags = np.stack([a_nz, b_nz], 1)
         return (res, flags) if return_flags else res
 
-    def valid_target(self):
-        if self.ref != 't':
-            raise NotImplementedError("FlowBatch.valid_target: built for ref 't' flows")
-        return _ops.valid_geom_t(self.vecs, -1.0, self.masks)
+    def valid_target(self, consider_mask=True):
+        """Device uint8 (N,H,W): Flow.valid_target frame by frame (flow_class.py:1113-1151)."""
+        if self.ref == 't':
+            return _ops.valid_geom_t(self.vecs, -1.0, self.masks)
+        _, area = _ops.forward_s(self.vecs, 1.0, None, self.masks, self.masks if consider_mask else None,
+                                 flow_nonzero=self._zero_flags())
+        return area
 
-    def valid_source(self):
-        if self.ref != 's':
-            raise NotImplementedError("FlowBatch.valid_source: built for ref 's' flows")
-        return _ops.valid_geom_t(self.vecs, 1.0, self.masks)
+    def valid_source(self, consider_mask=True):
+        if self.ref == 's':
+            return _ops.valid_geom_t(self.vecs, 1.0, self.masks)
+        _, area = _ops.forward_s(self.vecs, -1.0, None, self.masks, self.masks if consider_mask else None,
+                                 flow_nonzero=self._zero_flags())
+        return area
 
-    def invert(self, ref):
-        """Cross-reference inversion (negate + relabel, flow_class.py:748,751)."""
-        ref = get_valid_ref(ref)
-        if ref == self.ref:
-            raise NotImplementedError("FlowBatch.invert: same-reference inversion is per-frame (Flow.invert)")
-        return FlowBatch._wrap(_ops.scale(_lib.OP_MUL, self.vecs, -1.0, -1.0, False), ref, self.masks)
+    def _negated(self):
+        return _ops.scale(_lib.OP_MUL, self.vecs, -1.0, -1.0, False)
+
+    def switch_ref(self, mode='valid'):
+        """Frame-wise Flow.switch_ref (flow_class.py:697-733): one forward resampling of vectors and mask; frames whose
+        flow is exactly zero on its valid pixels, or zero below the threshold everywhere, are only relabelled (the two
+        tests run on the device)."""
+        other = 't' if self.ref == 's' else 's'
+        if mode == 'invalid':
+            return FlowBatch._wrap(self.vecs, other, self.masks)
+        if mode != 'valid':
+            raise ValueError("Error switching flow reference: Mode not recognised, should be 'valid' or 'invalid'")
+        active = _ops.and_flags(self._zero_flags(), _ops.nonzero_flags_device(self.vecs, self.masks, 0.0))
+        out, omask = _ops.forward_s(self.vecs, 1.0 if self.ref == 's' else -1.0, self.vecs, self.masks, self.masks,
+                                    True, _lib.RULE_STRICT, flow_nonzero=active)
+        return FlowBatch._wrap(out, other, omask)
+
+    def invert(self, ref=None):
+        """Frame-wise Flow.invert (flow_class.py:735-753): cross-reference = negate + relabel, same reference = one
+        forward resampling (s -> s: self.apply(-self); t -> t: self.invert('s').switch_ref())."""
+        ref = self.ref if ref is None else get_valid_ref(ref)
+        if ref != self.ref:
+            return FlowBatch._wrap(self._negated(), ref, self.masks)
+        if self.ref == 's':
+            neg = self._negated()
+            out, omask = _ops.forward_s(self.vecs, 1.0, neg, self.masks, self.masks, True, _lib.RULE_STRICT,
+                                        flow_nonzero=self._zero_flags())
+            return FlowBatch._wrap(out, 's', omask)
+        return FlowBatch._wrap(self._negated(), 's', self.masks).switch_ref()
 
 
 # ---------------------------------------------------------------------------------------------------- host-buffer calls
 def _c(a, dtype=None):
     return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _check_out(arr, shape, dtype, name):
+    """Caller-supplied output buffers become raw pointers for the copy engines: shape, dtype and layout must be exact."""
+    if not isinstance(arr, np.ndarray) or arr.shape != tuple(shape) or arr.dtype != np.dtype(dtype) or \
+            not arr.flags.c_contiguous or not arr.flags.writeable:
+        raise ValueError("{} needs to be a writeable C-contiguous numpy array of shape {} and dtype {}".format(
+            name, tuple(shape), np.dtype(dtype)))
 
 
 def apply_flow_host(flows, images, flow_masks=None, target_masks=None, return_valid_area=False, out=None,
@@ -192,6 +268,8 @@ def apply_flow_host(flows, images, flow_masks=None, target_masks=None, return_va
     Pass pinned arrays (device.pinned_empty) for full-rate copies. Returns numpy arrays."""
     flows = _c(flows, np.float32)
     images = _c(images)
+    if flows.ndim != 4 or flows.shape[3] != 2:
+        raise ValueError("Error applying flow: flows need shape (N,H,W,2)")
     if images.ndim == 3:
         images = images[..., None]
     n, h, w = flows.shape[:3]
@@ -202,10 +280,16 @@ def apply_flow_host(flows, images, flow_masks=None, target_masks=None, return_va
         arith, rule = _ops.promoted_rule(images.dtype, target_masks is not None)
     else:
         arith, rule = _lib.ARITH_NATIVE, _lib.RULE_STRICT
-    out = np.empty_like(images) if out is None else out
+    if out is None:
+        out = np.empty_like(images)
+    else:
+        _check_out(out, images.shape if out.ndim == 4 else images.shape[:3], images.dtype, 'out')
     pm = fm = om = None
     if return_valid_area:
-        out_valid = np.empty((n, h, w), np.bool_) if out_valid is None else out_valid
+        if out_valid is None:
+            out_valid = np.empty((n, h, w), np.bool_)
+        else:
+            _check_out(out_valid, (n, h, w), np.bool_, 'out_valid')
         om = out_valid.ctypes.data
         if target_masks is not None:
             target_masks = _c(target_masks, np.bool_)
@@ -221,19 +305,38 @@ def apply_flow_host(flows, images, flow_masks=None, target_masks=None, return_va
 
 def combine_flows_host(flows_1, flows_2, mode, ref, masks_1=None, masks_2=None, thresholded=False, out=None,
                        out_masks=None, device=None):
-    """Batched ``combine_flows(flows_1[i], flows_2[i], 3, ref)`` / ``Flow.combine_with`` on HOST arrays (ofh_combine3).
-    Returns (vecs (N,H,W,2) float32, masks (N,H,W) bool)."""
-    if mode != 3:
-        raise NotImplementedError("combine_flows_host: built for mode 3")
+    """Batched ``combine_flows(flows_1[i], flows_2[i], mode, ref)`` / ``Flow.combine_with`` on HOST arrays. Mode 3
+    streams through ofh_combine3 (pinned ring, copies overlapped with the kernel); modes 1 / 2 upload the batch, run the
+    device chain of FlowBatch.combine_with and download. Returns (vecs (N,H,W,2) float32, masks (N,H,W) bool)."""
+    if mode not in (1, 2, 3):
+        raise ValueError("Error combining flows: Mode needs to be 1, 2 or 3")
     ref = get_valid_ref(ref)
+    if mode != 3:
+        res = FlowBatch(flows_1, ref, masks_1).combine_with(FlowBatch(flows_2, ref, masks_2), mode, thresholded)
+        v, m = res.numpy()
+        if out is not None:
+            _check_out(out, v.shape, np.float32, 'out')
+            out[...] = v
+            v = out
+        if out_masks is not None:
+            _check_out(out_masks, m.shape, np.bool_, 'out_masks')
+            out_masks[...] = m
+            m = out_masks
+        return v, m
     a, b = _c(flows_1, np.float32), _c(flows_2, np.float32)
     if a.shape != b.shape or a.ndim != 4 or a.shape[3] != 2:
         raise ValueError("Error combining flows: Flow fields need to have the same shape (N,H,W,2)")
     n, h, w = a.shape[:3]
     am = None if masks_1 is None else _c(masks_1, np.bool_)
     bm = None if masks_2 is None else _c(masks_2, np.bool_)
-    out = np.empty_like(a) if out is None else out
-    out_masks = np.empty((n, h, w), np.bool_) if out_masks is None else out_masks
+    if out is None:
+        out = np.empty_like(a)
+    else:
+        _check_out(out, a.shape, np.float32, 'out')
+    if out_masks is None:
+        out_masks = np.empty((n, h, w), np.bool_)
+    else:
+        _check_out(out_masks, (n, h, w), np.bool_, 'out_masks')
     flags = np.empty((n, 2), np.int32)
     device = dev.get_device() if device is None else device
     _lib.call('ofh_combine3', a.ctypes.data, None if am is None else am.ctypes.data, b.ctypes.data,

@@ -4,6 +4,8 @@
 // grid-stride loops sized to the SM count.
 #include <math.h>
 
+#include <algorithm>
+
 #include "ofk_common.cuh"
 
 namespace ofk {
@@ -439,6 +441,64 @@ extern "C" int ofk_extent(const float* flow, const uint8_t* mask, float sign, fl
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
     extent_kernel<<<dim3(bx, N), 256, 0, st>>>(flow, mask, sign, thr, out4, H, W);
+    OFK_LAUNCHED();
+    return OFK_OK;
+}
+
+// dtype conversion of payloads around the float32 forward resampler (utils.py:256-258: np.round for integer targets,
+// then astype): to float32 exact for the 8 / 16-bit types; from float32 with round-half-even and saturation.
+namespace ofk {
+template <class T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ uint8_t from_f32<uint8_t>(float v) {
+    return (uint8_t)min(255, max(0, __float2int_rn(v)));
+}
+template <>
+__device__ __forceinline__ int16_t from_f32<int16_t>(float v) {
+    return (int16_t)min(32767, max(-32768, __float2int_rn(v)));
+}
+template <>
+__device__ __forceinline__ uint16_t from_f32<uint16_t>(float v) {
+    return (uint16_t)min(65535, max(0, __float2int_rn(v)));
+}
+template <>
+__device__ __forceinline__ double from_f32<double>(float v) {
+    return (double)v;
+}
+template <class T>
+__global__ void __launch_bounds__(256) cast_to_f32_kernel(const T* __restrict__ in, float* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) out[i] = (float)in[i];
+}
+template <class T>
+__global__ void __launch_bounds__(256) cast_from_f32_kernel(const float* __restrict__ in, T* __restrict__ out,
+                                                            size_t n) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
+        out[i] = from_f32<T>(in[i]);
+}
+}  // namespace ofk
+
+extern "C" int ofk_cast(const void* in, int in_dtype, void* out, int out_dtype, size_t n, ofk_stream_t stream) {
+    OFK_CHECK_ARG(in && out, "ofk_cast: NULL argument");
+    OFK_CHECK_ARG((in_dtype == OFK_F32) != (out_dtype == OFK_F32), "ofk_cast: exactly one side must be float32");
+    if (n == 0) return OFK_OK;
+    cudaStream_t st = as_stream(stream);
+    const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)sm_count() * 16);
+    const int other = in_dtype == OFK_F32 ? out_dtype : in_dtype;
+    OFK_CHECK_ARG(other == OFK_U8 || other == OFK_I16 || other == OFK_U16 || other == OFK_F64, "ofk_cast: bad dtype %d",
+                  other);
+#define OFK_CAST(T)                                                                                               \
+    do {                                                                                                          \
+        if (out_dtype == OFK_F32) cast_to_f32_kernel<T><<<grid, 256, 0, st>>>((const T*)in, (float*)out, n);      \
+        else cast_from_f32_kernel<T><<<grid, 256, 0, st>>>((const float*)in, (T*)out, n);                         \
+    } while (0)
+    switch (other) {
+        case OFK_U8: OFK_CAST(uint8_t); break;
+        case OFK_I16: OFK_CAST(int16_t); break;
+        case OFK_U16: OFK_CAST(uint16_t); break;
+        default: OFK_CAST(double); break;
+    }
+#undef OFK_CAST
     OFK_LAUNCHED();
     return OFK_OK;
 }

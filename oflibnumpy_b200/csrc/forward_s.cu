@@ -57,7 +57,8 @@ __device__ __forceinline__ double incircle(const P2& a, const P2& b, const P2& c
 
 // Corner naming of cell (i, j): a = (i, j), b = (i, j+1), c = (i+1, j), d = (i+1, j+1).
 // diag 0 splits along a-d: triangles (a, b, d) and (a, d, c); diag 1 along b-c: (a, b, c) and (b, d, c).
-__device__ __forceinline__ int choose_diagonal(const P2& a, const P2& b, const P2& c, const P2& d) {
+__device__ __forceinline__ int choose_diagonal(const P2& a, const P2& b, const P2& c, const P2& d,
+                                               double flip_tol = 0.0) {
     const double o0a = orient(a, b, d), o0b = orient(a, d, c);   // diag 0 halves
     const double o1a = orient(a, b, c), o1b = orient(b, d, c);   // diag 1 halves
     const bool ok0 = (o0a > 0 && o0b > 0) || (o0a < 0 && o0b < 0);
@@ -65,7 +66,7 @@ __device__ __forceinline__ int choose_diagonal(const P2& a, const P2& b, const P
     if (ok0 && ok1) {  // convex quad: Delaunay criterion
         const double det = incircle(a, b, d, c);
         const bool c_inside = (o0a > 0) ? (det > 0) : (det < 0);
-        return c_inside ? 1 : 0;
+        return (c_inside ? 1 : 0) ^ (fabs(det) <= flip_tol ? 1 : 0);   // flip_tol: test hook, see cell_diagonal
     }
     return ok1 && !ok0 ? 1 : 0;
 }
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(256, 4) fwd_scatter(const float* __restrict__ 
                                                    unsigned int* __restrict__ winner, int H, int W,
                                                    const int* __restrict__ folded) {
     const int n = blockIdx.y;
-    if (!folded[n]) return;
+    if (folded[n] != 1) return;
     const int tx = (W - 1 + 31) / 32, ty = (H - 1 + 7) / 8;
     for (int t = blockIdx.x; t < tx * ty; t += gridDim.x) scatter_tile(flow, sign, point_mask, winner, H, W, t % tx, t / tx, n);
 }
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(256) fwd_gather(const float* __restrict__ payl
                                                   uint8_t* __restrict__ out_mask, int rule, int H, int W,
                                                   unsigned long long inv_w, const int* __restrict__ folded) {
     const int n = blockIdx.y;
-    if (!folded[n]) return;
+    if (folded[n] != 1) return;
     const int tx = (W + 31) / 32, ty = (H + 7) / 8;
     for (int t = blockIdx.x; t < tx * ty; t += gridDim.x)
         gather_tile(payload, C, flow, sign, payload_mask, winner, out, out_mask, rule, H, W, inv_w, t % tx, t / tx, n);
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(256) fwd_gather(const float* __restrict__ payl
 __global__ void __launch_bounds__(256) fwd_clear(unsigned int* __restrict__ winner, size_t frame_px,
                                                  const int* __restrict__ folded) {
     const int n = blockIdx.y;
-    if (!folded[n]) return;
+    if (folded[n] != 1) return;
     for (size_t t = (size_t)blockIdx.x * 256 + threadIdx.x; t < frame_px; t += (size_t)gridDim.x * 256)
         winner[(size_t)n * frame_px + t] = 0u;
 }
@@ -324,6 +325,7 @@ __global__ void __launch_bounds__(256, 3) fwd_raster_kernel(const RasterArgs A) 
     uint8_t* s_pm = reinterpret_cast<uint8_t*>(s_q + 8 * QCAP);
     uint8_t* s_pt = s_pm + NV;
     const int n = blockIdx.z, i0 = blockIdx.y * TH, j0 = blockIdx.x * TW;
+    if (A.folded[n] == 2) return;   // passed through (zero flow)
     const size_t frame = (size_t)n * A.H * A.W;
     const float2* fl = reinterpret_cast<const float2*>(A.flow) + frame;
     // pixel origin of the tile's local float32 coordinates: the displaced centre vertex
@@ -1003,6 +1005,26 @@ __global__ void hull_ws_init_kernel(HullWs* ws, int N) {
     if (t < N * HULL_DIRS) ws[t / HULL_DIRS].ext[t % HULL_DIRS] = NO_SITE;
 }
 
+// Frames whose flow is zero below the threshold are not resampled: apply_flow returns the target itself there
+// (utils.py:215-216). frame_state: 0 = resample, 1 = folded (set by the raster kernel), 2 = pass through.
+__global__ void fwd_mark_inactive_kernel(const int* __restrict__ flow_nonzero, int* __restrict__ frame_state, int N) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < N && flow_nonzero[n] == 0) frame_state[n] = 2;
+}
+
+__global__ void __launch_bounds__(256) fwd_passthrough_kernel(const float* __restrict__ payload, int C,
+                                                              const uint8_t* __restrict__ payload_mask,
+                                                              float* __restrict__ out, uint8_t* __restrict__ out_mask,
+                                                              size_t frame_px, const int* __restrict__ frame_state) {
+    const int n = blockIdx.y;
+    if (frame_state[n] != 2) return;
+    const size_t base = (size_t)n * frame_px;
+    for (size_t p = (size_t)blockIdx.x * 256 + threadIdx.x; p < frame_px; p += (size_t)gridDim.x * 256) {
+        for (int c = 0; c < C; ++c) out[(base + p) * C + c] = payload[(base + p) * C + c];
+        if (out_mask) out_mask[base + p] = payload_mask ? (payload_mask[base + p] != 0) : 1;
+    }
+}
+
 unsigned long long stat(int which) {
 #if defined(OFK_FWD_INSTR)
     if (which >= 8 && which < 16) {
@@ -1052,6 +1074,14 @@ static void launch_raster(const fwdk::RasterArgs& A, int N, cudaStream_t st) {
 extern "C" int ofk_forward_s(const float* payload, int C, const float* flow, float flow_sign,
                              const uint8_t* payload_mask, const uint8_t* point_mask, float* out, uint8_t* out_mask,
                              int mask_rule, int N, int H, int W, void* ws, size_t ws_bytes, ofk_stream_t stream) {
+    return ofk_forward_s_ex(payload, C, flow, flow_sign, payload_mask, point_mask, nullptr, out, out_mask, mask_rule, N,
+                            H, W, ws, ws_bytes, stream);
+}
+
+extern "C" int ofk_forward_s_ex(const float* payload, int C, const float* flow, float flow_sign,
+                                const uint8_t* payload_mask, const uint8_t* point_mask, const int* flow_nonzero,
+                                float* out, uint8_t* out_mask, int mask_rule, int N, int H, int W, void* ws,
+                                size_t ws_bytes, ofk_stream_t stream) {
     using namespace fwdk;
     OFK_CHECK_ARG(flow != nullptr, "ofk_forward_s: flow is NULL");
     OFK_CHECK_ARG(N >= 0 && H > 0 && W > 0, "ofk_forward_s: bad shape N=%d H=%d W=%d", N, H, W);
@@ -1084,6 +1114,10 @@ extern "C" int ofk_forward_s(const float* payload, int C, const float* flow, flo
     OFK_CUDA(cudaMemsetAsync(d_cover, UNCOVERED, px, st));
     hull_ws_init_kernel<<<(N * fwd::HULL_DIRS + 255) / 256, 256, 0, st>>>(d_hullws, N);
     OFK_LAUNCHED();
+    if (flow_nonzero != nullptr) {
+        fwd_mark_inactive_kernel<<<(N + 255) / 256, 256, 0, st>>>(flow_nonzero, d_folded, N);
+        OFK_LAUNCHED();
+    }
 
     // ---- regular part
     if (H > 1 && W > 1) {
@@ -1155,6 +1189,11 @@ extern "C" int ofk_forward_s(const float* payload, int C, const float* flow, flo
     irr_heavy_kernel<<<sm_count() * 4, 256, 0, st>>>(S);
     OFK_LAUNCHED();
 
+    if (flow_nonzero != nullptr) {
+        fwd_passthrough_kernel<<<dim3(std::max(8, std::min(1184, 4736 / N)), N), 256, 0, st>>>(
+            payload, C, payload_mask, out, out_mask, (size_t)H * W, d_folded);
+        OFK_LAUNCHED();
+    }
     // ---- folding frames: redone by the order-independent resolve (no-ops for all other frames)
     if (H > 1 && W > 1) {
         unsigned int* winner = reinterpret_cast<unsigned int*>(d_sites);
@@ -1197,7 +1236,7 @@ __device__ __forceinline__ P2 mesh_vertex(const float2* __restrict__ fl, int W, 
 
 // tests cell (i, j); on success fills the three vertex indices and barycentric weights
 __device__ bool locate_in_cell(const float2* __restrict__ fl, int H, int W, float sign, int pos_f32, int i, int j,
-                               double qx, double qy, int (&vidx)[3], double (&w)[3]) {
+                               double qx, double qy, int (&vidx)[3], double (&w)[3], double flip_tol) {
     if (i < 0 || j < 0 || i >= H - 1 || j >= W - 1) return false;
     P2 v[4];
     v[0] = mesh_vertex(fl, W, i, j, sign, pos_f32);
@@ -1205,7 +1244,7 @@ __device__ bool locate_in_cell(const float2* __restrict__ fl, int H, int W, floa
     v[2] = mesh_vertex(fl, W, i + 1, j, sign, pos_f32);
     v[3] = mesh_vertex(fl, W, i + 1, j + 1, sign, pos_f32);
     const int vid[4] = {i * W + j, i * W + j + 1, (i + 1) * W + j, (i + 1) * W + j + 1};
-    const int diag = choose_diagonal(v[0], v[1], v[2], v[3]);
+    const int diag = choose_diagonal(v[0], v[1], v[2], v[3], flip_tol);
     for (int tri = 0; tri < 2; ++tri) {
         const int c0 = corner_of(diag, tri, 0), c1 = corner_of(diag, tri, 1), c2 = corner_of(diag, tri, 2);
         const double area2 = orient(v[c0], v[c1], v[c2]);
@@ -1233,7 +1272,10 @@ __global__ void __launch_bounds__(128) mesh_sample_kernel(const float* __restric
                                                           const float* __restrict__ query_flow, float query_sign,
                                                           const double* __restrict__ query_pts, int Q,
                                                           float* __restrict__ out, float* __restrict__ out_maskval,
-                                                          uint8_t* __restrict__ found, int H, int W) {
+                                                          uint8_t* __restrict__ found, int H, int W,
+                                                          const float* __restrict__ sub_from,
+                                                          const uint8_t* __restrict__ sub_mask,
+                                                          uint8_t* __restrict__ out_mask8, double flip_tol) {
     const int n = blockIdx.y;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= Q) return;
@@ -1279,30 +1321,36 @@ __global__ void __launch_bounds__(128) mesh_sample_kernel(const float* __restric
         for (int di = -ring; di <= ring && !hit; ++di)
             for (int dj = -ring; dj <= ring && !hit; ++dj) {
                 if (max(abs(di), abs(dj)) != ring) continue;
-                hit = locate_in_cell(fl, H, W, mesh_sign, pos_f32, ci + di, cj + dj, qx, qy, vidx, w);
+                hit = locate_in_cell(fl, H, W, mesh_sign, pos_f32, ci + di, cj + dj, qx, qy, vidx, w, flip_tol);
             }
     }
     const size_t o = (size_t)n * Q + k;
     if (found) found[o] = hit ? 1 : 0;
-    if (!hit) {
-        for (int c = 0; c < C; ++c) out[o * C + c] = 0.f;
-        if (out_maskval) out_maskval[o] = 0.f;
-        return;
-    }
-    const float* pay = payload + fbase * C;
-    for (int c = 0; c < C; ++c) {
-        const double val = w[0] * (double)__ldg(pay + (size_t)vidx[0] * C + c) +
-                           w[1] * (double)__ldg(pay + (size_t)vidx[1] * C + c) +
-                           w[2] * (double)__ldg(pay + (size_t)vidx[2] * C + c);
-        out[o * C + c] = (float)val;
-    }
-    if (out_maskval) {
+    float vals[4] = {0.f, 0.f, 0.f, 0.f};
+    float mval = 0.f;
+    if (hit) {
+        const float* pay = payload + fbase * C;
+        for (int c = 0; c < C; ++c) {
+            const double val = w[0] * (double)__ldg(pay + (size_t)vidx[0] * C + c) +
+                               w[1] * (double)__ldg(pay + (size_t)vidx[1] * C + c) +
+                               w[2] * (double)__ldg(pay + (size_t)vidx[2] * C + c);
+            if (sub_from == nullptr) out[o * C + c] = (float)val;
+            else vals[c & 3] = (float)val;
+        }
         double m = w[0] + w[1] + w[2];
         if (payload_mask) {
             const uint8_t* pm = payload_mask + fbase;
             m = (pm[vidx[0]] ? w[0] : 0.0) + (pm[vidx[1]] ? w[1] : 0.0) + (pm[vidx[2]] ? w[2] : 0.0);
         }
-        out_maskval[o] = (float)m;
+        mval = (float)m;
+    } else if (sub_from == nullptr) {
+        for (int c = 0; c < C; ++c) out[o * C + c] = 0.f;
+    }
+    if (out_maskval) out_maskval[o] = mval;
+    if (sub_from != nullptr) {
+        // combine_with mode 2 / ref 't' (flow_class.py:1410): B - Flow(resampled A, 't', resampled mask > .99)
+        for (int c = 0; c < C; ++c) out[o * C + c] = __fsub_rn(sub_from[o * C + c], vals[c & 3]);
+        out_mask8[o] = (mval > 0.99f ? 1 : 0) & (sub_mask ? sub_mask[o] : (uint8_t)1);
     }
 }
 
@@ -1326,7 +1374,27 @@ extern "C" int ofk_mesh_sample(const float* mesh_flow, float mesh_sign, int pos_
     dim3 grid((Q + 127) / 128, N);
     ofk::legacy::mesh_sample_kernel<<<grid, 128, 0, ofk::as_stream(stream)>>>(mesh_flow, mesh_sign, pos_f32, payload, C,
                                                                      payload_mask, query_flow, query_sign, query_pts,
-                                                                     Q, out, out_maskval, found, H, W);
+                                                                     Q, out, out_maskval, found, H, W, nullptr,
+                                                                     nullptr, nullptr, ofk::g_flip_tol.load());
+    OFK_LAUNCHED();
+    return OFK_OK;
+}
+
+// combine_with(mode = 2) for ref 't' in one launch (flow_class.py:1398-1410): A (vectors and mask) is resampled from
+// its source positions grid - A to the source positions grid - B of B (float32 coordinates, no point masking,
+// fill 0), subtracted from B, and valid where the resampled mask exceeds .99 and B is valid.
+extern "C" int ofk_combine2_t(const float* A, const uint8_t* Am, const float* B, const uint8_t* Bm, float* out,
+                              uint8_t* out_mask, int N, int H, int W, ofk_stream_t stream) {
+    OFK_CHECK_ARG(A && B && out && out_mask, "ofk_combine2_t: NULL operand");
+    OFK_CHECK_ARG(N >= 0 && H > 1 && W > 1, "ofk_combine2_t: bad shape N=%d H=%d W=%d", N, H, W);
+    OFK_CHECK_ARG((size_t)H * W < ((size_t)1 << 30), "ofk_combine2_t: frame too large");
+    if (N == 0) return OFK_OK;
+    OFK_CHECK_ARG(N <= 65535, "ofk_combine2_t: N too large");
+    const int Q = H * W;
+    dim3 grid((Q + 127) / 128, N);
+    ofk::legacy::mesh_sample_kernel<<<grid, 128, 0, ofk::as_stream(stream)>>>(A, -1.0f, 1, A, 2, Am, B, -1.0f, nullptr, Q,
+                                                                             out, nullptr, nullptr, H, W, B, Bm,
+                                                                             out_mask, ofk::g_flip_tol.load());
     OFK_LAUNCHED();
     return OFK_OK;
 }

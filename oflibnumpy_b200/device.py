@@ -183,6 +183,12 @@ class DeviceArray:
         _lib.call('ofk_rt_memcpy_d2d', a.ptr, self.ptr, self.nbytes, _current_stream)
         return a
 
+    def copy_from(self, other):
+        """Device-to-device copy of `other` (same size in bytes) into this array."""
+        if other.nbytes != self.nbytes:
+            raise ValueError("copy_from: size mismatch ({} vs {} bytes)".format(other.nbytes, self.nbytes))
+        _lib.call('ofk_rt_memcpy_d2d', self.ptr, other.ptr, self.nbytes, _current_stream)
+
     def reshape(self, *shape):
         if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
             shape = tuple(shape[0])

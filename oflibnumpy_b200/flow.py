@@ -469,7 +469,7 @@ class Flow(object):
                                           cut)
         if return_flow:
             return Flow._wrap(warped, target._ref, wmask)
-        img = warped.numpy()[0] if isinstance(warped, DeviceArray) else warped
+        img = warped.numpy()[0] if isinstance(warped, DeviceArray) else np.array(warped[0])
         if img.dtype != out_dtype:               # ref 's' resamples in float32
             if np.issubdtype(out_dtype, np.integer):
                 img = np.round(img)
@@ -496,7 +496,9 @@ class Flow(object):
 
     def _apply_s(self, payload, pmask, host_tmask, return_flow, want_mask, consider_mask, padding, cut):
         out_is_float = return_flow or np.issubdtype(payload.dtype, np.floating)
+        host_payload = None
         if not return_flow:
+            host_payload = payload[None]                   # kept for the zero-flow pass-through (any dtype, exact)
             payload = DeviceArray.from_numpy(payload[None], np.float32)
             pmask = None if host_tmask is None else DeviceArray.from_numpy(host_tmask[None].view(np.uint8))
         flow_v, flow_m = self._vd(), self._md()
@@ -510,11 +512,20 @@ class Flow(object):
                 host_tmask[...] = res_mask.numpy()[0].view(np.bool_)
         # integer payloads: the reference rounds the interpolated payload||mask array before `== 1` (utils.py:256-258)
         rule = _lib.RULE_STRICT if (return_flow or out_is_float) else _lib.RULE_GT_HALF
-        warped, wmask = _ops.forward_s(flow_v, 1.0, payload, res_mask, flow_m if consider_mask else None, want_mask,
-                                       rule)
+        if int(_ops.nonzero_flags(flow_v, None, DEFAULT_THRESHOLD)[0]) == 0:
+            # apply_flow returns its target untouched for a flow that is zero below the threshold (utils.py:215-216):
+            # nothing is resampled, the warped mask is the mask that went in
+            warped = payload.copy() if return_flow else host_payload
+            wmask = res_mask.copy() if (want_mask and res_mask is not None) else None
+        else:
+            warped, wmask = _ops.forward_s(flow_v, 1.0, payload, res_mask, flow_m if consider_mask else None,
+                                           want_mask, rule)
         if padding is not None and cut:
             fh, fw = self.shape
-            warped = _ops.crop(warped, padding[0], padding[2], fh, fw)
+            if isinstance(warped, np.ndarray):
+                warped = warped[:, padding[0]:padding[0] + fh, padding[2]:padding[2] + fw]
+            else:
+                warped = _ops.crop(warped, padding[0], padding[2], fh, fw)
             if wmask is not None:
                 wmask = _ops.crop(wmask, padding[0], padding[2], fh, fw)
         return warped, wmask
@@ -561,6 +572,8 @@ class Flow(object):
         if not isinstance(consider_mask, bool):
             raise TypeError("Error applying flow: Consider_mask needs to be a boolean")
         if self._ref == 's':
+            if int(_ops.nonzero_flags(self._vd(), None, DEFAULT_THRESHOLD)[0]) == 0:
+                return np.array(self.mask)      # apply_flow hands the mask back for a thresholded-zero flow
             _, area = _ops.forward_s(self._vd(), 1.0, None, self._md(), self._md() if consider_mask else None)
         else:
             area = _ops.valid_geom_t(self._vd(), -1.0, self._md())
@@ -573,6 +586,8 @@ class Flow(object):
         if self._ref == 's':
             area = _ops.valid_geom_t(self._vd(), 1.0, self._md())
         else:
+            if int(_ops.nonzero_flags(self._vd(), None, DEFAULT_THRESHOLD)[0]) == 0:
+                return np.array(self.mask)
             _, area = _ops.forward_s(self._vd(), -1.0, None, self._md(), self._md() if consider_mask else None)
         return area.numpy()[0].view(np.bool_)
 
@@ -647,18 +662,10 @@ class Flow(object):
             return flow
         if flow.is_zero(thresholded=thresholded):
             return self.invert()
-        if mode == 1:
-            if self._ref == 's':
-                flow_inv_t = flow.invert('t')
-                return flow - (flow_inv_t + flow_inv_t.apply(self.switch_ref())).apply(self)
-            self_s = self.switch_ref()
-            result = flow.switch_ref() - (self_s + self_s.invert(ref='t').apply(flow.invert('s'))).apply(self_s)
-            return result.switch_ref()
-        # mode == 2
-        if self._ref == 's':
-            return self.apply(flow - self)
-        from .ops import _combine2_t_device
-        return _combine2_t_device(self, flow)
+        # the chains of flow_class.py:1357-1410 (switch_ref / invert / apply / + / -) run as one device-resident
+        # sequence behind ofk_combine12, including the zero-flow tests inside switch_ref and apply_flow
+        v, m = _ops.combine12(mode, self._ref, self._vd(), self._md(), flow._vd(), flow._md())
+        return Flow._wrap(v, self._ref, m)
 
 
 def _ones_mask(shape):

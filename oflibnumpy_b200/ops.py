@@ -91,6 +91,8 @@ def apply_flow(flow, target, ref, mask=None):
     """Warp ``target`` (H,W[,C]) with ``flow`` (H,W,2): reference ``apply_flow`` (utils.py:199-261)."""
     ref = get_valid_ref(ref)
     flow, dflow = upload_flow_array(flow, "Error applying flow to a target: ")
+    if int(_ops.nonzero_flags(dflow, None, DEFAULT_THRESHOLD)[0]) == 0:
+        return target          # the reference returns the very same object (utils.py:215-216), before any other check
     if not isinstance(target, np.ndarray):
         raise TypeError("Error applying flow to a target: Target needs to be a numpy array")
     if target.ndim < 2 or target.ndim > 3:
