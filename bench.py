@@ -98,9 +98,33 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def cpu_reference_step(frames, sample, repeat=1):
-    """The reference's CPU path (oracle port: cv2.remap + the numpy glue of Flow.apply / combine_with) on `sample`
-    frames, `repeat` times over; returns seconds."""
+def reference_module():
+    """The UNMODIFIED reference (oflibnumpy 1.1.1), installed into baseline/_ref by __graft_entry__.build() in the build
+    container; the directory is git-ignored and travels to the GPU box with the snapshot. None if it is not there."""
+    path = os.path.join(ROOT, 'baseline', '_ref')
+    if not os.path.isdir(os.path.join(path, 'oflibnumpy')):
+        return None
+    if path not in sys.path:
+        sys.path.insert(0, path)
+    try:
+        import oflibnumpy
+        return oflibnumpy
+    except Exception:
+        return None
+
+
+def cpu_reference_step(frames, sample, repeat=1, ref=None):
+    """The reference's CPU path on `sample` frames, `repeat` times over; returns seconds. ref = the reference module
+    (oflibnumpy.Flow(...).apply / .combine_with, exactly what a user of the reference runs); without it the oracle port
+    (cv2.remap + the numpy glue of Flow.apply / combine_with, restated)."""
+    if ref is not None:
+        t0 = time.perf_counter()
+        for _ in range(repeat):
+            for (fa, fam, fb, fbm, img) in frames[:sample]:
+                a, b = ref.Flow(fa, 't', fam), ref.Flow(fb, 't', fbm)
+                a.apply(img, return_valid_area=True)
+                a.combine_with(b, 3)
+        return time.perf_counter() - t0
     from oracle import flowref as R
     t0 = time.perf_counter()
     for _ in range(repeat):
@@ -111,13 +135,17 @@ def cpu_reference_step(frames, sample, repeat=1):
     return time.perf_counter() - t0
 
 
-def cpu_frames(count):
-    from oracle import flowref as R
+def cpu_frames(count, ref=None):
     am, bm, img = host_inputs(count, seed=0)
+    if ref is not None:
+        gen = ref.from_transforms
+    else:
+        from oracle import flowref as R
+        gen = R.from_transforms
     frames = []
     for i in range(count):
         ta, tb = frame_transforms(i)
-        frames.append((R.from_transforms(ta, (H, W), 't'), am[i], R.from_transforms(tb, (H, W), 't'), bm[i], img[i]))
+        frames.append((gen(ta, (H, W), 't'), am[i], gen(tb, (H, W), 't'), bm[i], img[i]))
     return frames
 
 
@@ -126,10 +154,12 @@ def run_reference(args, rank, world):
         return
     import cv2
     sample = args.cpu_sample
-    frames = cpu_frames(sample)
+    ref = reference_module()
+    kind = "reference" if ref is not None else "port"
+    frames = cpu_frames(sample, ref)
     for _ in range(args.warmup):
-        cpu_reference_step(frames, 1)
-    secs = [cpu_reference_step(frames, sample) for _ in range(args.steps)]
+        cpu_reference_step(frames, 1, ref=ref)
+    secs = [cpu_reference_step(frames, sample, ref=ref) for _ in range(args.steps)]
     t = float(np.mean(secs))
     value = sample * H * W / t / 1e6
     cores = cv2.getNumThreads()
@@ -138,9 +168,11 @@ def run_reference(args, rank, world):
             "scaling": "weak", "vs_baseline": None, "dtype": "u8+f32", "data": "synthetic",
             "config": {"workload": "cfg4: 1920x1080 apply(uint8x3, valid area) + combine_with(mode=3), ref 't'",
                        "frames_per_step": sample},
-            "cpu_baseline": {"value": value, "unit": "Mpixel/s", "cores": cores, "kind": "port",
-                             "sample": "%d frames of 1920x1080 per step, per-frame Python loop (the reference has no "
-                                       "batch axis); cv2.remap uses %d threads, numpy glue 1" % (sample, cores)},
+            "cpu_baseline": {"value": value, "unit": "Mpixel/s", "cores": cores, "kind": kind,
+                             "sample": "%d frames of 1920x1080 per step, per-frame Python loop of %s (the reference has "
+                                       "no batch axis); cv2.remap uses %d threads, numpy glue 1" %
+                                       (sample, "oflibnumpy 1.1.1 itself (baseline/_ref: Flow.apply + Flow.combine_with)"
+                                        if ref is not None else "the oracle port", cores)},
             "e2e": {"value": value, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -152,13 +184,14 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--batch', type=int, default=256, help='frames per GPU per step')
     ap.add_argument('--e2e-batch', type=int, default=32, help='frames per GPU per end-to-end step (pinned host)')
-    ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--e2e-steps', type=int, default=10)
     ap.add_argument('--cpu-sample', type=int, default=8, help='distinct frames per CPU-baseline step')
     ap.add_argument('--cpu-repeat', type=int, default=12, help='passes over the CPU sample (about 13 s of CPU work)')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
-    ap.add_argument('--gather', action='store_true', help='also time the optional NCCL gather of the outputs')
+    ap.add_argument('--no-gather', action='store_true', help='skip the optional NCCL gather of the outputs (N > 1)')
+    ap.add_argument('--no-modes12', action='store_true', help='skip the modes 1 / 2 block')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3
@@ -180,7 +213,8 @@ def main():
     cpus = []
     if world > 1:
         from oflibnumpy_b200 import dist as ofd0
-        cpus = ofd0.bind_to_gpu_cpus(local_rank)      # NUMA-local pinned buffers / copy threads for the e2e leg
+        # disjoint GPU-local cores per rank: pinned buffers / copy threads of the e2e leg do not fight over one core set
+        cpus = ofd0.bind_to_gpu_cpus(local_rank, local_rank, int(os.environ.get('LOCAL_WORLD_SIZE', world)))
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
@@ -257,19 +291,84 @@ def main():
     if dist is not None:
         from oflibnumpy_b200 import dist as ofd
         total_ms, warp_ms, comb_ms = ofd.max_over_ranks([total_ms, warp_ms, comb_ms])
-    gather_ms = None
-    if args.gather and dist is not None:
-        # optional: collect the combined flows of all ranks on rank 0 over NCCL / NVLink (outside the headline timing)
+    # ---------------------------------------------------------------- optional gather of the outputs
+    # The combined flows of all ranks are collected on rank 0 over NCCL / NVLink, in chunks on a side stream, while
+    # this rank's stream already runs the next step (outputs double-buffered). Reported beside the headline: the
+    # gather alone (ms, GB/s into rank 0) and the throughput of steps with their gathers overlapped.
+    gather = None
+    if dist is not None and not args.no_gather:
         import torch
-        full = ofd.gather_frames(out_vecs, world * B, dst=0)      # warm-up: NCCL connects lazily
-        del full
+        ext = torch.cuda.ExternalStream(stream.handle)
+        comm = torch.cuda.Stream()
+        out_vecs2 = DeviceArray.empty((B, H, W, 2), np.float32)
+        bufs = [out_vecs, out_vecs2]
+        chunks = 4
+        full = torch.empty((world * B, H, W, 2), dtype=torch.float32, device='cuda') if rank == 0 else None
+
+        def gather_chunked(src):
+            """Chunk c of every rank's shard goes to rank 0 as one batched send/recv group (the NVSwitch serves all
+            peers at once); chunking lets the first bytes leave before the step's last tile is written."""
+            t = ofd.as_torch(src)
+            per = (B + chunks - 1) // chunks
+            for c in range(chunks):
+                a, b = c * per, min(B, (c + 1) * per)
+                if b <= a:
+                    break
+                ops = []
+                if rank == 0:
+                    full[a:b].copy_(t[a:b], non_blocking=True)
+                    for r in range(1, world):
+                        ops.append(dist.P2POp(dist.irecv, full[r * B + a:r * B + b], r))
+                else:
+                    ops.append(dist.P2POp(dist.isend, t[a:b], 0))
+                for q in dist.batch_isend_irecv(ops):
+                    q.wait()
+
+        with torch.cuda.stream(comm):
+            gather_chunked(out_vecs)                   # warm-up: NCCL connects lazily
+        torch.cuda.synchronize()
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        full = ofd.gather_frames(out_vecs, world * B, dst=0)
-        g1.record()
+        with torch.cuda.stream(comm):
+            g0.record()
+            gather_chunked(out_vecs)
+            g1.record()
         torch.cuda.synchronize()
-        gather_ms = ofd.max_over_ranks([g0.elapsed_time(g1)])[0]
+        alone_ms = ofd.max_over_ranks([g0.elapsed_time(g1)])[0]
+        gsteps = min(args.steps, 8)
+
+        def step_into(dst_vecs):
+            _lib.call('ofk_warp_t', imgs.ptr, _lib.U8, 3, arith, fa.vecs.ptr, -1.0, None, fa.masks.ptr, out_img.ptr,
+                      out_valid.ptr, rule, B, H, W, H, W, 0, 0, 1, stream.handle)
+            _lib.call('ofk_combine3', fa.vecs.ptr, fa.masks.ptr, fb.vecs.ptr, fb.masks.ptr, ord('t'), 0.0, dst_vecs.ptr,
+                      out_mask.ptr, flags.ptr, B, H, W, stream.handle)
+
+        barrier()
+        w0, w1 = Event(), Event()
+        w0.record(stream)
+        done = []
+        for k in range(gsteps):
+            buf = bufs[k % 2]
+            if k >= 2:
+                ext.wait_event(done[k - 2])            # the gather that read this buffer two steps ago has finished
+            step_into(buf)
+            comm.wait_stream(ext)
+            with torch.cuda.stream(comm):
+                gather_chunked(buf)
+                e = torch.cuda.Event()
+                e.record()
+                done.append(e)
+        ext.wait_stream(comm)
+        w1.record(stream)
+        barrier()
+        torch.cuda.synchronize()
+        with_ms = ofd.max_over_ranks([w0.elapsed_ms(w1)])[0] / gsteps
+        gbytes = (world - 1) * B * H * W * 8
+        gather = {"ms_alone": alone_ms, "bytes_into_rank0": gbytes, "gbs_into_rank0": gbytes / alone_ms / 1e6,
+                  "chunks": chunks, "steps": gsteps, "ms_per_step_with_gather": with_ms,
+                  "value_with_gather": world * B * H * W / (with_ms * 1e-3) / 1e6,
+                  "what": "combined flows of all ranks -> rank 0 (batched isend/irecv over NCCL, %d chunks on a side "
+                          "stream, overlapped with the next step; outputs double-buffered)" % chunks}
         del full
     ms_per_step = total_ms / args.steps
     px_step = world * B * H * W
@@ -295,26 +394,40 @@ def main():
             pin['am'][i], pin['bm'][i], pin['img'][i] = am_h[i % n_distinct], bm_h[i % n_distinct], img_h[i % n_distinct]
 
         def e2e_step():
+            of.batch.apply_combine_host(pin['a'], pin['b'], pin['img'], 't', pin['am'], pin['bm'],
+                                        out_images=pin['o_img'], out_valid=pin['o_valid'], out=pin['o_vecs'],
+                                        out_masks=pin['o_mask'], device=local_rank)
+
+        def e2e_two_calls():
             of.batch.apply_flow_host(pin['a'], pin['img'], flow_masks=pin['am'], return_valid_area=True,
                                      out=pin['o_img'], out_valid=pin['o_valid'], device=local_rank)
             of.batch.combine_flows_host(pin['a'], pin['b'], 3, 't', pin['am'], pin['bm'], out=pin['o_vecs'],
                                         out_masks=pin['o_mask'], device=local_rank)
 
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            e2e_step()
-        barrier()
-        dt = (time.perf_counter() - t0) / args.e2e_steps
-        if dist is not None:
-            dt = ofd.max_over_ranks([dt])[0]
+        def timed(fn, steps):
+            fn()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                fn()
+            barrier()
+            dt = (time.perf_counter() - t0) / steps
+            return ofd.max_over_ranks([dt])[0] if dist is not None else dt
+
+        dt2 = timed(e2e_two_calls, max(3, args.e2e_steps // 3))
+        pin['o_vecs'][...] = 0
+        pin['o_img'][...] = 0
+        dt = timed(e2e_step, args.e2e_steps)
         px = EB * H * W
-        h2d = px * (8 + 1 + 3) + px * (8 + 8 + 1 + 1)     # call 1: flow, flow mask, image; call 2: A, B, masks
+        h2d = px * (8 + 1 + 3 + 8 + 1)                    # A, A mask, image, B, B mask: every input once
         d2h = px * (3 + 1) + px * (8 + 1) + EB * 8
         e2e = {"value": world * px / dt / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "frames_per_step": EB, "api": "batch.apply_flow_host + "
-               "batch.combine_flows_host (ofh_warp_t, ofh_combine3), pinned numpy buffers"}
+               "d2h_bytes_per_step": d2h, "frames_per_step": EB, "steps": args.e2e_steps,
+               "api": "batch.apply_combine_host (ofh_apply_combine3: one pass of the pinned ring, A and its mask "
+                      "uploaded once for both kernels), pinned numpy buffers",
+               "h2d_gbs_per_gpu": px * 21 / dt / 1e9, "d2h_gbs_per_gpu": px * 13 / dt / 1e9,
+               "two_calls": {"value": world * px / dt2 / 1e6, "h2d_bytes_per_step": px * 30,
+                             "api": "batch.apply_flow_host + batch.combine_flows_host (round 1: A uploaded twice)"}}
         # results of the two paths must agree
         assert np.array_equal(pin['o_vecs'], out_vecs.frames(0, EB).numpy())
         assert np.array_equal(pin['o_img'], out_img.frames(0, EB).numpy())
@@ -342,23 +455,53 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": "c3_ws_kernel<masks> (ofk_combine3, ref t)", "achieved": comb_gbs, "peak": peak,
-                "unit": "GB/s", "frac": comb_gbs / peak, "traffic": traffic, "peak_source": peak_src,
+                "unit": "GB/s", "frac": comb_gbs / peak, "traffic": traffic,
+                "traffic_source": "profiles/traffic.json: ncu dram bytes per pixel of this kernel captured at batch 64, "
+                                  "scaled to this launch (not measured in this run)", "peak_source": peak_src,
                 "bytes_per_px": BYTES_COMBINE, "ms_per_launch": comb_ms,
                 "other_kernels": {"warp_u8x3_ws_kernel<half_even, geometry mask, flow mask> (ofk_warp_t)": {"achieved": warp_gbs, "frac": warp_gbs / peak,
                                                             "bytes_per_px": BYTES_WARP, "ms_per_launch": warp_ms}},
                 "frac_of_nominal_8TBs": comb_gbs / 8000.0}
+    # ---------------------------------------------------------------- modes 1 / 2 of configuration 4 (device-resident)
+    modes12 = None
+    if not args.no_modes12:
+        MB = min(B, 8)
+        sa = of.FlowBatch._wrap(fa.vecs.frames(0, MB), 't', fa.masks.frames(0, MB))
+        sb = of.FlowBatch._wrap(fb.vecs.frames(0, MB), 't', fb.masks.frames(0, MB))
+        modes12 = {"frames": MB, "what": "FlowBatch.combine_with(mode) on %d of the bench's 1080p frame pairs (2 %% "
+                   "invalid masks, ref 't'), device-resident, one ofk_combine12 chain per call; Mpixel/s" % MB}
+        for mode in (2, 1):
+            sa.combine_with(sb, mode)
+            stream.synchronize()
+            best = 1e30
+            for _ in range(3):
+                e0, e1 = Event(), Event()
+                e0.record(stream)
+                sa.combine_with(sb, mode)
+                e1.record(stream)
+                stream.synchronize()
+                best = min(best, e0.elapsed_ms(e1))
+            modes12["mode%d_t" % mode] = {"ms": best, "value": MB * H * W / best / 1e3}
     cpu = None
     if not args.no_cpu_baseline:
         import cv2
-        frames = cpu_frames(args.cpu_sample)
-        cpu_reference_step(frames, 1)
-        rep = args.cpu_repeat
-        secs = cpu_reference_step(frames, args.cpu_sample, rep)
+        ref = reference_module()
+        frames = cpu_frames(args.cpu_sample, ref)
+        cpu_reference_step(frames, 1, ref=ref)
+        rep = args.cpu_repeat if ref is None else max(1, args.cpu_repeat // 2)
+        secs = cpu_reference_step(frames, args.cpu_sample, rep, ref=ref)
         cpu = {"value": rep * args.cpu_sample * H * W / secs / 1e6, "unit": "Mpixel/s", "cores": cv2.getNumThreads(),
-               "kind": "port", "host_cpus": os.cpu_count(),
-               "sample": "%d frame pairs of 1920x1080 (%d distinct x %d), per-frame loop of the oracle port (cv2.remap on "
-                         "%d threads + single-threaded numpy glue), %.1f s" % (rep * args.cpu_sample, args.cpu_sample, rep,
-                                                                             cv2.getNumThreads(), secs)}
+               "kind": "reference" if ref is not None else "port", "host_cpus": os.cpu_count(),
+               "sample": "%d frame pairs of 1920x1080 (%d distinct x %d), per-frame loop of %s (cv2.remap on %d threads + "
+                         "single-threaded numpy glue), %.1f s" %
+                         (rep * args.cpu_sample, args.cpu_sample, rep,
+                          "oflibnumpy 1.1.1 itself (baseline/_ref)" if ref is not None else "the oracle port",
+                          cv2.getNumThreads(), secs)}
+        if ref is not None:       # the restated port beside it (it skips the per-Flow isfinite / astype copies)
+            pframes = cpu_frames(args.cpu_sample, None)
+            cpu_reference_step(pframes, 1)
+            psecs = cpu_reference_step(pframes, args.cpu_sample, 2)
+            cpu["port_value"] = 2 * args.cpu_sample * H * W / psecs / 1e6
     line = {"metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8+f32", "data": "synthetic",
@@ -369,9 +512,10 @@ def main():
                        "l2": "inputs (%.1f GB per GPU) exceed L2; no flush needed" %
                              (px_rank * (8 + 8 + 1 + 1 + 3) / 1e9)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
-    if gather_ms is not None:
-        line["gather"] = {"ms": gather_ms, "bytes": world * px_rank * 8, "what": "combined flows of all ranks -> rank 0 "
-                          "(isend/irecv over NCCL), outside the timed region"}
+    if modes12 is not None:
+        line["modes12"] = modes12
+    if gather is not None:
+        line["gather"] = gather
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

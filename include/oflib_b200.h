@@ -285,6 +285,14 @@ int ofh_warp_t(const void* payload, int dtype, int C, int arith, const float* fl
                int N, int H, int W, int device);
 int ofh_combine3(const float* A, const uint8_t* Am, const float* B, const uint8_t* Bm, int ref, float thr, float* out,
                  uint8_t* out_mask, int* flags, int N, int H, int W, int device);
+/* `A.apply(image, return_valid_area)` + `A.combine_with(B, 3)` of a batch in ONE pass of the ring: A and its mask are
+ * uploaded once and feed both kernels (the two calls above upload them twice). A is the warping flow (ref 't': sample
+ * at p - A[p]; ref 's' is accepted for the composition, the image warp then samples at p + A[p], i.e.
+ * `A.invert('t').apply(image)`). out_valid may be NULL (no valid area); flags as in ofk_combine3 (may be NULL). */
+int ofh_apply_combine3(const void* image, int dtype, int C, int arith, int mask_rule, const float* A, const uint8_t* Am,
+                       const float* B, const uint8_t* Bm, int ref, float thr, void* out_image, uint8_t* out_valid,
+                       float* out, uint8_t* out_mask, int* flags, int N, int H, int W, int device);
+/* All ofh_* calls leave the caller's current CUDA device unchanged. */
 /* release the internal ring (also done at process exit) */
 int ofh_release(void);
 
@@ -314,6 +322,7 @@ int ofk_rt_device_sync(void);
 int ofk_rt_event_create(void** event);
 int ofk_rt_event_destroy(void* event);
 int ofk_rt_event_record(void* event, ofk_stream_t stream);
+int ofk_rt_stream_wait_event(ofk_stream_t stream, void* event);   /* work queued later on stream waits for event */
 int ofk_rt_event_sync(void* event);
 int ofk_rt_event_elapsed_ms(void* start, void* stop, float* ms);
 /* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */

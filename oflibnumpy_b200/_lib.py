@@ -57,6 +57,7 @@ _SIGNATURES = {
     'ofk_mesh_sample': (_i, [_vp, _f, _i, _vp, _i, _vp, _vp, _f, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'ofh_warp_t': (_i, [_vp, _i, _i, _i, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i]),
     'ofh_combine3': (_i, [_vp, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _i, _i, _i, _i]),
+    'ofh_apply_combine3': (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
     'ofh_release': (_i, []),
     'ofk_rt_device_count': (_i, [C.POINTER(_i)]),
     'ofk_rt_set_device': (_i, [_i]),
@@ -79,6 +80,7 @@ _SIGNATURES = {
     'ofk_rt_event_create': (_i, [C.POINTER(_vp)]),
     'ofk_rt_event_destroy': (_i, [_vp]),
     'ofk_rt_event_record': (_i, [_vp, _vp]),
+    'ofk_rt_stream_wait_event': (_i, [_vp, _vp]),
     'ofk_rt_event_sync': (_i, [_vp]),
     'ofk_rt_event_elapsed_ms': (_i, [_vp, _vp, C.POINTER(_f)]),
     'ofk_rt_launch_count': (C.c_ulonglong, []),

@@ -13,7 +13,7 @@ from .device import DeviceArray
 from .flow import Flow
 from .validation import get_valid_ref, validate_shape, validate_transform_list, DEFAULT_THRESHOLD
 
-__all__ = ['FlowBatch', 'shard_range', 'apply_flow_host', 'combine_flows_host']
+__all__ = ['FlowBatch', 'shard_range', 'apply_flow_host', 'combine_flows_host', 'apply_combine_host']
 
 
 def shard_range(n, rank, world):
@@ -343,3 +343,41 @@ def combine_flows_host(flows_1, flows_2, mode, ref, masks_1=None, masks_2=None, 
               None if bm is None else bm.ctypes.data, ord(ref), DEFAULT_THRESHOLD if thresholded else 0.0,
               out.ctypes.data, out_masks.ctypes.data, flags.ctypes.data, n, h, w, device)
     return out, out_masks
+
+
+def apply_combine_host(flows_1, flows_2, images, ref='t', masks_1=None, masks_2=None, thresholded=False, out_images=None,
+                       out_valid=None, out=None, out_masks=None, device=None):
+    """The pair of calls of a frame pipeline on HOST arrays in one pass (ofh_apply_combine3):
+    ``Flow(flows_1[i], ref, masks_1[i]).apply(images[i], return_valid_area=True)`` and
+    ``....combine_with(Flow(flows_2[i], ref, masks_2[i]), 3)``. ``flows_1`` and ``masks_1`` are uploaded once for both
+    kernels (apply_flow_host + combine_flows_host upload them twice). Returns (images, valid areas, vecs, masks)."""
+    ref = get_valid_ref(ref)
+    a, b = _c(flows_1, np.float32), _c(flows_2, np.float32)
+    images = _c(images)
+    if a.shape != b.shape or a.ndim != 4 or a.shape[3] != 2:
+        raise ValueError("Error combining flows: Flow fields need to have the same shape (N,H,W,2)")
+    if images.ndim == 3:
+        images = images[..., None]
+    n, h, w = a.shape[:3]
+    if images.shape[:3] != (n, h, w):
+        raise ValueError("Error applying flow: Flow shape does not match target shape")
+    code = _ops.dtype_code(images.dtype)
+    arith, rule = _ops.promoted_rule(images.dtype, False)
+    am = None if masks_1 is None else _c(masks_1, np.bool_)
+    bm = None if masks_2 is None else _c(masks_2, np.bool_)
+    for name, arr, shape, dt in (('out_images', out_images, images.shape, images.dtype),
+                                 ('out_valid', out_valid, (n, h, w), np.bool_), ('out', out, a.shape, np.float32),
+                                 ('out_masks', out_masks, (n, h, w), np.bool_)):
+        if arr is not None:
+            _check_out(arr, shape, dt, name)
+    out_images = np.empty_like(images) if out_images is None else out_images
+    out_valid = np.empty((n, h, w), np.bool_) if out_valid is None else out_valid
+    out = np.empty_like(a) if out is None else out
+    out_masks = np.empty((n, h, w), np.bool_) if out_masks is None else out_masks
+    flags = np.empty((n, 2), np.int32)
+    device = dev.get_device() if device is None else device
+    _lib.call('ofh_apply_combine3', images.ctypes.data, code, images.shape[3], arith, rule, a.ctypes.data,
+              None if am is None else am.ctypes.data, b.ctypes.data, None if bm is None else bm.ctypes.data, ord(ref),
+              DEFAULT_THRESHOLD if thresholded else 0.0, out_images.ctypes.data, out_valid.ctypes.data, out.ctypes.data,
+              out_masks.ctypes.data, flags.ctypes.data, n, h, w, device)
+    return out_images, out_valid, out, out_masks

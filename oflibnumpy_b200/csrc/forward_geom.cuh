@@ -98,6 +98,37 @@ OFK_HD double incircle(const P2& a, const P2& b, const P2& c, const P2& d) {
     return dfma(a2, m2, dfma(ax, m0, -dmul(ay, m1)));
 }
 
+// In-circle test with a consistent answer for co-circular points: +1 = d inside the circumcircle of the positively
+// oriented (a, b, c), -1 = outside. A determinant that vanishes to within its rounding is decided by a symbolic
+// perturbation (every point lifted by an infinitesimal that shrinks rapidly with its id: the point with the smallest
+// id decides, through its cofactor). The perturbed points are in general position, so every search sees the SAME
+// triangulation of a co-circular set -- what keeps the point-location walk from cycling on exact lattices (similarity
+// transforms of the pixel grid, float32 positions).
+OFK_HD int incircle_sign(const P2& a, const P2& b, const P2& c, const P2& d, uint32_t ia, uint32_t ib, uint32_t ic_,
+                         uint32_t id) {
+    const double ax = dsub(a.x, d.x), ay = dsub(a.y, d.y), bx = dsub(b.x, d.x), by = dsub(b.y, d.y),
+                 cx = dsub(c.x, d.x), cy = dsub(c.y, d.y);
+    const double a2 = dfma(ax, ax, dmul(ay, ay)), b2 = dfma(bx, bx, dmul(by, by)), c2 = dfma(cx, cx, dmul(cy, cy));
+    const double m0 = dfma(by, c2, -dmul(b2, cy));
+    const double m1 = dfma(bx, c2, -dmul(b2, cx));
+    const double m2 = dfma(bx, cy, -dmul(by, cx));
+    const double det = dfma(a2, m2, dfma(ax, m0, -dmul(ay, m1)));
+    // rounding of the expansion: a few ulps of the largest term
+    const double mag = fabs(a2 * m2) + fabs(ax * m0) + fabs(ay * m1);
+    if (fabs(det) > 4e-15 * mag) return det > 0 ? 1 : -1;
+    // cofactors of the lifted coordinate: +orient(b,c,d), -orient(a,c,d), +orient(a,b,d), -orient(a,b,c)
+    uint32_t ids[4] = {ia, ib, ic_, id};
+    double cof[4] = {orient(b, c, d), -orient(a, c, d), orient(a, b, d), -orient(a, b, c)};
+    for (int round = 0; round < 4; ++round) {
+        int m = 0;
+        for (int k = 1; k < 4; ++k)
+            if (ids[k] < ids[m]) m = k;
+        if (cof[m] != 0.0) return cof[m] > 0 ? 1 : -1;
+        ids[m] = 0xffffffffu;
+    }
+    return -1;
+}
+
 // Edge function of point q against the edge u -> v, u being the endpoint with the SMALLER site index: both triangles
 // sharing an edge evaluate the very same expression; the one traversing the edge as u -> v owns F == 0.
 OFK_HD double edge_canon(const P2& u, const P2& v, double qx, double qy) {

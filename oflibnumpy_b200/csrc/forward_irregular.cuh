@@ -49,6 +49,9 @@ struct SiteGrid {
 
 OFK_HD int grid_bins(int extent) { return (extent + BIN - 1) >> BIN_SHIFT; }
 OFK_HD int grid_coarse(int nb) { return (nb + (1 << COARSE_SHIFT) - 1) >> COARSE_SHIFT; }
+// slots of the bin table and the slot of a fine bin (row-major over the frame)
+OFK_HD int grid_slots(int nbx, int nby) { return nbx * nby; }
+OFK_HD int bin_index(int nbx, int bx, int by) { return by * nbx + bx; }
 
 OFK_HD P2 site_pos(const SiteGrid& g, uint32_t id) {
     const int row = (int)(id / (uint32_t)g.W), col = (int)(id - (uint32_t)row * (uint32_t)g.W);
@@ -64,9 +67,12 @@ OFK_HD int bin_coord(double v, int nb) {
 
 template <class F>
 OFK_HD void scan_bin(const SiteGrid& g, int bx, int by, F& f) {
-    const int b = by * g.nbx + bx;
+    const int b = bin_index(g.nbx, bx, by);
     const uint32_t s0 = g.bin_start[b], s1 = g.bin_start[b + 1];
-    for (uint32_t s = s0; s < s1; ++s) f(g.sites[s]);
+    for (uint32_t s = s0; s < s1; ++s) {
+        const uint32_t id = g.sites[s];
+        f(id, site_pos(g, id));
+    }
 }
 
 // all sites of the bins at Chebyshev distance r from (cx, cy)
@@ -105,9 +111,8 @@ struct NearestScan {
     P2 p;
     uint32_t exclude, best;
     double best_d2;
-    OFK_HD void operator()(uint32_t s) {
+    OFK_HD void operator()(uint32_t s, const P2& ps) {
         if (s == exclude) return;
-        const P2 ps = site_pos(g, s);
         const double dx = dsub(ps.x, p.x), dy = dsub(ps.y, p.y), d2 = dfma(dx, dx, dmul(dy, dy));
         if (d2 < best_d2 || (d2 == best_d2 && s < best)) {
             best_d2 = d2;
@@ -159,18 +164,17 @@ struct ApexScan {
         pbest = ps;
         circ = circumcircle(pa, pb, ps);
     }
-    OFK_HD void operator()(uint32_t s) {
+    OFK_HD void operator()(uint32_t s, const P2& ps) {
         ++visited;
         OFK_COUNT(3);   // sites looked at (all searches)
         if (s == a || s == b || s == best) return;
-        const P2 ps = site_pos(g, s);
         if (!(orient(pa, pb, ps) > 0)) return;
         if (best == NO_SITE) {
             take(s, ps);
             return;
         }
-        const double ic = incircle(pa, pb, pbest, ps);   // > 0: s inside the circle of the current apex -> better
-        if (ic > 0 || (ic == 0 && s < best)) take(s, ps);
+        // s inside the circle of the current apex -> better (co-circular sets: consistently perturbed)
+        if (incircle_sign(pa, pb, pbest, ps, a, b, best, s) > 0) take(s, ps);
     }
     // can the block of bins [bx0, bx1] x [by0, by1] hold a site that beats the current apex? (conservative)
     OFK_HD bool may_hold_better(int bx0, int bx1, int by0, int by1) const {
@@ -234,10 +238,7 @@ OFK_HD void coop_reduce(ApexScan& sc, const Coop& coop) {
         op.y = __shfl_xor_sync(0xffffffffu, sc.pbest.y, o);
         if (ob == NO_SITE || ob == sc.best) continue;
         bool take = sc.best == NO_SITE;
-        if (!take) {
-            const double ic = incircle(sc.pa, sc.pb, sc.pbest, op);
-            take = ic > 0 || (ic == 0 && ob < sc.best);
-        }
+        if (!take) take = incircle_sign(sc.pa, sc.pb, sc.pbest, op, sc.a, sc.b, sc.best, ob) > 0;
         if (take) {
             sc.best = ob;
             sc.pbest = op;
@@ -293,7 +294,7 @@ OFK_HD uint32_t apex_site_impl(const SiteGrid& g, uint32_t a, uint32_t b, const 
             if (!sc.may_hold_better(fx0, fx1, fy0, fy1)) continue;
             for (int by = fy0; by <= fy1; ++by) {
                 for (int bx = fx0; bx <= fx1; ++bx) {
-                    const int bi = by * g.nbx + bx;
+                    const int bi = bin_index(g.nbx, bx, by);
                     if (g.bin_start[bi] == g.bin_start[bi + 1]) continue;
                     if (bx >= cx - NEAR_RINGS && bx <= cx + NEAR_RINGS && by >= cy - NEAR_RINGS && by <= cy + NEAR_RINGS)
                         continue;   // already scanned
@@ -325,7 +326,7 @@ OFK_HD uint32_t apex_site_impl(const SiteGrid& g, uint32_t a, uint32_t b, const 
                 if (!sc.may_hold_better(fx0, fx1, fy0, fy1)) continue;
                 for (int by = fy0; by <= fy1; ++by) {
                     for (int bx = fx0; bx <= fx1; ++bx) {
-                        const int bi = by * g.nbx + bx;
+                        const int bi = bin_index(g.nbx, bx, by);
                         if (g.bin_start[bi] == g.bin_start[bi + 1]) continue;
                         if (bx >= cx - NEAR_RINGS && bx <= cx + NEAR_RINGS && by >= cy - NEAR_RINGS &&
                             by <= cy + NEAR_RINGS)
@@ -351,7 +352,7 @@ OFK_HD uint32_t apex_site(const SiteGrid& g, uint32_t a, uint32_t b, const P2& p
 
 constexpr int LOC_FOUND = 0, LOC_OUTSIDE = 1, LOC_FAILED = 2, LOC_HEAVY = 3;
 constexpr int NO_BUDGET = 0x7fffffff;
-constexpr int LOC_MAX_STEPS = 256;
+constexpr int LOC_MAX_STEPS = 512;
 
 // The walk: from the Delaunay edge a -> b (q on its left or on its line) to the triangle that contains q.
 OFK_HD int locate_walk(const SiteGrid& g, const P2& q, uint32_t a, uint32_t b, P2 pa, P2 pb, uint32_t (&ids)[3],
@@ -529,6 +530,87 @@ inline void hull_build_serial(const SiteGrid& g, uint32_t nsites, const HullDirs
         for (int i = 0; i < h.m; ++i) h.slack[i] = fmin(h.slack[i], hull_edge_orient(h, i, p));
     }
     for (int i = 0; i < h.m; ++i) hull_edge_line(h, i);
+}
+
+// ---------------------------------------------------------------------------------------------- the exact hull
+// Pixels outside the convex hull of the sites are 0 / invalid. A search only finds that out when it reaches a hull
+// edge and sweeps the whole half plane beyond it for an apex that does not exist -- the most expensive search there
+// is, repeated by every pixel of the band just outside the hull. So the hull itself is built once per frame (gift
+// wrapping over the few sites on or beyond the inner polygon) and uncovered pixels are tested against it first.
+constexpr int HULL_MAX = 1024;        // hull vertices kept per frame; more: no exact test (the searches decide)
+constexpr int OUTER_CAP = 65536;      // candidate sites per frame for the wrap; more: no exact test
+
+struct HullPoly {
+    int m, ok;
+    double x[HULL_MAX], y[HULL_MAX];
+};
+
+// a site on or beyond an edge of the inner polygon can be a hull vertex, a site strictly inside it cannot
+OFK_HD bool hull_outer_candidate(const HullInfo& h, const P2& p) {
+    if (h.m == 0) return true;
+    for (int i = 0; i < h.m; ++i)
+        if (hull_edge_orient(h, i, p) <= 0) return true;
+    return false;
+}
+
+// start of the wrap: the lexicographically smallest position (always a hull vertex)
+OFK_HD bool wrap_start_better(const P2& q, uint32_t qid, const P2& b, uint32_t bid) {
+    if (bid == NO_SITE) return true;
+    if (q.x != b.x) return q.x < b.x;
+    if (q.y != b.y) return q.y < b.y;
+    return qid < bid;
+}
+
+// gift wrapping with the interior on the left: from pivot p, q is a better next vertex than b when it lies to the
+// right of p -> b; among collinear candidates the farthest one wins (hull vertices only, no points inside edges)
+OFK_HD bool wrap_better(const P2& p, const P2& q, uint32_t qid, const P2& b, uint32_t bid) {
+    if (q.x == p.x && q.y == p.y) return false;
+    if (bid == NO_SITE) return true;
+    const double o = orient(p, b, q);
+    if (o != 0.0) return o < 0;
+    const double qx = dsub(q.x, p.x), qy = dsub(q.y, p.y), bx = dsub(b.x, p.x), by = dsub(b.y, p.y);
+    const double dq = dfma(qx, qx, dmul(qy, qy)), db = dfma(bx, bx, dmul(by, by));
+    // the same direction from p: farther wins. Opposite directions cannot both be candidates of a hull pivot.
+    if (dq != db) return dq > db;
+    return qid < bid;
+}
+
+OFK_HD bool inside_hull(const HullPoly& hp, const P2& q) {
+    for (int i = 0; i < hp.m; ++i) {
+        const int k = i + 1 == hp.m ? 0 : i + 1;
+        P2 u, v;
+        u.x = hp.x[i]; u.y = hp.y[i];
+        v.x = hp.x[k]; v.y = hp.y[k];
+        if (orient(u, v, q) < 0) return false;
+    }
+    return true;
+}
+
+// serial reference of the wrap (host build); pos / ids: the outer candidates
+inline void hull_wrap_serial(const P2* pos, const uint32_t* ids, int n, HullPoly& hp) {
+    hp.m = 0;
+    hp.ok = 0;
+    if (n < 3 || n > OUTER_CAP) return;
+    int start = -1;
+    for (int k = 0; k < n; ++k)
+        if (start < 0 || wrap_start_better(pos[k], ids[k], pos[start], ids[start])) start = k;
+    int cur = start;
+    for (;;) {
+        if (hp.m >= HULL_MAX) {
+            hp.m = 0;
+            return;
+        }
+        hp.x[hp.m] = pos[cur].x;
+        hp.y[hp.m] = pos[cur].y;
+        ++hp.m;
+        int best = -1;
+        for (int k = 0; k < n; ++k)
+            if (wrap_better(pos[cur], pos[k], ids[k], best < 0 ? pos[cur] : pos[best], best < 0 ? NO_SITE : ids[best]))
+                best = k;
+        if (best < 0 || best == start) break;
+        cur = best;
+    }
+    hp.ok = hp.m >= 3 ? 1 : 0;
 }
 
 // a valid site is a boundary site when it sits on the frame border or one of its 8 neighbours has been removed

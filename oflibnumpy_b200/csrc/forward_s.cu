@@ -552,13 +552,14 @@ __global__ void __launch_bounds__(256) irr_sites_kernel(const IrrArgs A) {
     const float2 f = __ldg(reinterpret_cast<const float2*>(A.flow) + frame + id);
     const P2 p = displaced(f.x, f.y, row, col, A.sign);
     const int bx = bin_coord(p.x, A.nbx), by = bin_coord(p.y, A.nby);
-    const int nb = A.nbx * A.nby;
+    const int nb = grid_slots(A.nbx, A.nby);
     uint32_t* bins = A.bins + (size_t)n * (nb + 1);
+    const int bi = bin_index(A.nbx, bx, by);
     if (PASS == 0) {
-        atomicAdd(bins + by * A.nbx + bx, 1u);
+        atomicAdd(bins + bi, 1u);
         atomicAdd(A.coarse + (size_t)n * A.ncx * A.ncy + (by >> COARSE_SHIFT) * A.ncx + (bx >> COARSE_SHIFT), 1u);
     } else {
-        const uint32_t slot = atomicSub(bins + by * A.nbx + bx, 1u) - 1u;
+        const uint32_t slot = atomicSub(bins + bi, 1u) - 1u;
         A.sites[frame + slot] = id;
     }
 }
@@ -734,6 +735,129 @@ __global__ void hull_frame_kernel(const HullArgs A) {
     }
 }
 
+// ---- exact hull: candidates on / beyond the inner polygon, then gift wrapping (one CTA per frame)
+struct OuterArgs {
+    const float* flow;
+    const int* folded;
+    const uint32_t* bins;
+    const uint32_t* sites;
+    const HullInfo* info;
+    P2* opos;              // [N][OUTER_CAP]
+    uint32_t* oids;        // [N][OUTER_CAP]
+    unsigned int* ocount;  // [N]
+    HullPoly* poly;        // [N]
+    float sign;
+    int H, W, nb;
+};
+
+__global__ void __launch_bounds__(256) hull_outer_kernel(const OuterArgs A) {
+    const int n = blockIdx.y;
+    if (A.folded[n]) return;
+    const uint32_t total = A.bins[(size_t)n * (A.nb + 1) + A.nb];
+    __shared__ HullInfo s_info;
+    {
+        const int words = sizeof(HullInfo) / 4;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(A.info + n);
+        for (int k = threadIdx.x; k < words; k += 256) reinterpret_cast<uint32_t*>(&s_info)[k] = src[k];
+    }
+    __syncthreads();
+    SiteGrid g;
+    g.W = A.W;
+    g.H = A.H;
+    g.sites = A.sites + (size_t)n * A.H * A.W;
+    g.flow = A.flow + 2 * (size_t)n * A.H * A.W;
+    g.sign = A.sign;
+    for (uint32_t s = blockIdx.x * 256 + threadIdx.x; s < total; s += gridDim.x * 256) {
+        const uint32_t id = g.sites[s];
+        const P2 p = site_pos(g, id);
+        if (!hull_outer_candidate(s_info, p)) continue;
+        const unsigned slot = atomicAdd(A.ocount + n, 1u);
+        if (slot < (unsigned)OUTER_CAP) {
+            A.opos[(size_t)n * OUTER_CAP + slot] = p;
+            A.oids[(size_t)n * OUTER_CAP + slot] = id;
+        }
+    }
+}
+
+struct WrapCand {
+    P2 p;
+    uint32_t id;
+};
+
+template <class Better>
+__device__ __forceinline__ WrapCand wrap_block_reduce(WrapCand c, Better better, WrapCand* s_warp) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 16; o > 0; o >>= 1) {
+        WrapCand other;
+        other.p.x = __shfl_xor_sync(0xffffffffu, c.p.x, o);
+        other.p.y = __shfl_xor_sync(0xffffffffu, c.p.y, o);
+        other.id = __shfl_xor_sync(0xffffffffu, c.id, o);
+        if (other.id != NO_SITE && (c.id == NO_SITE || better(other, c))) c = other;
+    }
+    __syncthreads();
+    if (lane == 0) s_warp[warp] = c;
+    __syncthreads();
+    WrapCand r = s_warp[0];
+    for (int k = 1; k < 8; ++k) {
+        const WrapCand other = s_warp[k];
+        if (other.id != NO_SITE && (r.id == NO_SITE || better(other, r))) r = other;
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(256) hull_wrap_kernel(const OuterArgs A) {
+    const int n = blockIdx.x;
+    HullPoly& hp = A.poly[n];
+    if (threadIdx.x == 0) {
+        hp.m = 0;
+        hp.ok = 0;
+    }
+    if (A.folded[n]) return;
+    const unsigned cnt = A.ocount[n];
+    if (cnt < 3 || cnt > (unsigned)OUTER_CAP) return;
+    const P2* pos = A.opos + (size_t)n * OUTER_CAP;
+    const uint32_t* ids = A.oids + (size_t)n * OUTER_CAP;
+    __shared__ WrapCand s_warp[8];
+    WrapCand c;
+    c.id = NO_SITE;
+    c.p.x = c.p.y = 0.0;
+    for (unsigned k = threadIdx.x; k < cnt; k += 256)
+        if (wrap_start_better(pos[k], ids[k], c.p, c.id)) {
+            c.p = pos[k];
+            c.id = ids[k];
+        }
+    const WrapCand start = wrap_block_reduce(
+        c, [](const WrapCand& q, const WrapCand& b) { return wrap_start_better(q.p, q.id, b.p, b.id); }, s_warp);
+    WrapCand cur = start;
+    int m = 0;
+    for (;;) {
+        if (m >= HULL_MAX) return;   // hp.ok stays 0: the searches decide
+        if (threadIdx.x == 0) {
+            hp.x[m] = cur.p.x;
+            hp.y[m] = cur.p.y;
+        }
+        ++m;
+        WrapCand best;
+        best.id = NO_SITE;
+        best.p = cur.p;
+        for (unsigned k = threadIdx.x; k < cnt; k += 256)
+            if (wrap_better(cur.p, pos[k], ids[k], best.p, best.id)) {
+                best.p = pos[k];
+                best.id = ids[k];
+            }
+        const P2 pivot = cur.p;
+        best = wrap_block_reduce(
+            best, [pivot](const WrapCand& q, const WrapCand& b) { return wrap_better(pivot, q.p, q.id, b.p, b.id); },
+            s_warp);
+        if (best.id == NO_SITE || best.id == start.id) break;
+        cur = best;
+    }
+    if (threadIdx.x == 0) {
+        hp.m = m;
+        hp.ok = m >= 3 ? 1 : 0;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------- uncovered pixels
 struct SolveArgs {
     const float* payload;
@@ -744,6 +868,7 @@ struct SolveArgs {
     const uint32_t* coarse;
     const uint32_t* sites;
     const HullInfo* info;
+    const HullPoly* poly;
     float* out;
     uint8_t* out_mask;
     const uint8_t* cover;
@@ -843,12 +968,13 @@ __global__ void __launch_bounds__(256) irr_solve_kernel(const SolveArgs A) {
     g.nby = A.nby;
     g.ncx = A.ncx;
     g.ncy = A.ncy;
-    const int nb = A.nbx * A.nby;
+    const int nb = grid_slots(A.nbx, A.nby);
     g.bin_start = A.bins + (size_t)n * (nb + 1);
     g.coarse = A.coarse + (size_t)n * A.ncx * A.ncy;
     g.sites = A.sites + frame;
     g.flow = A.flow + 2 * frame;
     g.sign = A.sign;
+    const HullPoly& poly = A.poly[n];     // read through L1 / L2: only the pixels next to the hull get that far
     unsigned long long tally[4] = {0, 0, 0, 0};
     bool any_heavy = false;
     // ---- pass 1: one pixel per thread
@@ -861,7 +987,7 @@ __global__ void __launch_bounds__(256) irr_solve_kernel(const SolveArgs A) {
         uint32_t vid[3];
         double w[3];
         int st;
-        if (hull_rejects(s_hull, q)) {
+        if (hull_rejects(s_hull, q) || (poly.ok && !inside_hull(poly, q))) {
             st = LOC_OUTSIDE;
             ++tally[3];
         } else {
@@ -911,7 +1037,7 @@ __global__ void __launch_bounds__(256) irr_heavy_kernel(const SolveArgs A) {
         g.nby = A.nby;
         g.ncx = A.ncx;
         g.ncy = A.ncy;
-        const int nb = A.nbx * A.nby;
+        const int nb = grid_slots(A.nbx, A.nby);
         g.bin_start = A.bins + (size_t)n * (nb + 1);
         g.coarse = A.coarse + (size_t)n * A.ncx * A.ncy;
         g.sites = A.sites + frame;
@@ -957,7 +1083,7 @@ __global__ void __launch_bounds__(256) irr_heavy_kernel(const SolveArgs A) {
 
 // ------------------------------------------------------------------------------------------------- workspace layout
 struct WsLayout {
-    size_t sites, cover, heavy, heavy_count, bins, coarse, hullws, hullinfo, folded, chunks, total;
+    size_t sites, cover, heavy, heavy_count, bins, coarse, hullws, hullinfo, folded, chunks, opos, oids, ocount, poly, total;
     size_t zero_begin, zero_bytes;   // region cleared before every call (bins, coarse, hull keys, folded flags)
     int nbx, nby, ncx, ncy, nb, nc;
 };
@@ -970,7 +1096,7 @@ static WsLayout ws_layout(int N, int H, int W) {
     L.nby = grid_bins(H);
     L.ncx = grid_coarse(L.nbx);
     L.ncy = grid_coarse(L.nby);
-    L.nb = L.nbx * L.nby;
+    L.nb = grid_slots(L.nbx, L.nby);
     L.nc = L.ncx * L.ncy;
     const size_t px = (size_t)N * H * W;
     size_t o = 0;
@@ -982,6 +1108,12 @@ static WsLayout ws_layout(int N, int H, int W) {
     o = align_up(o + px + 8, 256);
     L.hullinfo = o;
     o = align_up(o + (size_t)N * sizeof(HullInfo), 256);
+    L.opos = o;
+    o = align_up(o + (size_t)N * OUTER_CAP * sizeof(P2), 256);
+    L.oids = o;
+    o = align_up(o + (size_t)N * OUTER_CAP * 4, 256);
+    L.poly = o;
+    o = align_up(o + (size_t)N * sizeof(HullPoly), 256);
     L.zero_begin = o;
     L.bins = o;
     o = align_up(o + (size_t)N * (L.nb + 1) * 4, 256);
@@ -995,6 +1127,8 @@ static WsLayout ws_layout(int N, int H, int W) {
     o = align_up(o + (size_t)N * ((L.nb + SCAN_CHUNK - 1) / SCAN_CHUNK) * 4, 256);
     L.heavy_count = o;
     o = align_up(o + 4, 256);
+    L.ocount = o;
+    o = align_up(o + (size_t)N * 4, 256);
     L.zero_bytes = o - L.zero_begin;
     L.total = o;
     return L;
@@ -1179,7 +1313,16 @@ extern "C" int ofk_forward_s_ex(const float* payload, int C, const float* flow, 
     hull_frame_kernel<1><<<N, 32, 0, st>>>(Hh);
     OFK_LAUNCHED();
 
-    SolveArgs S{payload, flow, payload_mask, d_folded, d_bins, d_coarse, d_sites, d_info, out, out_mask, d_cover,
+    OuterArgs O{flow, d_folded, d_bins, d_sites, d_info, reinterpret_cast<fwd::P2*>(base + L.opos),
+                reinterpret_cast<uint32_t*>(base + L.oids), reinterpret_cast<unsigned int*>(base + L.ocount),
+                reinterpret_cast<fwd::HullPoly*>(base + L.poly), flow_sign, H, W, L.nb};
+    hull_outer_kernel<<<dim3((unsigned)std::min<long long>((cand + 255) / 256, 64), N), 256, 0, st>>>(O);
+    OFK_LAUNCHED();
+    hull_wrap_kernel<<<N, 256, 0, st>>>(O);
+    OFK_LAUNCHED();
+
+    SolveArgs S{payload, flow, payload_mask, d_folded, d_bins, d_coarse, d_sites, d_info,
+                reinterpret_cast<const fwd::HullPoly*>(base + L.poly), out, out_mask, d_cover,
                 reinterpret_cast<unsigned long long*>(base + L.heavy),
                 reinterpret_cast<unsigned int*>(base + L.heavy_count), flow_sign, C, strict, H, W, L.nbx, L.nby, L.ncx,
                 L.ncy};

@@ -191,6 +191,10 @@ extern "C" int ofk_rt_event_record(void* ev, ofk_stream_t s) {
     OFK_CUDA(cudaEventRecord((cudaEvent_t)ev, as_stream(s)));
     return OFK_OK;
 }
+extern "C" int ofk_rt_stream_wait_event(ofk_stream_t s, void* ev) {
+    OFK_CUDA(cudaStreamWaitEvent(as_stream(s), (cudaEvent_t)ev, 0));
+    return OFK_OK;
+}
 extern "C" int ofk_rt_event_sync(void* ev) {
     OFK_CUDA(cudaEventSynchronize((cudaEvent_t)ev));
     return OFK_OK;
@@ -273,6 +277,20 @@ int ring_prepare(int device, size_t bytes_per_slot) {
     return OFK_OK;
 }
 
+// ofh_* calls run on the device they are given and leave the caller's current device as they found it.
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() {
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            cudaGetLastError();
+            prev = -1;
+        }
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 // Leaves no transfer in flight when an ofh_* call returns, on the error paths too: the copies read and write the
 // caller's buffers, which may be freed as soon as the call is over.
 struct DrainRing {
@@ -324,6 +342,7 @@ extern "C" int ofh_warp_t(const void* payload, int dtype, int C, int arith, cons
     OFK_CHECK_ARG(dtype >= OFK_U8 && dtype <= OFK_F64, "ofh_warp_t: unknown dtype %d", dtype);
     if (N == 0) return OFK_OK;
     std::lock_guard<std::mutex> lk(g_ring.mu);
+    DeviceGuard restore_device;
     const size_t px = (size_t)H * W, es = esize(dtype);
     const size_t b_flow = px * 8, b_pay = px * C * es, b_m = px;
     const size_t per_frame = pad256(b_flow) + 2 * pad256(b_pay) + 3 * pad256(b_m);
@@ -390,6 +409,7 @@ extern "C" int ofh_combine3(const float* A, const uint8_t* Am, const float* B, c
     OFK_CHECK_ARG(A && B && out && out_mask && N >= 0 && H > 0 && W > 0, "ofh_combine3: bad arguments");
     if (N == 0) return OFK_OK;
     std::lock_guard<std::mutex> lk(g_ring.mu);
+    DeviceGuard restore_device;
     const size_t px = (size_t)H * W;
     const size_t b_flow = px * 8, b_m = px;
     const size_t per_frame = 3 * pad256(b_flow) + 3 * pad256(b_m) + 256;
@@ -464,8 +484,109 @@ extern "C" int ofh_combine3(const float* A, const uint8_t* Am, const float* B, c
     return OFK_OK;
 }
 
+// The pair of calls a frame pipeline makes per batch -- `A.apply(image, return_valid_area=True)` and
+// `A.combine_with(B, 3)` -- on host buffers in one pass of the ring: A and its mask are uploaded ONCE and feed both
+// kernels of a chunk (two separate calls upload them twice: 30 bytes per pixel in, this 21).
+extern "C" int ofh_apply_combine3(const void* image, int dtype, int C, int arith, int mask_rule, const float* A,
+                                  const uint8_t* Am, const float* B, const uint8_t* Bm, int ref, float thr,
+                                  void* out_image, uint8_t* out_valid, float* out, uint8_t* out_mask, int* flags, int N,
+                                  int H, int W, int device) {
+    OFK_CHECK_ARG(image && A && B && out_image && out && out_mask && N >= 0 && H > 0 && W > 0 && C > 0,
+                  "ofh_apply_combine3: bad arguments");
+    OFK_CHECK_ARG(dtype >= OFK_U8 && dtype <= OFK_F64, "ofh_apply_combine3: unknown dtype %d", dtype);
+    OFK_CHECK_ARG(ref == 's' || ref == 't', "ofh_apply_combine3: ref must be 's' or 't'");
+    if (N == 0) return OFK_OK;
+    std::lock_guard<std::mutex> lk(g_ring.mu);
+    DeviceGuard restore_device;
+    const size_t px = (size_t)H * W, es = esize(dtype);
+    const size_t b_flow = px * 8, b_m = px, b_img = px * C * es;
+    const size_t per_frame = 3 * pad256(b_flow) + 4 * pad256(b_m) + 2 * pad256(b_img) + 256;
+    int cf = (int)(kChunkTarget / per_frame);
+    if (cf < 1) cf = 1;
+    if (cf > N) cf = N;
+    int rc = ring_prepare(device, per_frame * cf + 8192);
+    if (rc != OFK_OK) return rc;
+    DrainRing drain_on_exit;
+    struct Pending {
+        Slot* slot;
+        int n0, cn;
+        void* dOi;
+        uint8_t* dOv;
+        float* dO;
+        uint8_t* dOm;
+        int* dF;
+    };
+    Pending prev = {};
+    bool have_prev = false;
+    auto download = [&](const Pending& p) -> int {
+        Slot& s = *p.slot;
+        OFH_COPY_OUT((char*)out_image + (size_t)p.n0 * b_img, p.dOi, b_img * p.cn);
+        if (p.dOv) OFH_COPY_OUT(out_valid + (size_t)p.n0 * px, p.dOv, b_m * p.cn);
+        OFH_COPY_OUT(out + (size_t)p.n0 * px * 2, p.dO, b_flow * p.cn);
+        OFH_COPY_OUT(out_mask + (size_t)p.n0 * px, p.dOm, b_m * p.cn);
+        if (flags) {
+            OFK_CUDA(cudaMemcpyAsync(s.hflags, p.dF, sizeof(int) * 2 * p.cn, cudaMemcpyDeviceToHost, s.st));
+            s.flags_dst = flags + (size_t)p.n0 * 2;
+            s.flags_n = (size_t)2 * p.cn;
+        }
+        return OFK_OK;
+    };
+    int chunk = 0;
+    for (int n0 = 0; n0 < N; n0 += cf, ++chunk) {
+        Slot& s = g_ring.slot[chunk % kSlots];
+        const int cn = (N - n0 < cf) ? (N - n0) : cf;
+        OFK_CUDA(cudaStreamSynchronize(s.st));
+        s.deliver();
+        s.used = 0;
+        if (flags && s.hflags_cap < (size_t)2 * cf) {
+            if (s.hflags) OFK_CUDA(cudaFreeHost(s.hflags));
+            s.hflags = nullptr;
+            s.hflags_cap = 0;
+            OFK_CUDA(cudaHostAlloc((void**)&s.hflags, sizeof(int) * 2 * cf, cudaHostAllocDefault));
+            s.hflags_cap = (size_t)2 * cf;
+        }
+        float* dA = (float*)s.take(b_flow * cn);
+        float* dB = (float*)s.take(b_flow * cn);
+        float* dO = (float*)s.take(b_flow * cn);
+        void* dI = s.take(b_img * cn);
+        void* dOi = s.take(b_img * cn);
+        uint8_t* dAm = Am ? (uint8_t*)s.take(b_m * cn) : nullptr;
+        uint8_t* dBm = Bm ? (uint8_t*)s.take(b_m * cn) : nullptr;
+        uint8_t* dOm = (uint8_t*)s.take(b_m * cn);
+        uint8_t* dOv = out_valid ? (uint8_t*)s.take(b_m * cn) : nullptr;
+        int* dF = (int*)s.take(sizeof(int) * 2 * cn);
+        OFH_COPY_IN(dA, A + (size_t)n0 * px * 2, b_flow * cn);
+        if (dAm) OFH_COPY_IN(dAm, Am + (size_t)n0 * px, b_m * cn);
+        OFH_COPY_IN(dI, (const char*)image + (size_t)n0 * b_img, b_img * cn);
+        // the image warp starts while B is still on its way
+        rc = ofk_warp_t(dI, dtype, C, arith, dA, ref == 't' ? -1.0f : 1.0f, nullptr, dOv ? dAm : nullptr, dOi, dOv,
+                        mask_rule, cn, H, W, H, W, 0, 0, 1, (ofk_stream_t)s.st);
+        if (rc != OFK_OK) return rc;
+        OFH_COPY_IN(dB, B + (size_t)n0 * px * 2, b_flow * cn);
+        if (dBm) OFH_COPY_IN(dBm, Bm + (size_t)n0 * px, b_m * cn);
+        rc = ofk_combine3(dA, dAm, dB, dBm, ref, thr, dO, dOm, dF, cn, H, W, (ofk_stream_t)s.st);
+        if (rc != OFK_OK) return rc;
+        if (have_prev) {                                 // see ofh_warp_t: downloads trail the launches by one chunk
+            rc = download(prev);
+            if (rc != OFK_OK) return rc;
+        }
+        prev = {&s, n0, cn, dOi, dOv, dO, dOm, dF};
+        have_prev = true;
+    }
+    if (have_prev) {
+        rc = download(prev);
+        if (rc != OFK_OK) return rc;
+    }
+    for (auto& s : g_ring.slot) {
+        OFK_CUDA(cudaStreamSynchronize(s.st));
+        s.deliver();
+    }
+    return OFK_OK;
+}
+
 extern "C" int ofh_release(void) {
     std::lock_guard<std::mutex> lk(g_ring.mu);
+    DeviceGuard restore_device;
     if (g_ring.device >= 0) {
         cudaSetDevice(g_ring.device);
         for (auto& s : g_ring.slot) {

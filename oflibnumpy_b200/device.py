@@ -58,16 +58,30 @@ def require_gpu():
 
 
 def set_stream(stream):
-    """Stream used by every subsequent call (int / object with .cuda_stream / None for the default stream)."""
+    """Stream used by every subsequent call (int / object with .cuda_stream / None for the default stream).
+
+    One stream is current per process. Device buffers are returned to the stream-ordered pool on whatever stream is
+    current when they are collected, so a switch orders the new stream after everything queued on the old one (an
+    event on the old stream, a wait on the new one): a buffer whose kernels are still running on the old stream
+    cannot be handed to a new allocation on the new stream before they finish."""
     global _current_stream
     if stream is None:
-        _current_stream = None
+        new = None
     elif hasattr(stream, 'cuda_stream'):
-        _current_stream = int(stream.cuda_stream)
+        new = int(stream.cuda_stream)
     elif isinstance(stream, Stream):
-        _current_stream = stream.handle
+        new = stream.handle
     else:
-        _current_stream = int(stream)
+        new = int(stream)
+    if new != _current_stream and device_count() > 0:
+        ev = C.c_void_p()
+        _lib.call('ofk_rt_event_create', C.byref(ev))
+        try:
+            _lib.call('ofk_rt_event_record', ev.value, _current_stream)
+            _lib.call('ofk_rt_stream_wait_event', new, ev.value)
+        finally:
+            _lib.call('ofk_rt_event_destroy', ev.value)
+    _current_stream = new
 
 
 def current_stream():

@@ -12,11 +12,13 @@ from .batch import shard_range
 __all__ = ['shard_range', 'rank_world', 'max_over_ranks', 'gather_frames', 'as_torch', 'bind_to_gpu_cpus']
 
 
-def bind_to_gpu_cpus(device_index):
-    """Pin this process to the CPU cores NVML reports as local to GPU `device_index` (same NUMA node / PCIe root), so
-    that pinned host buffers allocated afterwards and the copy-issuing threads sit next to the GPU. With one process
-    per GPU this is what keeps host<->device streaming from crossing sockets. Returns the CPU list (empty if NVML or
-    the affinity call is unavailable: then nothing is changed)."""
+def bind_to_gpu_cpus(device_index, local_rank=None, local_world=None):
+    """Pin this process to CPU cores NVML reports as local to GPU `device_index` (same NUMA node / PCIe root), so that
+    pinned host buffers allocated afterwards and the copy-issuing threads sit next to the GPU. With `local_rank` /
+    `local_world` the GPU-local cores are dealt out round-robin, every rank of the node getting its own disjoint share
+    (on a VM that reports the same core set for every GPU, 8 ranks bound to the same 32 cores contend for them: the
+    end-to-end collapse of round 1). Returns the CPU list (empty if NVML or the affinity call is unavailable: then
+    nothing is changed)."""
     import os
     try:
         import pynvml
@@ -27,7 +29,9 @@ def bind_to_gpu_cpus(device_index):
         cpus = [64 * wi + b for wi, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
         cpus = [c for c in cpus if c < n_cpu]
         allowed = os.sched_getaffinity(0)
-        cpus = [c for c in cpus if c in allowed]
+        cpus = sorted(c for c in cpus if c in allowed)
+        if local_rank is not None and local_world and local_world > 1 and len(cpus) >= local_world:
+            cpus = cpus[int(local_rank) % int(local_world)::int(local_world)]
         if cpus:
             os.sched_setaffinity(0, cpus)
         return cpus

@@ -91,7 +91,7 @@ extern "C" int fwd_hostsim(const float* payload, int C, const float* flow, float
     g.ncy = grid_coarse(g.nby);
     g.flow = flow;
     g.sign = sign;
-    const int nb = g.nbx * g.nby;
+    const int nb = grid_slots(g.nbx, g.nby);
     std::vector<uint32_t> start(nb + 1, 0), coarse((size_t)g.ncx * g.ncy, 0), sites;
     std::vector<uint32_t> ids;
     for (int i = 0; i < H; ++i)
@@ -103,7 +103,7 @@ extern "C" int fwd_hostsim(const float* payload, int C, const float* flow, float
         const uint32_t id = ids[k];
         const P2 p = displaced(flow[2 * (size_t)id], flow[2 * (size_t)id + 1], (int)(id / W), (int)(id % W), sign);
         const int bx = bin_coord(p.x, g.nbx), by = bin_coord(p.y, g.nby);
-        bin_of[k] = by * g.nbx + bx;
+        bin_of[k] = bin_index(g.nbx, bx, by);
         ++start[bin_of[k] + 1];
         ++coarse[(by >> COARSE_SHIFT) * g.ncx + (bx >> COARSE_SHIFT)];
     }
@@ -125,7 +125,21 @@ extern "C" int fwd_hostsim(const float* payload, int C, const float* flow, float
         dirs.dy[k] = sin(2.0 * M_PI * k / HULL_DIRS);
     }
     hull_build_serial(g, (uint32_t)ids.size(), dirs, hull);
-    if (!use_prefilter) hull.m = 0;
+    std::vector<P2> opos;
+    std::vector<uint32_t> oids;
+    for (size_t k = 0; k < ids.size(); ++k) {
+        const P2 p = site_pos(g, ids[k]);
+        if (hull_outer_candidate(hull, p)) {
+            opos.push_back(p);
+            oids.push_back(ids[k]);
+        }
+    }
+    static HullPoly poly;
+    hull_wrap_serial(opos.data(), oids.data(), (int)opos.size(), poly);
+    if (!use_prefilter) {
+        hull.m = 0;
+        poly.ok = 0;
+    }
     // ---- irregular part
     for (int y = 0; y < H; ++y) {
         uint32_t hint[3] = {0, 0, 0};
@@ -139,7 +153,7 @@ extern "C" int fwd_hostsim(const float* payload, int C, const float* flow, float
             uint32_t vid[3];
             double w[3];
             int st;
-            if (hull_rejects(hull, q)) {
+            if (hull_rejects(hull, q) || (poly.ok && !inside_hull(poly, q))) {
                 st = LOC_OUTSIDE;
                 ++stats[4];
             } else {
