@@ -33,7 +33,7 @@ __device__ unsigned long long g_instr[8];
 
 constexpr int BIN_SHIFT = 2;               // fine bins of 4 x 4 pixels
 constexpr int BIN = 1 << BIN_SHIFT;
-constexpr int COARSE_SHIFT = 3;            // coarse bins of 8 x 8 fine bins (32 x 32 pixels), site counts only
+constexpr int COARSE_SHIFT = 3;            // coarse bins of 8 x 8 fine bins (32 x 32 pixels): one occupancy word each
 constexpr uint32_t NO_SITE = 0xffffffffu;
 constexpr int HULL_DIRS = 32;
 
@@ -41,7 +41,9 @@ struct SiteGrid {
     int H, W;
     int nbx, nby, ncx, ncy;
     const uint32_t* bin_start; // [nbx * nby + 1] offset of each bin in `sites` (the last entry is the site count)
-    const uint32_t* coarse;    // [ncx * ncy] number of sites per coarse bin
+    const unsigned long long* occ;   // [ncx * ncy] bit (ly * 8 + lx) set when fine bin (lx, ly) of the coarse bin holds a
+                                     // site: empty bins are skipped without touching the bin table (a search is a chain
+                                     // of dependent loads, and under a thin pocket cap most bins are empty)
     const uint32_t* sites;     // site ids (row * W + col), grouped by bin
     const float* flow;         // [H, W, 2] of this frame
     float sign;
@@ -65,8 +67,23 @@ OFK_HD int bin_coord(double v, int nb) {
     return b <= 0.0 ? 0 : (b >= (double)(nb - 1) ? nb - 1 : (int)b);
 }
 
+OFK_HD int ctz64(unsigned long long v) {   // index of the lowest set bit (v != 0)
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)v) - 1;
+#else
+    return __builtin_ctzll(v);
+#endif
+}
+
+OFK_HD bool bin_occupied(const SiteGrid& g, int bx, int by) {
+    const int cm = (1 << COARSE_SHIFT) - 1;
+    const unsigned long long w = g.occ[(by >> COARSE_SHIFT) * g.ncx + (bx >> COARSE_SHIFT)];
+    return (w >> (((by & cm) << COARSE_SHIFT) | (bx & cm))) & 1ull;
+}
+
 template <class F>
 OFK_HD void scan_bin(const SiteGrid& g, int bx, int by, F& f) {
+    if (!bin_occupied(g, bx, by)) return;
     const int b = bin_index(g.nbx, bx, by);
     const uint32_t s0 = g.bin_start[b], s1 = g.bin_start[b + 1];
     for (uint32_t s = s0; s < s1; ++s) {
@@ -288,19 +305,20 @@ OFK_HD uint32_t apex_site_impl(const SiteGrid& g, uint32_t a, uint32_t b, const 
         const int gw = gx1 - gx0 + 1, total = gw * (gy1 - gy0 + 1);
         for (int t = coop.lane; t < total; t += coop.n) {
             const int gy = gy0 + t / gw, gx = gx0 + t % gw;
-            if (g.coarse[gy * g.ncx + gx] == 0u) continue;
+            unsigned long long word = g.occ[gy * g.ncx + gx];
+            if (word == 0ull) continue;
             const int fx0 = (gx << cs) > x0 ? (gx << cs) : x0, fx1 = (gx << cs) + cw - 1 < x1 ? (gx << cs) + cw - 1 : x1;
             const int fy0 = (gy << cs) > y0 ? (gy << cs) : y0, fy1 = (gy << cs) + cw - 1 < y1 ? (gy << cs) + cw - 1 : y1;
             if (!sc.may_hold_better(fx0, fx1, fy0, fy1)) continue;
-            for (int by = fy0; by <= fy1; ++by) {
-                for (int bx = fx0; bx <= fx1; ++bx) {
-                    const int bi = bin_index(g.nbx, bx, by);
-                    if (g.bin_start[bi] == g.bin_start[bi + 1]) continue;
-                    if (bx >= cx - NEAR_RINGS && bx <= cx + NEAR_RINGS && by >= cy - NEAR_RINGS && by <= cy + NEAR_RINGS)
-                        continue;   // already scanned
-                    if (!sc.may_hold_better(bx, bx, by, by)) continue;
-                    scan_bin(g, bx, by, sc);
-                }
+            while (word) {   // the occupied fine bins of this coarse bin
+                const int bit = ctz64(word);
+                word &= word - 1;
+                const int bx = (gx << cs) | (bit & (cw - 1)), by = (gy << cs) | (bit >> cs);
+                if (bx < fx0 || bx > fx1 || by < fy0 || by > fy1) continue;
+                if (bx >= cx - NEAR_RINGS && bx <= cx + NEAR_RINGS && by >= cy - NEAR_RINGS && by <= cy + NEAR_RINGS)
+                    continue;   // already scanned
+                if (!sc.may_hold_better(bx, bx, by, by)) continue;
+                scan_bin(g, bx, by, sc);
             }
         }
         coop_reduce(sc, coop);
@@ -320,20 +338,20 @@ OFK_HD uint32_t apex_site_impl(const SiteGrid& g, uint32_t a, uint32_t b, const 
             const bool edge_row = (gy == ccy - rc || gy == ccy + rc);
             for (int gx = ccx - rc; gx <= ccx + rc; gx += (edge_row || rc == 0) ? 1 : 2 * rc) {
                 if (gx < gx0 || gx > gx1) continue;
-                if (g.coarse[gy * g.ncx + gx] == 0u) continue;
+                unsigned long long word = g.occ[gy * g.ncx + gx];
+                if (word == 0ull) continue;
                 const int fx0 = (gx << cs) > x0 ? (gx << cs) : x0, fx1 = (gx << cs) + cw - 1 < x1 ? (gx << cs) + cw - 1 : x1;
                 const int fy0 = (gy << cs) > y0 ? (gy << cs) : y0, fy1 = (gy << cs) + cw - 1 < y1 ? (gy << cs) + cw - 1 : y1;
                 if (!sc.may_hold_better(fx0, fx1, fy0, fy1)) continue;
-                for (int by = fy0; by <= fy1; ++by) {
-                    for (int bx = fx0; bx <= fx1; ++bx) {
-                        const int bi = bin_index(g.nbx, bx, by);
-                        if (g.bin_start[bi] == g.bin_start[bi + 1]) continue;
-                        if (bx >= cx - NEAR_RINGS && bx <= cx + NEAR_RINGS && by >= cy - NEAR_RINGS &&
-                            by <= cy + NEAR_RINGS)
-                            continue;   // already scanned
-                        if (!sc.may_hold_better(bx, bx, by, by)) continue;
-                        scan_bin(g, bx, by, sc);
-                    }
+                while (word) {   // the occupied fine bins of this coarse bin
+                    const int bit = ctz64(word);
+                    word &= word - 1;
+                    const int bx = (gx << cs) | (bit & (cw - 1)), by = (gy << cs) | (bit >> cs);
+                    if (bx < fx0 || bx > fx1 || by < fy0 || by > fy1) continue;
+                    if (bx >= cx - NEAR_RINGS && bx <= cx + NEAR_RINGS && by >= cy - NEAR_RINGS && by <= cy + NEAR_RINGS)
+                        continue;   // already scanned
+                    if (!sc.may_hold_better(bx, bx, by, by)) continue;
+                    scan_bin(g, bx, by, sc);
                 }
             }
         }

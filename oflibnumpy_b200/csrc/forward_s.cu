@@ -511,7 +511,7 @@ struct IrrArgs {
     const uint8_t* point_mask;
     const int* folded;
     uint32_t* bins;      // [N][nb + 1]
-    uint32_t* coarse;    // [N][nc]
+    unsigned long long* occ;   // [N][nc] occupancy words
     uint32_t* sites;     // [N][H * W]
     float sign;
     int H, W, nbx, nby, ncx, ncy;
@@ -557,7 +557,8 @@ __global__ void __launch_bounds__(256) irr_sites_kernel(const IrrArgs A) {
     const int bi = bin_index(A.nbx, bx, by);
     if (PASS == 0) {
         atomicAdd(bins + bi, 1u);
-        atomicAdd(A.coarse + (size_t)n * A.ncx * A.ncy + (by >> COARSE_SHIFT) * A.ncx + (bx >> COARSE_SHIFT), 1u);
+        atomicOr(A.occ + (size_t)n * A.ncx * A.ncy + (by >> COARSE_SHIFT) * A.ncx + (bx >> COARSE_SHIFT),
+                 1ull << ((((by & ((1 << COARSE_SHIFT) - 1)) << COARSE_SHIFT)) | (bx & ((1 << COARSE_SHIFT) - 1))));
     } else {
         const uint32_t slot = atomicSub(bins + bi, 1u) - 1u;
         A.sites[frame + slot] = id;
@@ -664,7 +665,7 @@ __device__ __forceinline__ SiteGrid hull_grid(const HullArgs& A, int n) {
     g.W = A.W;
     g.nbx = g.nby = g.ncx = g.ncy = 0;
     g.bin_start = nullptr;
-    g.coarse = nullptr;
+    g.occ = nullptr;
     g.sites = A.sites + (size_t)n * A.H * A.W;
     g.flow = A.flow + 2 * (size_t)n * A.H * A.W;
     g.sign = A.sign;
@@ -865,7 +866,7 @@ struct SolveArgs {
     const uint8_t* payload_mask;
     const int* folded;
     const uint32_t* bins;
-    const uint32_t* coarse;
+    const unsigned long long* occ;
     const uint32_t* sites;
     const HullInfo* info;
     const HullPoly* poly;
@@ -970,7 +971,7 @@ __global__ void __launch_bounds__(256) irr_solve_kernel(const SolveArgs A) {
     g.ncy = A.ncy;
     const int nb = grid_slots(A.nbx, A.nby);
     g.bin_start = A.bins + (size_t)n * (nb + 1);
-    g.coarse = A.coarse + (size_t)n * A.ncx * A.ncy;
+    g.occ = A.occ + (size_t)n * A.ncx * A.ncy;
     g.sites = A.sites + frame;
     g.flow = A.flow + 2 * frame;
     g.sign = A.sign;
@@ -1039,7 +1040,7 @@ __global__ void __launch_bounds__(256) irr_heavy_kernel(const SolveArgs A) {
         g.ncy = A.ncy;
         const int nb = grid_slots(A.nbx, A.nby);
         g.bin_start = A.bins + (size_t)n * (nb + 1);
-        g.coarse = A.coarse + (size_t)n * A.ncx * A.ncy;
+        g.occ = A.occ + (size_t)n * A.ncx * A.ncy;
         g.sites = A.sites + frame;
         g.flow = A.flow + 2 * frame;
         g.sign = A.sign;
@@ -1118,7 +1119,7 @@ static WsLayout ws_layout(int N, int H, int W) {
     L.bins = o;
     o = align_up(o + (size_t)N * (L.nb + 1) * 4, 256);
     L.coarse = o;
-    o = align_up(o + (size_t)N * L.nc * 4, 256);
+    o = align_up(o + (size_t)N * L.nc * 8, 256);
     L.hullws = o;
     o = align_up(o + (size_t)N * sizeof(HullWs), 256);
     L.folded = o;
@@ -1237,7 +1238,7 @@ extern "C" int ofk_forward_s_ex(const float* payload, int C, const float* flow, 
     uint32_t* d_sites = reinterpret_cast<uint32_t*>(base + L.sites);
     uint8_t* d_cover = out_mask != nullptr ? out_mask : reinterpret_cast<uint8_t*>(base + L.cover);
     uint32_t* d_bins = reinterpret_cast<uint32_t*>(base + L.bins);
-    uint32_t* d_coarse = reinterpret_cast<uint32_t*>(base + L.coarse);
+    unsigned long long* d_coarse = reinterpret_cast<unsigned long long*>(base + L.coarse);
     HullWs* d_hullws = reinterpret_cast<HullWs*>(base + L.hullws);
     fwd::HullInfo* d_info = reinterpret_cast<fwd::HullInfo*>(base + L.hullinfo);
     int* d_folded = reinterpret_cast<int*>(base + L.folded);

@@ -92,7 +92,8 @@ extern "C" int fwd_hostsim(const float* payload, int C, const float* flow, float
     g.flow = flow;
     g.sign = sign;
     const int nb = grid_slots(g.nbx, g.nby);
-    std::vector<uint32_t> start(nb + 1, 0), coarse((size_t)g.ncx * g.ncy, 0), sites;
+    std::vector<uint32_t> start(nb + 1, 0), sites;
+    std::vector<unsigned long long> occ((size_t)g.ncx * g.ncy, 0);
     std::vector<uint32_t> ids;
     for (int i = 0; i < H; ++i)
         for (int j = 0; j < W; ++j)
@@ -105,7 +106,8 @@ extern "C" int fwd_hostsim(const float* payload, int C, const float* flow, float
         const int bx = bin_coord(p.x, g.nbx), by = bin_coord(p.y, g.nby);
         bin_of[k] = bin_index(g.nbx, bx, by);
         ++start[bin_of[k] + 1];
-        ++coarse[(by >> COARSE_SHIFT) * g.ncx + (bx >> COARSE_SHIFT)];
+        occ[(by >> COARSE_SHIFT) * g.ncx + (bx >> COARSE_SHIFT)] |=
+            1ull << (((by & ((1 << COARSE_SHIFT) - 1)) << COARSE_SHIFT) | (bx & ((1 << COARSE_SHIFT) - 1)));
     }
     for (int b = 0; b < nb; ++b) start[b + 1] += start[b];
     sites.resize(ids.size());
@@ -115,7 +117,7 @@ extern "C" int fwd_hostsim(const float* payload, int C, const float* flow, float
         for (size_t k = ids.size(); k-- > 0;) sites[cur[bin_of[k]]++] = ids[k];
     }
     g.bin_start = start.data();
-    g.coarse = coarse.data();
+    g.occ = occ.data();
     g.sites = sites.data();
     // ---- hull pre-filter
     HullInfo hull;
