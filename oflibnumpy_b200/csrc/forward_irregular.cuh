@@ -561,6 +561,7 @@ constexpr int OUTER_CAP = 65536;      // candidate sites per frame for the wrap;
 struct HullPoly {
     int m, ok;
     double x[HULL_MAX], y[HULL_MAX];
+    uint32_t id[HULL_MAX];
 };
 
 // a site on or beyond an edge of the inner polygon can be a hull vertex, a site strictly inside it cannot
@@ -620,6 +621,7 @@ inline void hull_wrap_serial(const P2* pos, const uint32_t* ids, int n, HullPoly
         }
         hp.x[hp.m] = pos[cur].x;
         hp.y[hp.m] = pos[cur].y;
+        hp.id[hp.m] = ids[cur];
         ++hp.m;
         int best = -1;
         for (int k = 0; k < n; ++k)
@@ -629,6 +631,301 @@ inline void hull_wrap_serial(const P2* pos, const uint32_t* ids, int n, HullPoly
         cur = best;
     }
     hp.ok = hp.m >= 3 ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------ hull pockets
+// Without removed points the boundary sites are the frame border, a closed chain in a known order, and the region
+// between the displaced border and its hull falls into pockets: one per hull edge, bounded by that edge and the arc
+// of the chain between its end points. A pocket holds no site, so its Delaunay triangles only have vertices of its own
+// arc -- it is triangulated directly, by splitting: the triangle on the base edge (v_i, v_j) has the apex v_k, i < k < j,
+// whose circumcircle holds no other vertex of the arc; (v_i, v_k) and (v_k, v_j) are the next base edges. Every
+// triangle is found once and rasterised with the fill rule of the regular part, so that the pixels of a pocket (long
+// thin fans, the most expensive point locations there are) never reach the per-pixel search.
+//
+// Border in the orientation of the hull wrap (interior on the left): top row left to right, right column downwards,
+// bottom row right to left, left column upwards.
+OFK_HD int perim_count(int H, int W) { return 2 * W + 2 * H - 4; }   // H, W >= 2
+
+OFK_HD uint32_t perim_site(int H, int W, int k) {
+    if (k < W) return (uint32_t)k;
+    k -= W;
+    if (k < H - 1) return (uint32_t)((k + 1) * W + W - 1);
+    k -= H - 1;
+    if (k < W - 1) return (uint32_t)((H - 1) * W + (W - 2 - k));
+    k -= W - 1;
+    return (uint32_t)((H - 2 - k) * W);
+}
+
+OFK_HD int perim_index(int H, int W, uint32_t id) {
+    const int row = (int)(id / (uint32_t)W), col = (int)(id - (uint32_t)row * (uint32_t)W);
+    if (row == 0) return col;
+    if (col == W - 1) return W + row - 1;
+    if (row == H - 1) return W + H - 1 + (W - 2 - col);
+    if (col == 0) return 2 * W + H - 2 + (H - 2 - row);
+    return -1;
+}
+
+struct ArcBest {
+    uint32_t id;
+    int t;
+    P2 p;
+    double omin, omax, umin, umax;   // range of orient(a, b, .) and of (. - a) . (b - a) over the arc's vertices
+};
+
+OFK_HD void arc_reduce(ArcBest& b, const P2& pa, const P2& pb, uint32_t ia, uint32_t ib, const Coop& coop) {
+#if defined(__CUDA_ARCH__)
+    if (coop.n == 1) return;
+    for (int o = 16; o > 0; o >>= 1) {
+        ArcBest ob;
+        ob.id = __shfl_xor_sync(0xffffffffu, b.id, o);
+        ob.t = __shfl_xor_sync(0xffffffffu, b.t, o);
+        ob.p.x = __shfl_xor_sync(0xffffffffu, b.p.x, o);
+        ob.p.y = __shfl_xor_sync(0xffffffffu, b.p.y, o);
+        b.omin = fmin(b.omin, __shfl_xor_sync(0xffffffffu, b.omin, o));
+        b.omax = fmax(b.omax, __shfl_xor_sync(0xffffffffu, b.omax, o));
+        b.umin = fmin(b.umin, __shfl_xor_sync(0xffffffffu, b.umin, o));
+        b.umax = fmax(b.umax, __shfl_xor_sync(0xffffffffu, b.umax, o));
+        if (ob.id == NO_SITE || ob.id == b.id) continue;
+        if (b.id == NO_SITE || incircle_sign(pa, pb, b.p, ob.p, ia, ib, b.id, ob.id) > 0) {
+            b.id = ob.id;
+            b.t = ob.t;
+            b.p = ob.p;
+        }
+    }
+    b.id = __shfl_sync(0xffffffffu, b.id, 0);   // lane 0 has the last word (see coop_reduce)
+    b.t = __shfl_sync(0xffffffffu, b.t, 0);
+    b.p.x = __shfl_sync(0xffffffffu, b.p.x, 0);
+    b.p.y = __shfl_sync(0xffffffffu, b.p.y, 0);
+#else
+    (void)b; (void)pa; (void)pb; (void)ia; (void)ib; (void)coop;
+#endif
+}
+
+// Can the part of a pocket over the base edge (pa, pb) hold a pixel? It lies inside the oriented rectangle that bounds
+// its vertices: orient(pa, pb, .) in [omin, omax], (. - pa) . (pb - pa) in [umin, umax]. A border that is straight up
+// to the rounding of its float32 flow values (every affine field) consists of slivers a few 1e-6 px thick: thousands
+// of triangles per frame that contain no pixel and are not worth finding. Conservative: false only if no lattice
+// point of the frame lies in the rectangle (widened by a tolerance far above the rounding of this test).
+OFK_HD bool pocket_may_hold_pixel(const P2& pa, const P2& pb, const ArcBest& b, int W, int H, const Coop& coop) {
+    const double dx = pb.x - pa.x, dy = pb.y - pa.y, len2 = dx * dx + dy * dy;
+    if (!(len2 > 0.0)) return true;
+    const double len = sqrt(len2);
+    const double tol = 1e-7;
+    const double a = b.omin / len - tol, c = b.omax / len + tol;        // signed distance from the base line
+    if (c - a >= 0.5) return true;
+    const double t0 = b.umin / len2, t1 = b.umax / len2;                  // extent along the base edge
+    const bool major_x = fabs(dx) >= fabs(dy);
+    // extent of the rectangle along the major axis (its corners: pa + t d + s n, n = (-dy, dx) / len)
+    const double nx = -dy / len, ny = dx / len;
+    double lo = 1e300, hi = -1e300;
+    for (int k = 0; k < 4; ++k) {
+        const double t = (k & 1) ? t1 : t0, sd = (k & 2) ? c : a;
+        const double v = major_x ? pa.x + t * dx + sd * nx : pa.y + t * dy + sd * ny;
+        lo = fmin(lo, v);
+        hi = fmax(hi, v);
+    }
+    const double lim = (double)((major_x ? W : H) - 1);
+    if (!(hi >= 0.0 && lo <= lim)) return false;
+    const int m0 = (int)ceil(fmax(lo - tol, 0.0)), m1 = (int)floor(fmin(hi + tol, lim));
+    bool found = false;
+    for (int m = m0 + coop.lane; m <= m1 && !found; m += coop.n) {
+        // signed distance of (x, y): ((y - pa.y) dx - (x - pa.x) dy) / len in [a, c]
+        double qlo, qhi;
+        if (major_x) {
+            const double base = pa.y + ((double)m - pa.x) * dy / dx, k = len / dx;   // y = base + dist * len / dx
+            qlo = base + fmin(a * k, c * k);
+            qhi = base + fmax(a * k, c * k);
+        } else {
+            const double base = pa.x + ((double)m - pa.y) * dx / dy, k = -len / dy;  // x = base - dist * len / dy
+            qlo = base + fmin(a * k, c * k);
+            qhi = base + fmax(a * k, c * k);
+        }
+        const double other = (double)((major_x ? H : W) - 1);
+        const double l = ceil(fmax(qlo - tol, 0.0)), h = floor(fmin(qhi + tol, other));
+        found = l <= h;
+    }
+#if defined(__CUDA_ARCH__)
+    if (coop.n > 1) found = __any_sync(0xffffffffu, found);
+#endif
+    return found;
+}
+
+// Triangulates the part [i0, j0] (positions along the arc that starts at border index k0) of a pocket; tri(ia, ib, ic,
+// pa, pb, pc) receives the triangles that can hold a pixel (positively oriented). Parts are independent of each other:
+// share(i, j) may take the longer child of a split away (another warp works on it) by returning true.
+// Returns false when the splitting stack overflowed (cannot happen for arcs below 2^POCKET_STACK vertices).
+constexpr int POCKET_STACK = 40;
+struct NoShare {
+    OFK_HD bool operator()(int, int) const { return false; }
+};
+template <class TriFn, class ShareFn>
+OFK_HD bool pocket_triangulate(const SiteGrid& g, int k0, int i0, int j0, const Coop& coop, TriFn& tri, ShareFn& share) {
+    const int P = perim_count(g.H, g.W);
+    if (j0 - i0 < 2) return true;
+    int lo[POCKET_STACK], hi[POCKET_STACK], sp = 0;
+    lo[sp] = i0;
+    hi[sp++] = j0;
+    while (sp > 0) {
+        --sp;
+        int i = lo[sp], j = hi[sp];
+        while (j - i >= 2) {
+            const uint32_t ia = perim_site(g.H, g.W, (k0 + i) % P), ib = perim_site(g.H, g.W, (k0 + j) % P);
+            const P2 pa = site_pos(g, ia), pb = site_pos(g, ib);
+            const double ex = dsub(pb.x, pa.x), ey = dsub(pb.y, pa.y);
+            ArcBest b;
+            b.id = NO_SITE;
+            b.t = 0;
+            b.p = pa;
+            b.omin = b.omax = 0.0;
+            b.umin = 0.0;
+            b.umax = dfma(ex, ex, dmul(ey, ey));
+            for (int t = i + 1 + coop.lane; t < j; t += coop.n) {
+                const uint32_t id = perim_site(g.H, g.W, (k0 + t) % P);
+                const P2 p = site_pos(g, id);
+                const double o = orient(pa, pb, p);
+                const double u = dfma(dsub(p.x, pa.x), ex, dmul(dsub(p.y, pa.y), ey));
+                b.omin = fmin(b.omin, o);
+                b.omax = fmax(b.omax, o);
+                b.umin = fmin(b.umin, u);
+                b.umax = fmax(b.umax, u);
+                if (!(o > 0)) continue;
+                if (b.id == NO_SITE || incircle_sign(pa, pb, b.p, p, ia, ib, b.id, id) > 0) {
+                    b.id = id;
+                    b.t = t;
+                    b.p = p;
+                }
+            }
+            arc_reduce(b, pa, pb, ia, ib, coop);
+            if (b.id == NO_SITE) break;   // nothing left of the base edge: collinear border
+            if (!pocket_may_hold_pixel(pa, pb, b, g.W, g.H, coop)) break;
+            tri(ia, ib, b.id, pa, pb, b.p);
+            // continue with the shorter part; the longer one goes to another warp or is kept for later (the stack stays
+            // logarithmic)
+            const int t = b.t;
+            const bool left_longer = t - i > j - t;
+            const int li = left_longer ? i : t, lj = left_longer ? t : j;
+            if (lj - li >= 2 && !share(li, lj)) {
+                if (sp >= POCKET_STACK) return false;
+                lo[sp] = li;
+                hi[sp++] = lj;
+            }
+            if (left_longer) i = t;
+            else j = t;
+        }
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------- triangle rasteriser
+// Pixels owned by the positively oriented triangle (p0, p1, p2) with site indices (i0, i1, i2), by the fill rule of
+// forward_geom.cuh: an edge evaluated from its smaller-index endpoint, F == 0 given to the triangle that traverses it
+// in that direction. Rows are dealt out to the lanes of `coop`; per row the x-interval is bounded conservatively from
+// the three edges (long thin pocket triangles have bounding boxes thousands of times their area) and every candidate
+// is decided by the exact edge functions. fn(x, y, w0, w1, w2) receives the barycentric weights.
+template <class PixelFn>
+OFK_HD void raster_triangle(const P2& p0, const P2& p1, const P2& p2, uint32_t i0, uint32_t i1, uint32_t i2, int W,
+                            int H, const Coop& coop, PixelFn& fn) {
+    const double area2 = orient(p0, p1, p2);
+    if (!(area2 > 0.0)) return;
+    const double ylo = fmin(p0.y, fmin(p1.y, p2.y)), yhi = fmax(p0.y, fmax(p1.y, p2.y));
+    const double xlo = fmin(p0.x, fmin(p1.x, p2.x)), xhi = fmax(p0.x, fmax(p1.x, p2.x));
+    if (!(xhi >= 0.0 && yhi >= 0.0 && xlo <= (double)(W - 1) && ylo <= (double)(H - 1))) return;
+    const int y0 = (int)ceil(fmax(ylo, 0.0)), y1 = (int)floor(fmin(yhi, (double)(H - 1)));
+    const double bx0 = fmax(xlo, 0.0), bx1 = fmin(xhi, (double)(W - 1));
+    // edge k is opposite vertex k: (p1 -> p2), (p2 -> p0), (p0 -> p1); canonical endpoints and traversal direction
+    const P2* eu[3] = {&p1, &p2, &p0};
+    const P2* ev[3] = {&p2, &p0, &p1};
+    const bool fwd_dir[3] = {i1 < i2, i2 < i0, i0 < i1};
+    const double r = drcp(area2);
+    for (int y = y0 + coop.lane; y <= y1; y += coop.n) {
+        const double qy = (double)y;
+        double xl = bx0, xr = bx1;
+        for (int k = 0; k < 3; ++k) {   // inside: dx * (qy - u.y) - dy * (qx - u.x) >= 0
+            const double dx = ev[k]->x - eu[k]->x, dy = ev[k]->y - eu[k]->y;
+            if (dy == 0.0) continue;
+            const double xc = eu[k]->x + dx * (qy - eu[k]->y) / dy;
+            const double slack = 1e-6 + 1e-12 * fabs(xc);
+            if (dy > 0.0) xr = fmin(xr, xc + slack);
+            else xl = fmax(xl, xc - slack);
+        }
+        if (!(xl <= xr)) continue;
+        const int xa = (int)ceil(xl), xb = (int)floor(xr);
+        for (int x = xa; x <= xb; ++x) {
+            const double qx = (double)x;
+            double e[3];
+            bool in = true;
+            for (int k = 0; k < 3; ++k) {
+                if (fwd_dir[k]) {
+                    e[k] = edge_canon(*eu[k], *ev[k], qx, qy);
+                    in = in && e[k] >= 0.0;
+                } else {
+                    e[k] = -edge_canon(*ev[k], *eu[k], qx, qy);
+                    in = in && e[k] > 0.0;
+                }
+            }
+            if (!in) continue;
+            const double w0 = dmul(e[0], r), w1 = dmul(e[1], r);
+            fn(x, y, w0, w1, dsub(dsub(1.0, w0), w1));
+        }
+    }
+}
+
+// Pixels exactly on the segment (pa, pb) -- edge function exactly 0, evaluated from the end point with the smaller
+// index like everywhere else, end points included: fn(x, y, wa, wb). On a hull edge the fill rule can leave them to
+// nobody (the one triangle there may traverse the edge from the larger index to the smaller); they are inside the hull.
+template <class LineFn>
+OFK_HD void raster_segment(const P2& pa, const P2& pb, int W, int H, const Coop& coop, LineFn& fn) {
+    const double xlo = fmin(pa.x, pb.x), xhi = fmax(pa.x, pb.x), ylo = fmin(pa.y, pb.y), yhi = fmax(pa.y, pb.y);
+    if (!(xhi >= 0.0 && yhi >= 0.0 && xlo <= (double)(W - 1) && ylo <= (double)(H - 1))) return;
+    const int x0 = (int)ceil(fmax(xlo, 0.0)), x1 = (int)floor(fmin(xhi, (double)(W - 1)));
+    const int y0 = (int)ceil(fmax(ylo, 0.0)), y1 = (int)floor(fmin(yhi, (double)(H - 1)));
+    const double dx = dsub(pb.x, pa.x), dy = dsub(pb.y, pa.y);
+    const double len2 = dfma(dx, dx, dmul(dy, dy));
+    if (!(len2 > 0.0)) return;
+    const bool steep = fabs(dy) > fabs(dx);
+    // one candidate per row (steep) or per column: the lattice point next to the line
+    const int n = steep ? y1 - y0 + 1 : x1 - x0 + 1;
+    for (int t = coop.lane; t < n; t += coop.n) {
+        int x, y;
+        if (steep) {
+            y = y0 + t;
+            x = (int)rint(pa.x + dx * ((double)y - pa.y) / dy);
+        } else {
+            x = x0 + t;
+            y = (int)rint(pa.y + dy * ((double)x - pa.x) / dx);
+        }
+        if (x < x0 || x > x1 || y < y0 || y > y1) continue;
+        if (edge_canon(pa, pb, (double)x, (double)y) != 0.0) continue;
+        const double rx = dsub((double)x, pa.x), ry = dsub((double)y, pa.y);
+        double wb = dfma(rx, dx, dmul(ry, dy)) / len2;
+        wb = wb < 0.0 ? 0.0 : (wb > 1.0 ? 1.0 : wb);
+        fn(x, y, dsub(1.0, wb), wb);
+    }
+}
+
+// The pixels exactly on border edges t0 <= t < t1 (edge t joins border sites t and t + 1) that no intact cell
+// produced: seg(ia, ib, pa, pb, coop) gets the end points ordered by index. They come before the triangles of the
+// pockets (which leave produced pixels alone), the hull edge of a pocket -- pocket_chord -- after them.
+template <class SegFn>
+OFK_HD void pocket_border_edges(const SiteGrid& g, int t0, int t1, int stride, SegFn& seg) {
+    const int P = perim_count(g.H, g.W);
+    const Coop solo{0, 1};
+    for (int t = t0; t < t1; t += stride) {
+        const uint32_t ia = perim_site(g.H, g.W, t), ib = perim_site(g.H, g.W, t + 1 == P ? 0 : t + 1);
+        const P2 pa = site_pos(g, ia), pb = site_pos(g, ib);
+        if (ia < ib) seg(ia, ib, pa, pb, solo);
+        else seg(ib, ia, pb, pa, solo);
+    }
+}
+
+template <class SegFn>
+OFK_HD void pocket_chord(const SiteGrid& g, int k0, int k1, const Coop& coop, SegFn& seg) {
+    const int P = perim_count(g.H, g.W);
+    if (((k1 - k0) % P + P) % P < 2) return;
+    const uint32_t ia = perim_site(g.H, g.W, k0), ib = perim_site(g.H, g.W, k1);
+    const P2 pa = site_pos(g, ia), pb = site_pos(g, ib);
+    if (ia < ib) seg(ia, ib, pa, pb, coop);
+    else seg(ib, ia, pb, pa, coop);
 }
 
 // a valid site is a boundary site when it sits on the frame border or one of its 8 neighbours has been removed

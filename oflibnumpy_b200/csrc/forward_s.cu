@@ -836,6 +836,7 @@ __global__ void __launch_bounds__(256) hull_wrap_kernel(const OuterArgs A) {
         if (threadIdx.x == 0) {
             hp.x[m] = cur.p.x;
             hp.y[m] = cur.p.y;
+            hp.id[m] = cur.id;
         }
         ++m;
         WrapCand best;
@@ -857,6 +858,198 @@ __global__ void __launch_bounds__(256) hull_wrap_kernel(const OuterArgs A) {
         hp.m = m;
         hp.ok = m >= 3 ? 1 : 0;
     }
+}
+
+// ------------------------------------------------------------------------------------------------- hull pockets
+struct PocketArgs {
+    const float* payload;
+    const float* flow;
+    const uint8_t* payload_mask;
+    const int* folded;
+    const HullPoly* poly;
+    float* out;
+    uint8_t* out_mask;
+    uint8_t* cover;
+    float sign;
+    int C, rule_strict, H, W;
+};
+
+struct PocketPixel {
+    const PocketArgs& A;
+    size_t frame;
+    uint32_t v0, v1, v2;
+    unsigned long long& count;
+    __device__ __forceinline__ void operator()(int x, int y, double w0, double w1, double w2) {
+        const size_t px = frame + (size_t)y * A.W + x;
+        if (A.cover[px] != UNCOVERED) return;   // only what no intact cell produced
+        const uint8_t* pm = A.payload_mask ? A.payload_mask + frame : nullptr;
+        const float* pay = A.payload + frame * A.C;
+        interp_store(pay + (size_t)v0 * A.C, pay + (size_t)v1 * A.C, pay + (size_t)v2 * A.C, pm ? pm[v0] != 0 : true,
+                     pm ? pm[v1] != 0 : true, pm ? pm[v2] != 0 : true, w0, w1, w2, A.C, A.out + px * A.C,
+                     A.out_mask ? A.out_mask + px : nullptr, A.rule_strict);
+        if (A.out_mask == nullptr) A.cover[px] = 1;
+        ++count;
+    }
+};
+
+struct PocketTri {
+    const PocketArgs& A;
+    size_t frame;
+    Coop coop;
+    unsigned long long& count;
+    __device__ __forceinline__ void operator()(uint32_t ia, uint32_t ib, uint32_t ic, const P2& pa, const P2& pb,
+                                               const P2& pc) {
+        PocketPixel px{A, frame, ia, ib, ic, count};
+        raster_triangle(pa, pb, pc, ia, ib, ic, A.W, A.H, coop, px);
+    }
+};
+
+struct PocketSegPixel {
+    PocketPixel px;
+    __device__ __forceinline__ void operator()(int x, int y, double wa, double wb) { px(x, y, wa, wb, 0.0); }
+};
+
+struct PocketSeg {
+    const PocketArgs& A;
+    size_t frame;
+    unsigned long long& count;
+    __device__ __forceinline__ void operator()(uint32_t ia, uint32_t ib, const P2& pa, const P2& pb, const Coop& co) {
+        PocketSegPixel px{PocketPixel{A, frame, ia, ib, ib, count}};
+        raster_segment(pa, pb, A.W, A.H, co, px);
+    }
+};
+
+__device__ __forceinline__ SiteGrid pocket_grid(const PocketArgs& A, size_t frame) {
+    SiteGrid g;
+    g.H = A.H;
+    g.W = A.W;
+    g.nbx = g.nby = g.ncx = g.ncy = 0;
+    g.bin_start = nullptr;
+    g.occ = nullptr;
+    g.sites = nullptr;
+    g.flow = A.flow + 2 * frame;
+    g.sign = A.sign;
+    return g;
+}
+
+// Frames without removed points, first the pixels exactly on the displaced frame border that no cell produced (a
+// straight border: every pixel of a column after an integer shift) ...
+__global__ void __launch_bounds__(256) irr_border_edges_kernel(const PocketArgs A) {
+    const int n = blockIdx.y;
+    if (A.folded[n]) return;
+    const size_t frame = (size_t)n * A.H * A.W;
+    const SiteGrid g = pocket_grid(A, frame);
+    unsigned long long pixels = 0;
+    PocketSeg seg{A, frame, pixels};
+    pocket_border_edges(g, blockIdx.x * 256 + threadIdx.x, perim_count(A.H, A.W), gridDim.x * 256, seg);
+    for (int o = 16; o > 0; o >>= 1) pixels += __shfl_xor_sync(0xffffffffu, pixels, o);
+    if ((threadIdx.x & 31) == 0 && pixels) atomicAdd(&g_stats[0], pixels);
+}
+
+// ... then the pockets: a CTA per hull edge triangulates the pocket between that edge and the displaced frame border
+// (pocket_triangulate) and rasterises its triangles. A warp works on one part of the arc, its lanes sharing the scans
+// and the rows; when it splits a part, the longer half goes to a small pool in shared memory that idle warps draw from.
+constexpr int POOL_CAP = 16, POOL_MIN_LEN = 24;
+
+struct PocketPool {
+    int lo[POOL_CAP], hi[POOL_CAP];
+    int n, active, lock;
+};
+
+__device__ __forceinline__ void pool_lock(PocketPool& p) {
+    while (atomicCAS(&p.lock, 0, 1) != 0) __nanosleep(20);
+    __threadfence_block();
+}
+__device__ __forceinline__ void pool_unlock(PocketPool& p) {
+    __threadfence_block();
+    atomicExch(&p.lock, 0);
+}
+
+struct PocketShare {
+    PocketPool& pool;
+    int lane;
+    __device__ __forceinline__ bool operator()(int i, int j) const {
+        if (j - i < POOL_MIN_LEN) return false;
+        int took = 0;
+        if (lane == 0 && *(volatile int*)&pool.n < POOL_CAP / 2) {
+            pool_lock(pool);
+            if (pool.n < POOL_CAP) {
+                pool.lo[pool.n] = i;
+                pool.hi[pool.n] = j;
+                ++pool.n;
+                took = 1;
+            }
+            pool_unlock(pool);
+        }
+        return __shfl_sync(0xffffffffu, took, 0) != 0;
+    }
+};
+
+__global__ void __launch_bounds__(256) irr_pockets_kernel(const PocketArgs A) {
+    const int n = blockIdx.y;
+    if (A.folded[n]) return;
+    const HullPoly& hp = A.poly[n];
+    if (!hp.ok) return;
+    __shared__ PocketPool pool;
+    const int lane = threadIdx.x & 31;
+    const Coop coop{lane, 32};
+    const size_t frame = (size_t)n * A.H * A.W;
+    const SiteGrid g = pocket_grid(A, frame);
+    unsigned long long pixels = 0;
+    PocketTri tri{A, frame, coop, pixels};
+    PocketSeg seg{A, frame, pixels};
+    PocketShare share{pool, lane};
+    const int m = hp.m, P = perim_count(A.H, A.W);
+    for (int e = blockIdx.x; e < m; e += gridDim.x) {
+        const int k0 = perim_index(A.H, A.W, hp.id[e]), k1 = perim_index(A.H, A.W, hp.id[e + 1 == m ? 0 : e + 1]);
+        if (k0 < 0 || k1 < 0) continue;
+        const int len = ((k1 - k0) % P + P) % P;
+        if (len < 2) continue;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            pool.lo[0] = 0;
+            pool.hi[0] = len;
+            pool.n = 1;
+            pool.active = 0;
+            pool.lock = 0;
+        }
+        __syncthreads();
+        for (;;) {
+            int got = 0, i = 0, j = 0;
+            if (lane == 0) {
+                pool_lock(pool);
+                if (pool.n > 0) {
+                    --pool.n;
+                    i = pool.lo[pool.n];
+                    j = pool.hi[pool.n];
+                    ++pool.active;
+                    got = 1;
+                } else if (pool.active == 0) {
+                    got = -1;
+                }
+                pool_unlock(pool);
+            }
+            got = __shfl_sync(0xffffffffu, got, 0);
+            if (got < 0) break;
+            if (got == 0) {
+                __nanosleep(200);
+                continue;
+            }
+            i = __shfl_sync(0xffffffffu, i, 0);
+            j = __shfl_sync(0xffffffffu, j, 0);
+            pocket_triangulate(g, k0, i, j, coop, tri, share);
+            __syncwarp();
+            if (lane == 0) {
+                pool_lock(pool);
+                --pool.active;
+                pool_unlock(pool);
+            }
+        }
+        __syncthreads();   // the pixels exactly on the hull edge come after the triangles of its pocket
+        if (threadIdx.x < 32) pocket_chord(g, k0, k1, coop, seg);
+    }
+    for (int o = 16; o > 0; o >>= 1) pixels += __shfl_xor_sync(0xffffffffu, pixels, o);
+    if (lane == 0 && pixels) atomicAdd(&g_stats[0], pixels);
 }
 
 // ------------------------------------------------------------------------------------------------- uncovered pixels
@@ -1321,6 +1514,16 @@ extern "C" int ofk_forward_s_ex(const float* payload, int C, const float* flow, 
     OFK_LAUNCHED();
     hull_wrap_kernel<<<N, 256, 0, st>>>(O);
     OFK_LAUNCHED();
+
+    if (I.perimeter_only) {
+        PocketArgs Pk{payload, flow, payload_mask, d_folded, reinterpret_cast<const fwd::HullPoly*>(base + L.poly), out,
+                      out_mask, d_cover, flow_sign, C, strict, H, W};
+        const int P = 2 * W + 2 * H - 4;
+        irr_border_edges_kernel<<<dim3(std::min((P + 255) / 256, 8), N), 256, 0, st>>>(Pk);
+        OFK_LAUNCHED();
+        irr_pockets_kernel<<<dim3(std::max(1, std::min(32, (sm_count() * 6 + N - 1) / N)), N), 256, 0, st>>>(Pk);
+        OFK_LAUNCHED();
+    }
 
     SolveArgs S{payload, flow, payload_mask, d_folded, d_bins, d_coarse, d_sites, d_info,
                 reinterpret_cast<const fwd::HullPoly*>(base + L.poly), out, out_mask, d_cover,

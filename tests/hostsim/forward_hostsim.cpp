@@ -54,6 +54,7 @@ extern "C" int fwd_hostsim(const float* payload, int C, const float* flow, float
                            const uint8_t* point_mask, float* out, uint8_t* out_mask, int rule_strict, int H, int W,
                            int use_prefilter, double flip_tol, long long* stats) {
     const int use_hints = (use_prefilter & 2) != 0;
+    const int flags = use_prefilter;
     use_prefilter &= 1;
     std::vector<uint8_t> cover((size_t)H * W, 0);
     Frame f{payload, C, flow, sign, payload_mask, point_mask, out, out_mask, rule_strict, H, W, cover.data()};
@@ -141,6 +142,49 @@ extern "C" int fwd_hostsim(const float* payload, int C, const float* flow, float
     if (!use_prefilter) {
         hull.m = 0;
         poly.ok = 0;
+    }
+    // ---- hull pockets of a frame without removed points: triangulated arc by arc, rasterised directly
+    if (point_mask == nullptr && H >= 3 && W >= 3 && poly.ok && (flags & 4) == 0) {
+        const Coop solo{0, 1};
+        const uint8_t* pm = payload_mask;
+        auto seg = [&](uint32_t ia, uint32_t ib, const P2& pa, const P2& pb, const Coop& co) {
+            auto pixel = [&](int x, int y, double wa, double wb) {
+                const size_t px = (size_t)y * W + x;
+                if (cover[px]) return;
+                cover[px] = 3;
+                ++stats[1];
+                interp_store(payload + (size_t)ia * C, payload + (size_t)ib * C, payload + (size_t)ib * C,
+                             pm ? pm[ia] != 0 : true, pm ? pm[ib] != 0 : true, pm ? pm[ib] != 0 : true, wa, wb, 0.0, C,
+                             out + px * C, out_mask ? out_mask + px : nullptr, rule_strict);
+            };
+            raster_segment(pa, pb, W, H, co, pixel);
+        };
+        pocket_border_edges(g, 0, perim_count(H, W), 1, seg);
+        for (int e = 0; e < poly.m; ++e) {
+            const int k0 = perim_index(H, W, poly.id[e]), k1 = perim_index(H, W, poly.id[e + 1 == poly.m ? 0 : e + 1]);
+            if (k0 < 0 || k1 < 0) continue;
+            auto tri = [&](uint32_t ia, uint32_t ib, uint32_t ic, const P2& pa, const P2& pb, const P2& pc) {
+                auto pixel = [&](int x, int y, double w0, double w1, double w2) {
+                    const size_t px = (size_t)y * W + x;
+                    // a pixel within rounding of the displaced border can be claimed from both sides (the sliver's
+                    // edges are chords, not the border edge the cell was tested against): the cell keeps it
+                    if (cover[px]) {
+                        if (cover[px] == 2) ++stats[6];
+                        return;
+                    }
+                    cover[px] = 2;
+                    ++stats[1];
+                    interp_store(payload + (size_t)ia * C, payload + (size_t)ib * C, payload + (size_t)ic * C,
+                                 pm ? pm[ia] != 0 : true, pm ? pm[ib] != 0 : true, pm ? pm[ic] != 0 : true, w0, w1, w2, C,
+                                 out + px * C, out_mask ? out_mask + px : nullptr, rule_strict);
+                };
+                raster_triangle(pa, pb, pc, ia, ib, ic, W, H, solo, pixel);
+            };
+            const int P = perim_count(H, W);
+            NoShare noshare;
+            if (!pocket_triangulate(g, k0, 0, ((k1 - k0) % P + P) % P, solo, tri, noshare)) ++stats[3];
+            pocket_chord(g, k0, k1, solo, seg);
+        }
     }
     // ---- irregular part
     for (int y = 0; y < H; ++y) {
