@@ -395,8 +395,8 @@ __global__ void __launch_bounds__(256, 3) fwd_raster_kernel(const RasterArgs A) 
                 tri = owner_triangle(a, b, c, d, diag, qx, qy);
                 if (tri < 0) return;
             }
-            area2 = diag == 0 ? (tri == 0 ? orient(a, b, d) : orient(a, d, c))
-                              : (tri == 0 ? orient(a, b, c) : orient(b, d, c));
+            const bool s11 = diag == 1 && tri == 1, s00 = diag == 0 && tri == 0;
+            area2 = orient(s11 ? b : a, tri == 0 ? b : d, s00 ? d : c);
         } else {
             double ar[2];
             diag = cell_diagonal(a, b, c, d, ar, A.flip_tol);
@@ -405,9 +405,22 @@ __global__ void __launch_bounds__(256, 3) fwd_raster_kernel(const RasterArgs A) 
             if (tri < 0) return;
             area2 = ar[tri];
         }
-        int k[3];
+        // weights as triangle_weights() computes them, with the vertices selected instead of four copies of the code
+        // (the lanes of a warp hold all four (diagonal, triangle) cases): (a, b, d), (a, d, c), (a, b, c), (b, d, c)
+        const bool t11 = diag == 1 && tri == 1, t00 = diag == 0 && tri == 0, tr0 = tri == 0;
+        const P2 p0 = t11 ? b : a, p2 = t00 ? d : c;
+        const P2 eu = tr0 ? b : c, ev = tr0 ? p2 : d;   // edge opposite p0, from its smaller-index end point
+        const double ee0 = edge_canon(eu, ev, qx, qy), e0 = tr0 ? ee0 : -ee0;
+        const double e1 = -edge_canon(p0, p2, qx, qy);
+        const double r = drcp(area2);
         double w[3];
-        triangle_weights(a, b, c, d, diag, tri, area2, qx, qy, k, w);
+        w[0] = dmul(e0, r);
+        w[1] = dmul(e1, r);
+        w[2] = dsub(dsub(1.0, w[0]), w[1]);
+        int k[3];
+        k[0] = t11 ? 1 : 0;
+        k[1] = tr0 ? 1 : 3;
+        k[2] = t00 ? 3 : 2;
         const int v0 = sb + (k[0] >> 1) * SW + (k[0] & 1), v1 = sb + (k[1] >> 1) * SW + (k[1] & 1),
                   v2 = sb + (k[2] >> 1) * SW + (k[2] & 1);
         const size_t px = frame + (size_t)y * A.W + x;
