@@ -750,7 +750,7 @@ OFK_HD bool pocket_may_hold_pixel(const P2& pa, const P2& pb, const ArcBest& b, 
     return found;
 }
 
-// Triangulates the part [i0, j0] (positions along the arc that starts at border index k0) of a pocket; tri(ia, ib, ic,
+// Triangulates the part [i0, j0] (positions along the arc; arc(t) = site at position t) of a pocket; tri(ia, ib, ic,
 // pa, pb, pc) receives the triangles that can hold a pixel (positively oriented). Parts are independent of each other:
 // share(i, j) may take the longer child of a split away (another warp works on it) by returning true.
 // Returns false when the splitting stack overflowed (cannot happen for arcs below 2^POCKET_STACK vertices).
@@ -758,9 +758,13 @@ constexpr int POCKET_STACK = 40;
 struct NoShare {
     OFK_HD bool operator()(int, int) const { return false; }
 };
-template <class TriFn, class ShareFn>
-OFK_HD bool pocket_triangulate(const SiteGrid& g, int k0, int i0, int j0, const Coop& coop, TriFn& tri, ShareFn& share) {
-    const int P = perim_count(g.H, g.W);
+struct PerimArc {   // position t along the arc that starts at border index k0 -> site
+    int H, W, P, k0;
+    OFK_HD uint32_t operator()(int t) const { return perim_site(H, W, (k0 + t) % P); }
+};
+template <class ArcFn, class TriFn, class ShareFn>
+OFK_HD bool pocket_triangulate(const SiteGrid& g, const ArcFn& arc, int i0, int j0, const Coop& coop, TriFn& tri,
+                               ShareFn& share) {
     if (j0 - i0 < 2) return true;
     int lo[POCKET_STACK], hi[POCKET_STACK], sp = 0;
     lo[sp] = i0;
@@ -769,7 +773,7 @@ OFK_HD bool pocket_triangulate(const SiteGrid& g, int k0, int i0, int j0, const 
         --sp;
         int i = lo[sp], j = hi[sp];
         while (j - i >= 2) {
-            const uint32_t ia = perim_site(g.H, g.W, (k0 + i) % P), ib = perim_site(g.H, g.W, (k0 + j) % P);
+            const uint32_t ia = arc(i), ib = arc(j);
             const P2 pa = site_pos(g, ia), pb = site_pos(g, ib);
             const double ex = dsub(pb.x, pa.x), ey = dsub(pb.y, pa.y);
             ArcBest b;
@@ -780,7 +784,7 @@ OFK_HD bool pocket_triangulate(const SiteGrid& g, int k0, int i0, int j0, const 
             b.umin = 0.0;
             b.umax = dfma(ex, ex, dmul(ey, ey));
             for (int t = i + 1 + coop.lane; t < j; t += coop.n) {
-                const uint32_t id = perim_site(g.H, g.W, (k0 + t) % P);
+                const uint32_t id = arc(t);
                 const P2 p = site_pos(g, id);
                 const double o = orient(pa, pb, p);
                 const double u = dfma(dsub(p.x, pa.x), ex, dmul(dsub(p.y, pa.y), ey));
@@ -813,6 +817,95 @@ OFK_HD bool pocket_triangulate(const SiteGrid& g, int k0, int i0, int j0, const 
             else j = t;
         }
     }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------- small holes
+// Removed points (`consider_mask`) leave faces that no intact cell covers. A face that is a simple polygon of a few
+// boundary sites strictly inside the frame, with no site inside -- a single removed point leaves an octagon -- is
+// triangulated like a pocket, by one thread: its Delaunay triangles only have its own boundary sites as vertices. The
+// thread of the FIRST removed point of a face (smallest index) walks the boundary: from the directed edge a -> b (b the
+// neighbour of a in direction k, the face on its left, an intact cell on its right) the boundary continues from b
+// along the first direction, turning back from k + 1, that has an intact cell on its right. Faces that are larger,
+// touch the frame border, are pinched at a vertex or hold a site are left to the per-pixel search.
+constexpr int HOLE_MAXV = 48;
+
+// cell (ci, cj) = the pixels (ci, cj), (ci, cj+1), (ci+1, cj), (ci+1, cj+1); intact when all four are present
+OFK_HD bool cell_intact(const uint8_t* point_mask, int H, int W, int ci, int cj) {
+    if (ci < 0 || cj < 0 || ci + 1 >= H || cj + 1 >= W) return false;
+    if (point_mask == nullptr) return true;
+    const uint8_t* m = point_mask + (size_t)ci * W + cj;
+    return m[0] && m[1] && m[W] && m[W + 1];
+}
+
+struct HoleLoop {
+    int n;
+    uint32_t v[HOLE_MAXV];   // boundary sites, the face on the RIGHT of v[t] -> v[t + 1] (the order of a pocket's arc)
+    OFK_HD uint32_t operator()(int t) const { return v[t]; }
+};
+
+// quadrant q (0..3 = SE, SW, NW, NE) of site (r, c) as a cell
+OFK_HD void quadrant_cell(int r, int c, int q, int& ci, int& cj) {
+    ci = r - (q >> 1);
+    cj = c - (((q + 1) >> 1) & 1);
+}
+
+OFK_HD bool hole_loop(const uint8_t* pm, int H, int W, int r, int c, HoleLoop& L) {
+    const uint32_t self = (uint32_t)(r * W + c);
+    // for the first removed point of a face the two rows above it hold no removed point of the face: the edge
+    // (r-1, c-1) -> (r-1, c) has an intact cell above and the face below
+    if (r < 2 || c < 1 || !cell_intact(pm, H, W, r - 2, c - 1)) return false;
+    const int dr[4] = {0, 1, 0, -1}, dc[4] = {1, 0, -1, 0};
+    int ar = r - 1, ac = c - 1, k = 0, n = 0;
+    uint32_t fwd_order[HOLE_MAXV];
+    int rmin = ar, rmax = ar, cmin = ac, cmax = ac;
+    for (;;) {
+        if (n >= HOLE_MAXV) return false;
+        fwd_order[n++] = (uint32_t)(ar * W + ac);
+        rmin = ar < rmin ? ar : rmin; rmax = ar > rmax ? ar : rmax;
+        cmin = ac < cmin ? ac : cmin; cmax = ac > cmax ? ac : cmax;
+        // the face cell on the left of this edge: inside the frame, and no removed corner before `self`
+        int ci, cj;
+        quadrant_cell(ar, ac, k, ci, cj);
+        if (ci < 0 || cj < 0 || ci + 1 >= H || cj + 1 >= W) return false;
+        for (int t = 0; t < 4; ++t) {
+            const uint32_t id = (uint32_t)((ci + (t >> 1)) * W + cj + (t & 1));
+            if (!pm[id] && id < self) return false;
+        }
+        const int br = ar + dr[k], bc = ac + dc[k];
+        int j = k + 1, turns = 0;
+        for (;; --j, ++turns) {
+            if (turns > 3) return false;
+            quadrant_cell(br, bc, (j + 3) & 3, ci, cj);
+            if (cell_intact(pm, H, W, ci, cj)) break;
+        }
+        ar = br;
+        ac = bc;
+        k = j & 3;
+        if (ar == r - 1 && ac == c - 1 && k == 0) break;
+    }
+    if (n < 3) return false;
+    for (int i = 0; i < n; ++i)       // pinched at a vertex: not a simple polygon
+        for (int j = i + 1; j < n; ++j)
+            if (fwd_order[i] == fwd_order[j]) return false;
+    for (int y = rmin + 1; y < rmax; ++y)   // a site that no intact cell touches may lie inside the face
+        for (int x = cmin + 1; x < cmax; ++x)
+            if (pm[(size_t)y * W + x] && !cell_intact(pm, H, W, y, x) && !cell_intact(pm, H, W, y, x - 1) &&
+                !cell_intact(pm, H, W, y - 1, x - 1) && !cell_intact(pm, H, W, y - 1, x))
+                return false;
+    L.n = n;
+    for (int i = 0; i < n; ++i) L.v[i] = fwd_order[n - 1 - i];
+    return true;
+}
+
+// triangles of the face whose first removed point is (r, c), if it qualifies
+template <class TriFn>
+OFK_HD bool hole_fill(const SiteGrid& g, const uint8_t* pm, int r, int c, TriFn& tri) {
+    HoleLoop L;
+    if (!hole_loop(pm, g.H, g.W, r, c, L)) return false;
+    const Coop solo{0, 1};
+    NoShare noshare;
+    pocket_triangulate(g, L, 0, L.n - 1, solo, tri, noshare);
     return true;
 }
 

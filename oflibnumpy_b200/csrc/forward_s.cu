@@ -529,6 +529,9 @@ struct IrrArgs {
     float sign;
     int H, W, nbx, nby, ncx, ncy;
     int perimeter_only;  // no point mask: the boundary sites are the frame border
+    unsigned long long* holes;   // removed points (frame << 32 | index), the candidates for hole_fill()
+    unsigned int* hole_count;
+    unsigned int hole_cap;
 };
 
 __device__ __forceinline__ bool irr_site_of_thread(const IrrArgs& A, int n, long long t, int& row, int& col) {
@@ -559,8 +562,17 @@ __global__ void __launch_bounds__(256) irr_sites_kernel(const IrrArgs A) {
     const int n = blockIdx.y;
     if (A.folded[n]) return;
     int row, col;
-    if (!irr_site_of_thread(A, n, (long long)blockIdx.x * 256 + threadIdx.x, row, col)) return;
     const size_t frame = (size_t)n * A.H * A.W;
+    if (!irr_site_of_thread(A, n, (long long)blockIdx.x * 256 + threadIdx.x, row, col)) {
+        if (PASS == 0 && !A.perimeter_only) {   // a removed point: queued for the small-face pass
+            const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+            if (t < (long long)A.H * A.W && A.point_mask != nullptr && !A.point_mask[frame + t]) {
+                const unsigned slot = atomicAdd(A.hole_count, 1u);
+                if (slot < A.hole_cap) A.holes[slot] = ((unsigned long long)n << 32) | (unsigned long long)t;
+            }
+        }
+        return;
+    }
     const uint32_t id = (uint32_t)(row * A.W + col);
     const float2 f = __ldg(reinterpret_cast<const float2*>(A.flow) + frame + id);
     const P2 p = displaced(f.x, f.y, row, col, A.sign);
@@ -700,8 +712,15 @@ __global__ void __launch_bounds__(256) hull_sites_kernel(const HullArgs A) {
     const int lane = threadIdx.x & 31;
     for (int it = 0; it < HULL_ITEMS; ++it) {
         const uint32_t s = s0 + it * 256 + threadIdx.x;
-        const bool have = s < total;
+        bool have = s < total;
         const uint32_t id = have ? g.sites[s] : 0u;
+        if (PASS != 2) {
+            // the polygon only has to lie inside the hull: its vertices are taken from the frame border (with removed
+            // points every rim of a hole is a boundary site, a hundred times more of them, none of them extreme)
+            const uint32_t row = id / (uint32_t)A.W, col = id - row * (uint32_t)A.W;
+            have = have && (row == 0u || col == 0u || row == (uint32_t)(A.H - 1) || col == (uint32_t)(A.W - 1));
+            if (!__any_sync(0xffffffffu, have)) continue;
+        }
         P2 p;
         p.x = p.y = 0.0;
         if (have) p = site_pos(g, id);
@@ -945,6 +964,30 @@ __device__ __forceinline__ SiteGrid pocket_grid(const PocketArgs& A, size_t fram
     return g;
 }
 
+// ------------------------------------------------------------------------------------------------- small holes
+// One thread per removed point: the first removed point of a small face (hole_loop) triangulates it and rasterises
+// the triangles; all other threads find a removed point with a smaller index on their walk and stop.
+__global__ void __launch_bounds__(128) irr_holes_kernel(const PocketArgs A, const uint8_t* __restrict__ point_mask,
+                                                        const unsigned long long* __restrict__ holes,
+                                                        const unsigned int* __restrict__ hole_count,
+                                                        unsigned int hole_cap) {
+    const unsigned count = min(*hole_count, hole_cap);
+    const Coop solo{0, 1};
+    unsigned long long pixels = 0;
+    for (unsigned it = blockIdx.x * 128 + threadIdx.x; it < count; it += gridDim.x * 128) {
+        const unsigned long long item = holes[it];
+        const int n = (int)(item >> 32);
+        if (A.folded[n]) continue;
+        const uint32_t id = (uint32_t)(item & 0xffffffffu);
+        const size_t frame = (size_t)n * A.H * A.W;
+        const SiteGrid g = pocket_grid(A, frame);
+        PocketTri tri{A, frame, solo, pixels};
+        hole_fill(g, point_mask + frame, (int)(id / (uint32_t)A.W), (int)(id % (uint32_t)A.W), tri);
+    }
+    for (int o = 16; o > 0; o >>= 1) pixels += __shfl_xor_sync(0xffffffffu, pixels, o);
+    if ((threadIdx.x & 31) == 0 && pixels) atomicAdd(&g_stats[0], pixels);
+}
+
 // Frames without removed points, first the pixels exactly on the displaced frame border that no cell produced (a
 // straight border: every pixel of a column after an integer shift) ...
 __global__ void __launch_bounds__(256) irr_border_edges_kernel(const PocketArgs A) {
@@ -1050,7 +1093,7 @@ __global__ void __launch_bounds__(256) irr_pockets_kernel(const PocketArgs A) {
             }
             i = __shfl_sync(0xffffffffu, i, 0);
             j = __shfl_sync(0xffffffffu, j, 0);
-            pocket_triangulate(g, k0, i, j, coop, tri, share);
+            pocket_triangulate(g, PerimArc{A.H, A.W, P, k0}, i, j, coop, tri, share);
             __syncwarp();
             if (lane == 0) {
                 pool_lock(pool);
@@ -1290,7 +1333,7 @@ __global__ void __launch_bounds__(256) irr_heavy_kernel(const SolveArgs A) {
 
 // ------------------------------------------------------------------------------------------------- workspace layout
 struct WsLayout {
-    size_t sites, cover, heavy, heavy_count, bins, coarse, hullws, hullinfo, folded, chunks, opos, oids, ocount, poly, total;
+    size_t sites, cover, heavy, heavy_count, hole_count, bins, coarse, hullws, hullinfo, folded, chunks, opos, oids, ocount, poly, total;
     size_t zero_begin, zero_bytes;   // region cleared before every call (bins, coarse, hull keys, folded flags)
     int nbx, nby, ncx, ncy, nb, nc;
 };
@@ -1333,6 +1376,8 @@ static WsLayout ws_layout(int N, int H, int W) {
     L.chunks = o;
     o = align_up(o + (size_t)N * ((L.nb + SCAN_CHUNK - 1) / SCAN_CHUNK) * 4, 256);
     L.heavy_count = o;
+    o = align_up(o + 4, 256);
+    L.hole_count = o;
     o = align_up(o + 4, 256);
     L.ocount = o;
     o = align_up(o + (size_t)N * 4, 256);
@@ -1476,8 +1521,11 @@ extern "C" int ofk_forward_s_ex(const float* payload, int C, const float* flow, 
     }
 
     // ---- irregular part: boundary sites -> bins -> hull filter -> per-pixel point location
+    // the list of removed points shares its buffer with the work items of the pocket pass (used one after the other)
+    const unsigned int hole_cap = (unsigned int)std::min<size_t>(((size_t)N * H * W + 8) / 8, 0xffffffffu);
     IrrArgs I{flow, point_mask, d_folded, d_bins, d_coarse, d_sites, flow_sign, H, W, L.nbx, L.nby, L.ncx, L.ncy,
-              (point_mask == nullptr && H >= 3 && W >= 3) ? 1 : 0};
+              (point_mask == nullptr && H >= 3 && W >= 3) ? 1 : 0, reinterpret_cast<unsigned long long*>(base + L.heavy),
+              reinterpret_cast<unsigned int*>(base + L.hole_count), hole_cap};
     const long long cand = I.perimeter_only ? 2ll * W + 2ll * (H - 2) : (long long)H * W;
     dim3 sgrid((unsigned)((cand + 255) / 256), N);
     irr_sites_kernel<0><<<sgrid, 256, 0, st>>>(I);
@@ -1528,9 +1576,13 @@ extern "C" int ofk_forward_s_ex(const float* payload, int C, const float* flow, 
     hull_wrap_kernel<<<N, 256, 0, st>>>(O);
     OFK_LAUNCHED();
 
+    PocketArgs Pk{payload, flow, payload_mask, d_folded, reinterpret_cast<const fwd::HullPoly*>(base + L.poly), out,
+                  out_mask, d_cover, flow_sign, C, strict, H, W};
+    if (point_mask != nullptr && H >= 3 && W >= 3) {
+        irr_holes_kernel<<<sm_count() * 8, 128, 0, st>>>(Pk, point_mask, I.holes, I.hole_count, hole_cap);
+        OFK_LAUNCHED();
+    }
     if (I.perimeter_only) {
-        PocketArgs Pk{payload, flow, payload_mask, d_folded, reinterpret_cast<const fwd::HullPoly*>(base + L.poly), out,
-                      out_mask, d_cover, flow_sign, C, strict, H, W};
         const int P = 2 * W + 2 * H - 4;
         irr_border_edges_kernel<<<dim3(std::min((P + 255) / 256, 8), N), 256, 0, st>>>(Pk);
         OFK_LAUNCHED();

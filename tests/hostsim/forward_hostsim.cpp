@@ -182,9 +182,34 @@ extern "C" int fwd_hostsim(const float* payload, int C, const float* flow, float
             };
             const int P = perim_count(H, W);
             NoShare noshare;
-            if (!pocket_triangulate(g, k0, 0, ((k1 - k0) % P + P) % P, solo, tri, noshare)) ++stats[3];
+            const PerimArc arc{H, W, P, k0};
+            if (!pocket_triangulate(g, arc, 0, ((k1 - k0) % P + P) % P, solo, tri, noshare)) ++stats[3];
             pocket_chord(g, k0, k1, solo, seg);
         }
+    }
+    // ---- small faces left by removed points: triangulated by the thread of their first removed point
+    if (point_mask != nullptr && (flags & 8) == 0) {
+        const uint8_t* pm = payload_mask;
+        for (int r = 0; r < H; ++r)
+            for (int c = 0; c < W; ++c) {
+                if (point_mask[(size_t)r * W + c]) continue;
+                auto tri = [&](uint32_t ia, uint32_t ib, uint32_t ic, const P2& pa, const P2& pb, const P2& pc) {
+                    auto pixel = [&](int x, int y, double w0, double w1, double w2) {
+                        const size_t px = (size_t)y * W + x;
+                        if (cover[px]) {
+                            if (cover[px] == 2) ++stats[6];
+                            return;
+                        }
+                        cover[px] = 2;
+                        ++stats[1];
+                        interp_store(payload + (size_t)ia * C, payload + (size_t)ib * C, payload + (size_t)ic * C,
+                                     pm ? pm[ia] != 0 : true, pm ? pm[ib] != 0 : true, pm ? pm[ic] != 0 : true, w0, w1,
+                                     w2, C, out + px * C, out_mask ? out_mask + px : nullptr, rule_strict);
+                    };
+                    raster_triangle(pa, pb, pc, ia, ib, ic, W, H, Coop{0, 1}, pixel);
+                };
+                if (hole_fill(g, point_mask, r, c, tri)) ++stats[4];
+            }
     }
     // ---- irregular part
     for (int y = 0; y < H; ++y) {
