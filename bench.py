@@ -482,6 +482,31 @@ def main():
                 stream.synchronize()
                 best = min(best, e0.elapsed_ms(e1))
             modes12["mode%d_t" % mode] = {"ms": best, "value": MB * H * W / best / 1e3}
+    # ---------------------------------------------------------------- source-referenced resampler (cfg 3 operations)
+    forward = None
+    if not args.no_modes12:
+        import golden_inputs as gi
+        FB = min(B, 8)
+        rot = of.FlowBatch.from_transforms([gi.cfg4_transforms(i) for i in range(FB)], (H, W), 's')
+        smooth = of.FlowBatch(np.ascontiguousarray(np.broadcast_to(gi.smooth_field(H, W)[None], (FB, H, W, 2))), 's')
+        rot_m = of.FlowBatch._wrap(rot.vecs, 's', fa.masks.frames(0, FB))
+        forward = {"frames": FB, "what": "FlowBatch.invert() (same reference: ofk_forward_s, 18 B/px) on %d 1080p 's' "
+                   "flows, device-resident: cfg-4 similarity transforms with full masks, the smooth non-affine field of "
+                   "SURVEY 8d with full masks (hull pockets), the transforms with 2 %% of the points removed "
+                   "(consider_mask: holes bridged); Mpixel/s, fraction of the HBM roofline" % FB}
+        for name, fl in (("rotation", rot), ("smooth", smooth), ("rotation_2pct_removed", rot_m)):
+            fl.invert()
+            stream.synchronize()
+            best = 1e30
+            for _ in range(3):
+                e0, e1 = Event(), Event()
+                e0.record(stream)
+                fl.invert()
+                e1.record(stream)
+                stream.synchronize()
+                best = min(best, e0.elapsed_ms(e1))
+            forward[name] = {"ms": best, "value": FB * H * W / best / 1e3,
+                             "frac": FB * H * W * 18 / (best * 1e-3) / 1e9 / peak}
     cpu = None
     if not args.no_cpu_baseline:
         import cv2
@@ -514,6 +539,8 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
     if modes12 is not None:
         line["modes12"] = modes12
+    if forward is not None:
+        line["forward_s"] = forward
     if gather is not None:
         line["gather"] = gather
     print(json.dumps(line))

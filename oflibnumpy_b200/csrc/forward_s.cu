@@ -528,14 +528,20 @@ struct IrrArgs {
     uint32_t* sites;     // [N][H * W]
     float sign;
     int H, W, nbx, nby, ncx, ncy;
-    int perimeter_only;  // no point mask: the boundary sites are the frame border
+    int perimeter_only;  // no point mask at all: every frame's boundary sites are the frame border
+    const int* masked;   // [N] set when the frame's point mask removes a point; a frame without removed points is
+                         // handled like one without a point mask (Flow.apply passes the flow's mask, mostly all true)
     unsigned long long* holes;   // removed points (frame << 32 | index), the candidates for hole_fill()
     unsigned int* hole_count;
     unsigned int hole_cap;
 };
 
+__device__ __forceinline__ bool frame_is_plain(const int* masked, int n, int H, int W) {
+    return H >= 3 && W >= 3 && (masked == nullptr || masked[n] == 0);
+}
+
 __device__ __forceinline__ bool irr_site_of_thread(const IrrArgs& A, int n, long long t, int& row, int& col) {
-    if (A.perimeter_only) {
+    if (A.perimeter_only || frame_is_plain(A.masked, n, A.H, A.W)) {
         const long long P = 2ll * A.W + 2ll * (A.H - 2);
         if (t >= P) return false;
         if (t < A.W) {
@@ -557,6 +563,26 @@ __device__ __forceinline__ bool irr_site_of_thread(const IrrArgs& A, int n, long
     return is_boundary_site(A.point_mask ? A.point_mask + (size_t)n * A.H * A.W : nullptr, A.H, A.W, row, col);
 }
 
+// does the point mask of a frame remove anything?
+__global__ void __launch_bounds__(256) fwd_scan_mask_kernel(const uint8_t* __restrict__ point_mask, size_t frame_px,
+                                                            int* __restrict__ masked) {
+    const int n = blockIdx.y;
+    const uint8_t* m = point_mask + (size_t)n * frame_px;
+    bool zero = false;
+    const size_t words = ((reinterpret_cast<uintptr_t>(m) & 15) == 0) ? frame_px / 16 : 0;
+    const uint4* m4 = reinterpret_cast<const uint4*>(m);
+    for (size_t k = (size_t)blockIdx.x * 256 + threadIdx.x; k < words; k += (size_t)gridDim.x * 256) {
+        const uint4 v = m4[k];
+        // a zero byte in any of the four words
+        const uint32_t z = ((v.x - 0x01010101u) & ~v.x) | ((v.y - 0x01010101u) & ~v.y) | ((v.z - 0x01010101u) & ~v.z) |
+                           ((v.w - 0x01010101u) & ~v.w);
+        zero = zero || (z & 0x80808080u) != 0u;
+    }
+    for (size_t k = words * 16 + (size_t)blockIdx.x * 256 + threadIdx.x; k < frame_px; k += (size_t)gridDim.x * 256)
+        zero = zero || m[k] == 0;
+    if (__syncthreads_or(zero ? 1 : 0) && threadIdx.x == 0) masked[n] = 1;
+}
+
 template <int PASS>   // 0: count sites per bin, 1: fill the site lists (bins hold the end offsets, counted down)
 __global__ void __launch_bounds__(256) irr_sites_kernel(const IrrArgs A) {
     const int n = blockIdx.y;
@@ -564,7 +590,7 @@ __global__ void __launch_bounds__(256) irr_sites_kernel(const IrrArgs A) {
     int row, col;
     const size_t frame = (size_t)n * A.H * A.W;
     if (!irr_site_of_thread(A, n, (long long)blockIdx.x * 256 + threadIdx.x, row, col)) {
-        if (PASS == 0 && !A.perimeter_only) {   // a removed point: queued for the small-face pass
+        if (PASS == 0 && !A.perimeter_only && !frame_is_plain(A.masked, n, A.H, A.W)) {   // a removed point: queued
             const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
             if (t < (long long)A.H * A.W && A.point_mask != nullptr && !A.point_mask[frame + t]) {
                 const unsigned slot = atomicAdd(A.hole_count, 1u);
@@ -697,7 +723,7 @@ __device__ __forceinline__ SiteGrid hull_grid(const HullArgs& A, int n) {
     return g;
 }
 
-constexpr int HULL_ITEMS = 4;   // sites per thread
+constexpr int HULL_ITEMS = 8;   // sites per thread
 
 template <int PASS>   // 0: largest dot product per direction, 1: smallest site id among the maximisers, 2: edge slack
 __global__ void __launch_bounds__(256) hull_sites_kernel(const HullArgs A) {
@@ -710,39 +736,44 @@ __global__ void __launch_bounds__(256) hull_sites_kernel(const HullArgs A) {
     HullWs& ws = A.ws[n];
     const HullInfo& info = A.info[n];
     const int lane = threadIdx.x & 31;
+    const int count = PASS == 2 ? info.m : HULL_DIRS;
+    // every thread folds its sites first, one warp reduction and one atomic per direction at the end (with removed
+    // points the rims of all holes are boundary sites: a hundred times more of them than on the frame border)
+    unsigned long long acc[HULL_DIRS];
+#pragma unroll
+    for (int k = 0; k < HULL_DIRS; ++k) acc[k] = PASS == 2 ? ~0ull : 0ull;
     for (int it = 0; it < HULL_ITEMS; ++it) {
         const uint32_t s = s0 + it * 256 + threadIdx.x;
-        bool have = s < total;
-        const uint32_t id = have ? g.sites[s] : 0u;
-        if (PASS != 2) {
-            // the polygon only has to lie inside the hull: its vertices are taken from the frame border (with removed
-            // points every rim of a hole is a boundary site, a hundred times more of them, none of them extreme)
-            const uint32_t row = id / (uint32_t)A.W, col = id - row * (uint32_t)A.W;
-            have = have && (row == 0u || col == 0u || row == (uint32_t)(A.H - 1) || col == (uint32_t)(A.W - 1));
-            if (!__any_sync(0xffffffffu, have)) continue;
-        }
-        P2 p;
-        p.x = p.y = 0.0;
-        if (have) p = site_pos(g, id);
-        const int count = PASS == 2 ? info.m : HULL_DIRS;
-        for (int k = 0; k < count; ++k) {
+        if (s >= total) break;
+        const uint32_t id = g.sites[s];
+        const P2 p = site_pos(g, id);
+#pragma unroll
+        for (int k = 0; k < HULL_DIRS; ++k) {
             if (PASS == 0) {
-                unsigned long long key = have ? order_key(dfma(A.dirs.dx[k], p.x, dmul(A.dirs.dy[k], p.y))) : 0ull;
-                for (int o = 16; o > 0; o >>= 1) {
-                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
-                    key = other > key ? other : key;
-                }
-                if (lane == 0 && key != 0ull) atomicMax(&ws.dotkey[k], key);
+                const unsigned long long key = order_key(dfma(A.dirs.dx[k], p.x, dmul(A.dirs.dy[k], p.y)));
+                acc[k] = key > acc[k] ? key : acc[k];
             } else if (PASS == 1) {
-                const bool hit = have && order_key(dfma(A.dirs.dx[k], p.x, dmul(A.dirs.dy[k], p.y))) == ws.dotkey[k];
-                if (hit) atomicMin(&ws.ext[k], id);
+                if (order_key(dfma(A.dirs.dx[k], p.x, dmul(A.dirs.dy[k], p.y))) == ws.dotkey[k]) atomicMin(&ws.ext[k], id);
+            } else if (k < count) {
+                const unsigned long long key = order_key(hull_edge_orient(info, k, p));
+                acc[k] = key < acc[k] ? key : acc[k];
+            }
+        }
+    }
+    if (PASS == 1) return;
+#pragma unroll
+    for (int k = 0; k < HULL_DIRS; ++k) {
+        if (PASS == 2 && k >= count) break;
+        unsigned long long key = acc[k];
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+            key = PASS == 0 ? (other > key ? other : key) : (other < key ? other : key);
+        }
+        if (lane == 0) {
+            if (PASS == 0) {
+                if (key != 0ull) atomicMax(&ws.dotkey[k], key);
             } else {
-                unsigned long long key = have ? order_key(hull_edge_orient(info, k, p)) : ~0ull;
-                for (int o = 16; o > 0; o >>= 1) {
-                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
-                    key = other < key ? other : key;
-                }
-                if (lane == 0) atomicMin(&ws.slackkey[k], key);
+                atomicMin(&ws.slackkey[k], key);
             }
         }
     }
@@ -898,6 +929,7 @@ struct PocketArgs {
     const float* flow;
     const uint8_t* payload_mask;
     const int* folded;
+    const int* masked;       // [N] or nullptr, see IrrArgs
     const HullPoly* poly;
     float* out;
     uint8_t* out_mask;
@@ -992,7 +1024,7 @@ __global__ void __launch_bounds__(128) irr_holes_kernel(const PocketArgs A, cons
 // straight border: every pixel of a column after an integer shift) ...
 __global__ void __launch_bounds__(256) irr_border_edges_kernel(const PocketArgs A) {
     const int n = blockIdx.y;
-    if (A.folded[n]) return;
+    if (A.folded[n] || !frame_is_plain(A.masked, n, A.H, A.W)) return;
     const size_t frame = (size_t)n * A.H * A.W;
     const SiteGrid g = pocket_grid(A, frame);
     unsigned long long pixels = 0;
@@ -1043,7 +1075,7 @@ struct PocketShare {
 
 __global__ void __launch_bounds__(256) irr_pockets_kernel(const PocketArgs A) {
     const int n = blockIdx.y;
-    if (A.folded[n]) return;
+    if (A.folded[n] || !frame_is_plain(A.masked, n, A.H, A.W)) return;
     const HullPoly& hp = A.poly[n];
     if (!hp.ok) return;
     __shared__ PocketPool pool;
@@ -1333,7 +1365,7 @@ __global__ void __launch_bounds__(256) irr_heavy_kernel(const SolveArgs A) {
 
 // ------------------------------------------------------------------------------------------------- workspace layout
 struct WsLayout {
-    size_t sites, cover, heavy, heavy_count, hole_count, bins, coarse, hullws, hullinfo, folded, chunks, opos, oids, ocount, poly, total;
+    size_t sites, cover, heavy, heavy_count, hole_count, masked, bins, coarse, hullws, hullinfo, folded, chunks, opos, oids, ocount, poly, total;
     size_t zero_begin, zero_bytes;   // region cleared before every call (bins, coarse, hull keys, folded flags)
     int nbx, nby, ncx, ncy, nb, nc;
 };
@@ -1379,6 +1411,8 @@ static WsLayout ws_layout(int N, int H, int W) {
     o = align_up(o + 4, 256);
     L.hole_count = o;
     o = align_up(o + 4, 256);
+    L.masked = o;
+    o = align_up(o + (size_t)N * 4, 256);
     L.ocount = o;
     o = align_up(o + (size_t)N * 4, 256);
     L.zero_bytes = o - L.zero_begin;
@@ -1523,8 +1557,15 @@ extern "C" int ofk_forward_s_ex(const float* payload, int C, const float* flow, 
     // ---- irregular part: boundary sites -> bins -> hull filter -> per-pixel point location
     // the list of removed points shares its buffer with the work items of the pocket pass (used one after the other)
     const unsigned int hole_cap = (unsigned int)std::min<size_t>(((size_t)N * H * W + 8) / 8, 0xffffffffu);
+    int* d_masked = point_mask != nullptr ? reinterpret_cast<int*>(base + L.masked) : nullptr;
+    if (point_mask != nullptr) {
+        fwd_scan_mask_kernel<<<dim3(std::max(1, std::min(64, (sm_count() * 8 + N - 1) / N)), N), 256, 0, st>>>(
+            point_mask, (size_t)H * W, d_masked);
+        OFK_LAUNCHED();
+    }
     IrrArgs I{flow, point_mask, d_folded, d_bins, d_coarse, d_sites, flow_sign, H, W, L.nbx, L.nby, L.ncx, L.ncy,
-              (point_mask == nullptr && H >= 3 && W >= 3) ? 1 : 0, reinterpret_cast<unsigned long long*>(base + L.heavy),
+              (point_mask == nullptr && H >= 3 && W >= 3) ? 1 : 0, d_masked,
+              reinterpret_cast<unsigned long long*>(base + L.heavy),
               reinterpret_cast<unsigned int*>(base + L.hole_count), hole_cap};
     const long long cand = I.perimeter_only ? 2ll * W + 2ll * (H - 2) : (long long)H * W;
     dim3 sgrid((unsigned)((cand + 255) / 256), N);
@@ -1576,13 +1617,13 @@ extern "C" int ofk_forward_s_ex(const float* payload, int C, const float* flow, 
     hull_wrap_kernel<<<N, 256, 0, st>>>(O);
     OFK_LAUNCHED();
 
-    PocketArgs Pk{payload, flow, payload_mask, d_folded, reinterpret_cast<const fwd::HullPoly*>(base + L.poly), out,
-                  out_mask, d_cover, flow_sign, C, strict, H, W};
+    PocketArgs Pk{payload, flow, payload_mask, d_folded, d_masked, reinterpret_cast<const fwd::HullPoly*>(base + L.poly),
+                  out, out_mask, d_cover, flow_sign, C, strict, H, W};
     if (point_mask != nullptr && H >= 3 && W >= 3) {
         irr_holes_kernel<<<sm_count() * 8, 128, 0, st>>>(Pk, point_mask, I.holes, I.hole_count, hole_cap);
         OFK_LAUNCHED();
     }
-    if (I.perimeter_only) {
+    if (H >= 3 && W >= 3) {   // frames without removed points (per-frame test inside)
         const int P = 2 * W + 2 * H - 4;
         irr_border_edges_kernel<<<dim3(std::min((P + 255) / 256, 8), N), 256, 0, st>>>(Pk);
         OFK_LAUNCHED();

@@ -75,6 +75,7 @@ stats0 = [c('ofk_rt_path_count', k) for k in range(6, 10)]
 timeit("rotation: invert / switch_ref, full masks (18 B/px)", 18, fwd(fa.vecs, 2, fa.vecs, fa.masks, None, o_v))
 timeit("rotation: apply 's' f32x3 + valid (33 B/px)", 33, fwd(imgf, 3, fa.vecs, None, None, o_f))
 timeit("rotation: valid_target 's' (8+1+1 = 10 B/px)", 10, fwd(None, 0, fa.vecs, fa.masks, None, None))
+timeit("smooth field: invert as Flow.invert() calls it (all-true point mask)", 18, fwd(fsm.vecs, 2, fsm.vecs, fsm.masks, fsm.masks, o_v), reps=3)
 timeit("rotation: invert, 2 % points removed, consider_mask (18 B/px)", 18, fwd(fa.vecs, 2, fa.vecs, mask, mask, o_v))
 timeit("rotation: invert, 2 % masked, consider_mask=False (18 B/px)", 18, fwd(fa.vecs, 2, fa.vecs, mask, None, o_v))
 timeit("smooth field: invert, full masks (18 B/px)", 18, fwd(fsm.vecs, 2, fsm.vecs, fsm.masks, None, o_v), reps=3)
