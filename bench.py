@@ -149,7 +149,7 @@ def cpu_frames(count, ref=None):
     return frames
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, restore_stdout=lambda: None):
     if rank != 0:
         return
     import cv2
@@ -174,6 +174,7 @@ def run_reference(args, rank, world):
                                        (sample, "oflibnumpy 1.1.1 itself (baseline/_ref: Flow.apply + Flow.combine_with)"
                                         if ref is not None else "the oracle port", cores)},
             "e2e": {"value": value, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    restore_stdout()
     print(json.dumps(line))
 
 
@@ -200,8 +201,18 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
 
+    # stdout carries the ONE JSON line and nothing else: whatever libraries print there meanwhile (NCCL announces its
+    # version on stdout) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def restore_stdout():
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+
     if args.impl == 'reference':
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, restore_stdout)
         return
 
     import oflibnumpy_b200 as of
@@ -543,6 +554,7 @@ def main():
         line["forward_s"] = forward
     if gather is not None:
         line["gather"] = gather
+    restore_stdout()
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
