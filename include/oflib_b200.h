@@ -107,7 +107,9 @@ int ofk_warp_t(const void* payload, int dtype, int C, int arith, const float* fl
  * If A is zero on its valid pixels (|c| < thr when thr > 0, exact 0 otherwise) frame n of out is a copy of B (and of
  * A if B is zero), as the reference returns that operand. flags (int32 [N][2], device) receives
  * {A_nonzero, B_nonzero} per frame so the host can restore object identity; with flags == NULL the zero tests and
- * the early exits are skipped (plain composition). Am/Bm may be NULL (all valid). */
+ * the early exits are skipped (plain composition). Am/Bm may be NULL (all valid). Mask bytes must be 0 or 1 (numpy
+ * bool): the kernels AND them as words; a caller holding "non-zero = valid" bytes normalises them first (ofk_greater
+ * with threshold 0 on a float copy, or host side). */
 int ofk_combine3(const float* A, const uint8_t* Am, const float* B, const uint8_t* Bm, int ref /* 's' or 't' */,
                  float thr, float* out, uint8_t* out_mask, int* flags, int N, int H, int W, ofk_stream_t stream);
 
@@ -219,9 +221,12 @@ int ofk_decode_sintel_mask(const uint8_t* invalid, uint8_t* mask, size_t n_pixel
 /* Source-referenced (forward) resampling: replaces `griddata(grid + flow, payload, grid, 'linear')` + nan_to_num in
  * apply_flow (utils.py:237-258): the Delaunay triangulation of the displaced pixel positions p + flow_sign * flow[p]
  * with barycentric interpolation (float64 geometry) and 0 outside the convex hull. Cells of the displaced grid with
- * four valid corners are rasterised directly (each split along its Delaunay diagonal); everything else -- holes left
- * by removed points, the pockets between the displaced frame border and its convex hull -- is located per pixel in
- * the Delaunay triangulation of the boundary points, exactly as Qhull bridges them.
+ * four valid corners are rasterised directly (each split along its Delaunay diagonal); everything else is covered by
+ * the Delaunay triangles of the boundary points, exactly as Qhull bridges them: the pockets between the displaced frame
+ * border and its convex hull (frames without removed points) and the small faces left by removed points are
+ * triangulated explicitly and rasterised with the same fill rule, what remains (large or border-touching faces) is
+ * located per pixel in the triangulation of the boundary points. A frame whose point_mask removes nothing is treated
+ * like one without a point mask (tested per frame on the device).
  *   payload       float32 [N,H,W,C]; payload_mask [N,H,W] (or NULL = all valid) is resampled with it and turned into
  *                 out_mask by mask_rule: OFK_RULE_STRICT (float payloads: interpolated mask == 1 after the float32
  *                 cast) or OFK_RULE_GT_HALF (integer payloads: numpy.round(interpolated mask) == 1)
