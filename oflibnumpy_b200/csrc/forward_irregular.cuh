@@ -827,7 +827,8 @@ OFK_HD bool pocket_triangulate(const SiteGrid& g, const ArcFn& arc, int i0, int 
 // thread of the FIRST removed point of a face (smallest index) walks the boundary: from the directed edge a -> b (b the
 // neighbour of a in direction k, the face on its left, an intact cell on its right) the boundary continues from b
 // along the first direction, turning back from k + 1, that has an intact cell on its right. Faces that are larger,
-// touch the frame border, are pinched at a vertex or hold a site are left to the per-pixel search.
+// touch the frame border, are pinched at a vertex, hold a site or surround an island of intact cells are left to the
+// per-pixel search.
 constexpr int HOLE_MAXV = 48;
 
 // cell (ci, cj) = the pixels (ci, cj), (ci, cj+1), (ci+1, cj), (ci+1, cj+1); intact when all four are present
@@ -888,6 +889,19 @@ OFK_HD bool hole_loop(const uint8_t* pm, int H, int W, int r, int c, HoleLoop& L
     for (int i = 0; i < n; ++i)       // pinched at a vertex: not a simple polygon
         for (int j = i + 1; j < n; ++j)
             if (fwd_order[i] == fwd_order[j]) return false;
+    // an intact cell inside the polygon: the face is a ring around an island of the mesh (four removed points in a
+    // pinwheel do that), not a simple polygon. Crossing number of the cell centre against the vertical boundary edges.
+    for (int ci = rmin; ci < rmax; ++ci)
+        for (int cj = cmin; cj < cmax; ++cj) {
+            if (!cell_intact(pm, H, W, ci, cj)) continue;
+            int crossings = 0;
+            for (int i = 0; i < n; ++i) {
+                const uint32_t u = fwd_order[i], v = fwd_order[i + 1 == n ? 0 : i + 1];
+                const int ur = (int)(u / (uint32_t)W), uc = (int)(u % (uint32_t)W), vr = (int)(v / (uint32_t)W);
+                if (ur != vr && uc > cj && (ur < vr ? ur : vr) == ci) ++crossings;
+            }
+            if (crossings & 1) return false;
+        }
     for (int y = rmin + 1; y < rmax; ++y)   // a site that no intact cell touches may lie inside the face
         for (int x = cmin + 1; x < cmax; ++x)
             if (pm[(size_t)y * W + x] && !cell_intact(pm, H, W, y, x) && !cell_intact(pm, H, W, y, x - 1) &&

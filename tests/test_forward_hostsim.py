@@ -33,7 +33,7 @@ def sim(tmp_path_factory):
     def ptr(a):
         return None if a is None else a.ctypes.data_as(C.c_void_p)
 
-    def run(payload, flow, sign=1.0, payload_mask=None, point_mask=None, strict=True, flip=0.0):
+    def run(payload, flow, sign=1.0, payload_mask=None, point_mask=None, strict=True, flip=0.0, flags=1):
         h, w = flow.shape[:2]
         pay = None if payload is None else np.ascontiguousarray(payload, np.float32)
         c = 0 if pay is None else pay.shape[2]
@@ -44,7 +44,8 @@ def sim(tmp_path_factory):
         pt = None if point_mask is None else np.ascontiguousarray(point_mask).view(np.uint8)
         fl = np.ascontiguousarray(flow, np.float32)
         lib.fwd_hostsim(ptr(pay), c, ptr(fl), C.c_float(sign), ptr(pm), ptr(pt), ptr(out), ptr(om), int(strict), h, w,
-                        1, C.c_double(flip), ptr(stats))
+                        flags, C.c_double(flip), ptr(stats))
+        run.stats = stats
         assert stats[3] == 0, "point-location walks that did not terminate"
         assert stats[5] == 0, "folded cells"
         assert stats[6] == 0, "pixels produced by more than one triangle: the fill rule is broken"
@@ -185,3 +186,41 @@ def test_integer_translation_and_exact_hull_edges(sim):
         wm[ys, xs] = True
         assert np.array_equal(m, wm)
         assert np.array_equal(vals, want)
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize('masked', [False, True])
+def test_enumerated_triangles_equal_the_per_pixel_search(sim, masked):
+    """Hull pockets (frames without removed points) and the small faces left by removed points are triangulated
+    explicitly and rasterised; flags 4 / 8 switch that off, so that every pixel outside the intact cells is located by
+    the walk through the Delaunay triangulation of the boundary sites instead. Both are the same triangulation: masks
+    identical, values equal to rounding (the weights come out of different but equivalent expressions)."""
+    inp = gi.cfg3_full()
+    v, img = inp['smooth'], inp['img_f32c3']
+    m = inp['mask'] if masked else None
+    a_v, a_m = sim(img, v, 1.0, m, m)
+    produced = int(sim.stats[1])
+    b_v, b_m = sim(img, v, 1.0, m, m, flags=1 | 4 | 8)
+    assert produced > 1000 and int(sim.stats[1]) >= produced      # the search path now finds all of them itself
+    assert np.array_equal(a_m, b_m)
+    assert np.abs(a_v - b_v)[a_m].max() <= 1e-4
+
+
+@pytest.mark.parametrize('density', [0.02, 0.06, 0.12, 0.25])
+def test_enumerated_faces_equal_the_search_on_random_masks(sim, density):
+    """The same equivalence over masks of growing density (faces merge, pinch, surround islands of intact cells and
+    single points, reach the frame border): whatever hole_loop() accepts has to be a simple polygon without anything
+    inside, everything else has to be left to the search."""
+    h, w = 150, 220
+    for seed in range(3):
+        rng = np.random.default_rng(100 + seed)
+        v = (gi.smooth_field(h, w) * 0.6).astype(np.float32)
+        m = rng.random((h, w)) > density
+        yy, xx = np.mgrid[:h, :w].astype(np.float32)
+        pay = np.stack([xx, yy, rng.random((h, w)).astype(np.float32) * 255], -1)
+        a_v, a_m = sim(pay, v, 1.0, m, m)
+        faces = int(sim.stats[4])
+        b_v, b_m = sim(pay, v, 1.0, m, m, flags=1 | 4 | 8)
+        assert faces > 20
+        assert np.array_equal(a_m, b_m)
+        assert np.abs(a_v - b_v)[a_m].max() <= 1e-3

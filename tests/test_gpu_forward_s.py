@@ -345,3 +345,44 @@ def test_next_rows_track_resize_padding(of):
     assert np.issubdtype(got.dtype, np.integer)
     f = of.from_transforms([['translation', 10, 20]], (512, 512), 's')
     np.testing.assert_array_equal(of.track_pts(f, 's', np.array([[20, 10], [8, 7]])), [[40, 20], [28, 17]])
+
+
+def test_point_mask_that_removes_nothing_takes_the_unmasked_path(of):
+    """Flow.apply / invert hand the flow's mask to ofk_forward_s as `consider_mask`; a frame whose mask is all true is
+    recognised on the device and processed like one without a point mask (hull pockets triangulated arc by arc):
+    bit-identical outputs, in a batch that mixes both kinds of frames."""
+    from oflibnumpy_b200 import _lib, _ops
+    from oflibnumpy_b200.device import DeviceArray
+    h, w = 200, 320
+    rng = np.random.default_rng(11)
+    flows = np.stack([gi.smooth_field(h, w), gi.smooth_field(h, w) * 0.5, gi.smooth_field(h, w)]).astype(np.float32)
+    masks = np.ones((3, h, w), bool)
+    masks[1] = rng.random((h, w)) > 0.03
+    pay = rng.random((3, h, w, 2)).astype(np.float32)
+    d_f, d_p = DeviceArray.from_numpy(flows), DeviceArray.from_numpy(pay)
+    d_m = DeviceArray.from_numpy(masks.view(np.uint8))
+    o1, m1 = _ops.forward_s(d_f, 1.0, d_p, d_m, d_m)
+    # frames 0 and 2 alone, without any point mask
+    sel = np.ascontiguousarray(flows[[0, 2]])
+    o2, m2 = _ops.forward_s(DeviceArray.from_numpy(sel), 1.0, DeviceArray.from_numpy(np.ascontiguousarray(pay[[0, 2]])),
+                            None, None)
+    o1, m1, o2, m2 = o1.numpy(), m1.numpy(), o2.numpy(), m2.numpy()
+    assert np.array_equal(m1[[0, 2]], m2) and np.array_equal(o1[[0, 2]], o2)
+    assert m2.any() and not m2.all()
+    # the masked frame in the middle equals the same frame processed alone
+    o3, m3 = _ops.forward_s(DeviceArray.from_numpy(flows[1:2]), 1.0, DeviceArray.from_numpy(pay[1:2]),
+                            DeviceArray.from_numpy(masks[1:2].view(np.uint8)),
+                            DeviceArray.from_numpy(masks[1:2].view(np.uint8)))
+    assert np.array_equal(m1[1:2], m3.numpy()) and np.array_equal(o1[1:2], o3.numpy())
+
+
+def test_forward_s_is_deterministic(of):
+    """Pockets are shared between the warps of a CTA and holes between threads in whatever order the scheduler picks:
+    the result may not depend on it."""
+    g = load_golden('forward')
+    v = g['in_smooth']
+    fs = of.Flow(v, 's', g['in_mask'])
+    first = fs.apply(g['in_img_f32c3'], return_valid_area=True)
+    for _ in range(5):
+        again = fs.apply(g['in_img_f32c3'], return_valid_area=True)
+        assert np.array_equal(first[0], again[0]) and np.array_equal(first[1], again[1])

@@ -907,3 +907,35 @@ def test_host_buffer_api_with_plain_numpy_batches(of):
         dv, dm = FlowBatch(a, 't', am).combine_with(FlowBatch(b, 't', bm), 3).numpy()
         same(v, dv)
         same(m.view(np.uint8), dm.view(np.uint8))
+
+
+def test_torch_cuda_tensors_pass_through_zero_copy(of):
+    """Optional PyTorch interop (north star): torch.cuda tensors are adopted through __cuda_array_interface__ without
+    a copy -- as flow vectors / masks of Flow and FlowBatch -- and results are exported the same way."""
+    torch = pytest.importorskip('torch')
+    if not torch.cuda.is_available():
+        pytest.skip('torch sees no GPU')
+    h, w = 96, 160
+    rng = np.random.default_rng(3)
+    vecs = (rng.random((h, w, 2)).astype(np.float32) - 0.5) * 6
+    mask = rng.random((h, w)) > 0.1
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    tv = torch.from_numpy(vecs).cuda()
+    tm = torch.from_numpy(mask.view(np.uint8)).cuda()
+    torch.cuda.synchronize()
+    f_t = of.Flow(tv, 't', tm)
+    assert f_t.vecs_device.ptr == tv.data_ptr() and f_t.mask_device.ptr == tm.data_ptr()      # adopted, not copied
+    f_n = of.Flow(vecs, 't', mask)
+    a, va = f_t.apply(img, return_valid_area=True)
+    b, vb = f_n.apply(img, return_valid_area=True)
+    assert np.array_equal(a, b) and np.array_equal(va, vb)
+    c_t, c_n = f_t.combine_with(f_n, 3), f_n.combine_with(f_n, 3)
+    assert np.array_equal(c_t.vecs, c_n.vecs) and np.array_equal(c_t.mask, c_n.mask)
+    # export: a torch view of the result's device storage, no copy
+    out = torch.as_tensor(c_t.vecs_device, device='cuda')
+    assert out.data_ptr() == c_t.vecs_device.ptr
+    assert np.array_equal(out.cpu().numpy(), c_n.vecs)
+    # batch container
+    fb = of.FlowBatch(torch.stack([tv, tv]), 't', torch.stack([tm, tm]))
+    r = fb.combine_with(fb, 3)
+    assert np.array_equal(r.vecs.numpy()[1], c_n.vecs)
