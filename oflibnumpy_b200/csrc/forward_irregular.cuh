@@ -47,6 +47,7 @@ struct SiteGrid {
     const uint32_t* sites;     // site ids (row * W + col), grouped by bin
     const float* flow;         // [H, W, 2] of this frame
     float sign;
+    uint32_t inv_w;            // grid_inv(W): index -> (row, col) without an integer division (0: divide)
 };
 
 OFK_HD int grid_bins(int extent) { return (extent + BIN - 1) >> BIN_SHIFT; }
@@ -55,8 +56,22 @@ OFK_HD int grid_coarse(int nb) { return (nb + (1 << COARSE_SHIFT) - 1) >> COARSE
 OFK_HD int grid_slots(int nbx, int nby) { return nbx * nby; }
 OFK_HD int bin_index(int nbx, int bx, int by) { return by * nbx + bx; }
 
+// floor(2^32 / W) + 1: (id * inv) >> 32 is floor(id / W) or one more, for every id < 2^32
+OFK_HD uint32_t grid_inv(int W) { return W > 1 ? (uint32_t)(0x100000000ull / (unsigned long long)W) + 1u : 0u; }
+
 OFK_HD P2 site_pos(const SiteGrid& g, uint32_t id) {
-    const int row = (int)(id / (uint32_t)g.W), col = (int)(id - (uint32_t)row * (uint32_t)g.W);
+    int row, col;
+    if (g.inv_w != 0u) {   // every search looks at dozens of sites: the division was a sixth of all instructions
+        row = (int)(((unsigned long long)id * g.inv_w) >> 32);
+        col = (int)id - row * g.W;
+        if (col < 0) {
+            --row;
+            col += g.W;
+        }
+    } else {
+        row = (int)(id / (uint32_t)g.W);
+        col = (int)(id - (uint32_t)row * (uint32_t)g.W);
+    }
     const float* f = g.flow + 2 * (size_t)id;
     return displaced(f[0], f[1], row, col, g.sign);
 }

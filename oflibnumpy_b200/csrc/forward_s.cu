@@ -589,16 +589,21 @@ __global__ void __launch_bounds__(256) irr_sites_kernel(const IrrArgs A) {
     if (A.folded[n]) return;
     int row, col;
     const size_t frame = (size_t)n * A.H * A.W;
-    if (!irr_site_of_thread(A, n, (long long)blockIdx.x * 256 + threadIdx.x, row, col)) {
-        if (PASS == 0 && !A.perimeter_only && !frame_is_plain(A.masked, n, A.H, A.W)) {   // a removed point: queued
-            const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
-            if (t < (long long)A.H * A.W && A.point_mask != nullptr && !A.point_mask[frame + t]) {
-                const unsigned slot = atomicAdd(A.hole_count, 1u);
-                if (slot < A.hole_cap) A.holes[slot] = ((unsigned long long)n << 32) | (unsigned long long)t;
-            }
+    const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+    const bool site = irr_site_of_thread(A, n, t, row, col);
+    if (PASS == 0 && !A.perimeter_only && !frame_is_plain(A.masked, n, A.H, A.W)) {
+        // removed points are queued for the small-face pass: one atomic per warp
+        const bool removed = !site && t < (long long)A.H * A.W && A.point_mask != nullptr && !A.point_mask[frame + t];
+        const unsigned bal = __ballot_sync(0xffffffffu, removed);
+        if (bal) {
+            const int lane = threadIdx.x & 31, leader = __ffs(bal) - 1;
+            unsigned slot = 0;
+            if (lane == leader) slot = atomicAdd(A.hole_count, (unsigned)__popc(bal));
+            slot = __shfl_sync(0xffffffffu, slot, leader) + __popc(bal & ((1u << lane) - 1u));
+            if (removed && slot < A.hole_cap) A.holes[slot] = ((unsigned long long)n << 32) | (unsigned long long)t;
         }
-        return;
     }
+    if (!site) return;
     const uint32_t id = (uint32_t)(row * A.W + col);
     const float2 f = __ldg(reinterpret_cast<const float2*>(A.flow) + frame + id);
     const P2 p = displaced(f.x, f.y, row, col, A.sign);
@@ -720,6 +725,7 @@ __device__ __forceinline__ SiteGrid hull_grid(const HullArgs& A, int n) {
     g.sites = A.sites + (size_t)n * A.H * A.W;
     g.flow = A.flow + 2 * (size_t)n * A.H * A.W;
     g.sign = A.sign;
+    g.inv_w = grid_inv(A.W);
     return g;
 }
 
@@ -831,6 +837,7 @@ __global__ void __launch_bounds__(256) hull_outer_kernel(const OuterArgs A) {
     g.sites = A.sites + (size_t)n * A.H * A.W;
     g.flow = A.flow + 2 * (size_t)n * A.H * A.W;
     g.sign = A.sign;
+    g.inv_w = grid_inv(A.W);
     for (uint32_t s = blockIdx.x * 256 + threadIdx.x; s < total; s += gridDim.x * 256) {
         const uint32_t id = g.sites[s];
         const P2 p = site_pos(g, id);
@@ -993,6 +1000,7 @@ __device__ __forceinline__ SiteGrid pocket_grid(const PocketArgs& A, size_t fram
     g.sites = nullptr;
     g.flow = A.flow + 2 * frame;
     g.sign = A.sign;
+    g.inv_w = grid_inv(A.W);
     return g;
 }
 
@@ -1146,6 +1154,7 @@ struct SolveArgs {
     const float* flow;
     const uint8_t* payload_mask;
     const int* folded;
+    const int* masked;               // [N] or nullptr, see IrrArgs
     const uint32_t* bins;
     const unsigned long long* occ;
     const uint32_t* sites;
@@ -1156,6 +1165,9 @@ struct SolveArgs {
     const uint8_t* cover;
     unsigned long long* heavy;       // work items of the pocket pass: frame << 40 | 8-pixel block << 8 | pixel bits
     unsigned int* heavy_count;
+    unsigned long long* todo;        // pixels that need a search: frame << 32 | pixel
+    unsigned int* todo_count;
+    unsigned int todo_cap;
     float sign;
     int C, rule_strict, H, W, nbx, nby, ncx, ncy;
 };
@@ -1163,18 +1175,50 @@ struct SolveArgs {
 constexpr int SOLVE_SPAN = 4096;          // pixels per CTA, 16 per thread
 constexpr int THREAD_BUDGET = 320;        // sites one thread looks at per apex search before the pixel goes to a warp
 
+// a located pixel is written; one outside the hull keeps its marker (fwd_finalize_kernel zeroes whatever is left: a
+// marker that turned into 0 here would look like a produced pixel to the neighbour test of irr_solve_kernel)
 __device__ __forceinline__ void solve_store(const SolveArgs& A, size_t frame, uint32_t p, int st, const uint32_t (&vid)[3],
                                             const double (&w)[3]) {
+    if (st != LOC_FOUND) return;
     const size_t px = frame + p;
-    if (st == LOC_FOUND) {
-        const uint8_t* pm = A.payload_mask ? A.payload_mask + frame : nullptr;
-        const float* pay = A.payload + frame * A.C;
-        interp_store(pay + (size_t)vid[0] * A.C, pay + (size_t)vid[1] * A.C, pay + (size_t)vid[2] * A.C,
-                     pm ? pm[vid[0]] != 0 : true, pm ? pm[vid[1]] != 0 : true, pm ? pm[vid[2]] != 0 : true, w[0], w[1],
-                     w[2], A.C, A.out + px * A.C, A.out_mask ? A.out_mask + px : nullptr, A.rule_strict);
-    } else {
-        for (int c = 0; c < A.C; ++c) A.out[px * A.C + c] = 0.f;
-        if (A.out_mask) A.out_mask[px] = 0;
+    const uint8_t* pm = A.payload_mask ? A.payload_mask + frame : nullptr;
+    const float* pay = A.payload + frame * A.C;
+    interp_store(pay + (size_t)vid[0] * A.C, pay + (size_t)vid[1] * A.C, pay + (size_t)vid[2] * A.C,
+                 pm ? pm[vid[0]] != 0 : true, pm ? pm[vid[1]] != 0 : true, pm ? pm[vid[2]] != 0 : true, w[0], w[1],
+                 w[2], A.C, A.out + px * A.C, A.out_mask ? A.out_mask + px : nullptr, A.rule_strict);
+}
+
+// Whatever still carries the marker after all passes lies outside the convex hull of the points: 0 / invalid
+// (utils.py:254-256).
+__global__ void __launch_bounds__(256) fwd_finalize_kernel(float* __restrict__ out, int C, uint8_t* __restrict__ out_mask,
+                                                           const uint8_t* __restrict__ cover, size_t frame_px,
+                                                           const int* __restrict__ folded) {
+    const int n = blockIdx.y;
+    if (folded[n]) return;
+    const size_t frame = (size_t)n * frame_px;
+    for (size_t p0 = ((size_t)blockIdx.x * 256 + threadIdx.x) * 16; p0 < frame_px; p0 += (size_t)gridDim.x * 256 * 16) {
+        const uint8_t* cv = cover + frame + p0;
+        uint32_t wds[4];
+        if (p0 + 16 <= frame_px && (reinterpret_cast<uintptr_t>(cv) & 15) == 0) {
+            const uint4 v = *reinterpret_cast<const uint4*>(cv);
+            wds[0] = v.x; wds[1] = v.y; wds[2] = v.z; wds[3] = v.w;
+        } else {
+            for (int k = 0; k < 4; ++k) {
+                wds[k] = 0;
+                for (int b = 0; b < 4; ++b)
+                    if (p0 + 4 * k + b < frame_px) wds[k] |= (uint32_t)cv[4 * k + b] << (8 * b);
+            }
+        }
+        for (int k = 0; k < 4; ++k) {
+            uint32_t hit = ((wds[k] & 0x7f7f7f7fu) + 0x01010101u) & wds[k] & 0x80808080u;   // bytes equal to 0xFF
+            while (hit) {
+                const int b = (__ffs(hit) - 1) >> 3;
+                hit &= hit - 1;
+                const size_t px = frame + p0 + 4 * k + b;
+                for (int c = 0; c < C; ++c) out[px * C + c] = 0.f;
+                if (out_mask) out_mask[px] = 0;
+            }
+        }
     }
 }
 
@@ -1189,14 +1233,12 @@ __global__ void __launch_bounds__(256) irr_solve_kernel(const SolveArgs A) {
     if (A.folded[n]) return;
     __shared__ HullInfo s_hull;
     __shared__ uint32_t s_list[SOLVE_SPAN];
-    __shared__ uint32_t s_blocks[SOLVE_SPAN / 8];
     __shared__ uint32_t s_warp[8];
     const size_t frame_px = (size_t)A.H * A.W, frame = (size_t)n * frame_px;
     const size_t p0 = (size_t)blockIdx.x * SOLVE_SPAN + (size_t)threadIdx.x * 16;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t hits[4] = {0, 0, 0, 0};
     int mine = 0;
-    for (int b = threadIdx.x; b < SOLVE_SPAN / 8; b += 256) s_blocks[b] = 0;
     if (p0 < frame_px) {
         const uint8_t* cv = A.cover + frame + p0;
         uint32_t wds[4];
@@ -1256,45 +1298,137 @@ __global__ void __launch_bounds__(256) irr_solve_kernel(const SolveArgs A) {
     g.sites = A.sites + frame;
     g.flow = A.flow + 2 * frame;
     g.sign = A.sign;
+    g.inv_w = grid_inv(A.W);
     const HullPoly& poly = A.poly[n];     // read through L1 / L2: only the pixels next to the hull get that far
     unsigned long long tally[4] = {0, 0, 0, 0};
-    bool any_heavy = false;
-    // ---- pass 1: one pixel per thread
+    const bool plain = frame_is_plain(A.masked, n, A.H, A.W) && poly.ok;   // the pockets have been filled
+    // ---- sort out the pixels outside the hull (most of what is marked); the others go to a list of the whole batch,
+    // so that the searches run on full warps (irr_search_kernel): done here, every thread on the pixel it found, they
+    // were 3 lanes in 32 wide
+    __shared__ uint32_t s_todo[SOLVE_SPAN];
+    __shared__ unsigned s_ntodo, s_base;
+    if (threadIdx.x == 0) s_ntodo = 0;
+    __syncthreads();
     for (unsigned e = threadIdx.x; e < count; e += 256) {
         const uint32_t p = s_list[e];
         const int y = (int)(p / (uint32_t)A.W), x = (int)(p - (uint32_t)y * (uint32_t)A.W);
         P2 q;
         q.x = x;
         q.y = y;
-        uint32_t vid[3];
-        double w[3];
-        int st;
-        if (hull_rejects(s_hull, q) || (poly.ok && !inside_hull(poly, q))) {
-            st = LOC_OUTSIDE;
-            ++tally[3];
-        } else {
-            st = locate(g, q, vid, w, Coop{0, 1}, THREAD_BUDGET);
-            if (st == LOC_HEAVY) {
-                atomicOr(&s_blocks[(p >> 3) - blockIdx.x * (SOLVE_SPAN / 8)], 1u << (p & 7));
-                any_heavy = true;
-                continue;
+        // A frame without removed points has been covered completely (cells, pockets, border): what is left inside
+        // the hull are single pixels the fill rule gave to nobody, and those have produced pixels around them. A
+        // marked pixel among marked pixels is outside -- no test against the hull (hundreds of edges on a border that
+        // is straight only up to float32 rounding) for the empty corners a rotation leaves.
+        bool lonely = plain;
+        if (plain) {
+            for (int dy = -1; dy <= 1 && lonely; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int yy = y + dy, xx = x + dx;
+                    if ((dy | dx) != 0 && yy >= 0 && xx >= 0 && yy < A.H && xx < A.W &&
+                        A.cover[frame + (size_t)yy * A.W + xx] != UNCOVERED) {
+                        lonely = false;
+                        break;
+                    }
+                }
+        }
+        if (lonely || hull_rejects(s_hull, q) || (poly.ok && !inside_hull(poly, q))) ++tally[3];
+        else s_todo[atomicAdd(&s_ntodo, 1u)] = p;
+    }
+    __syncthreads();
+    const unsigned ntodo = s_ntodo;
+    if (ntodo > 0) {
+        if (threadIdx.x == 0) s_base = atomicAdd(A.todo_count, ntodo);
+        __syncthreads();
+        const unsigned base_slot = s_base;
+        for (unsigned e = threadIdx.x; e < ntodo; e += 256) {
+            const uint32_t p = s_todo[e];
+            if (base_slot + e < A.todo_cap) {
+                A.todo[base_slot + e] = ((unsigned long long)n << 32) | p;
+            } else {   // no room in the list: searched here
+                const int y = (int)(p / (uint32_t)A.W), x = (int)(p - (uint32_t)y * (uint32_t)A.W);
+                P2 q;
+                q.x = x;
+                q.y = y;
+                uint32_t vid[3];
+                double w[3];
+                const int st = locate(g, q, vid, w, Coop{0, 1}, NO_BUDGET);
+                ++tally[st == LOC_FOUND ? 0 : (st == LOC_OUTSIDE ? 1 : 2)];
+                solve_store(A, frame, p, st, vid, w);
             }
-            ++tally[st == LOC_FOUND ? 0 : (st == LOC_OUTSIDE ? 1 : 2)];
         }
-        solve_store(A, frame, p, st, vid, w);
     }
-    // ---- the abandoned searches become work items of the pocket pass
-    if (__syncthreads_or(any_heavy ? 1 : 0)) {
-        for (unsigned b = threadIdx.x; b < SOLVE_SPAN / 8; b += 256) {
-            const uint32_t bits = s_blocks[b];
-            if (bits == 0) continue;
+    for (int k = 0; k < 4; ++k) {   // one atomic per warp: thousands of threads on one counter serialise in L2
+        unsigned long long v = tally[k];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && v) atomicAdd(&g_stats[k], v);
+    }
+}
+
+__device__ __forceinline__ SiteGrid solve_grid(const SolveArgs& A, int n) {
+    const size_t frame = (size_t)n * A.H * A.W;
+    SiteGrid g;
+    g.H = A.H;
+    g.W = A.W;
+    g.nbx = A.nbx;
+    g.nby = A.nby;
+    g.ncx = A.ncx;
+    g.ncy = A.ncy;
+    const int nb = grid_slots(A.nbx, A.nby);
+    g.bin_start = A.bins + (size_t)n * (nb + 1);
+    g.occ = A.occ + (size_t)n * A.ncx * A.ncy;
+    g.sites = A.sites + frame;
+    g.flow = A.flow + 2 * frame;
+    g.sign = A.sign;
+    g.inv_w = grid_inv(A.W);
+    return g;
+}
+
+// The searches: one listed pixel per thread, warps full. A search that looks at more than THREAD_BUDGET sites is
+// abandoned and handed to irr_heavy_kernel (one warp per pixel).
+__global__ void __launch_bounds__(128) irr_search_kernel(const SolveArgs A) {
+    const unsigned count = min(*A.todo_count, A.todo_cap);
+    const unsigned lane = threadIdx.x & 31;
+    unsigned long long tally[3] = {0, 0, 0};
+    for (unsigned it0 = blockIdx.x * 128 + (threadIdx.x & ~31u); it0 < count; it0 += gridDim.x * 128) {
+        const unsigned it = it0 + lane;
+        bool heavy = false;
+        unsigned long long key = ~0ull - lane;      // unique per lane unless the pixel goes to the pocket pass
+        uint32_t p = 0;
+        if (it < count) {
+            const unsigned long long item = A.todo[it];
+            const int n = (int)(item >> 32);
+            p = (uint32_t)(item & 0xffffffffu);
+            const size_t frame = (size_t)n * A.H * A.W;
+            const SiteGrid g = solve_grid(A, n);
+            const int y = (int)(p / (uint32_t)A.W), x = (int)(p - (uint32_t)y * (uint32_t)A.W);
+            P2 q;
+            q.x = x;
+            q.y = y;
+            uint32_t vid[3];
+            double w[3];
+            const int st = locate(g, q, vid, w, Coop{0, 1}, THREAD_BUDGET);
+            if (st == LOC_HEAVY) {
+                heavy = true;
+                key = ((unsigned long long)n << 40) | ((unsigned long long)(p >> 3) << 8);
+            } else {
+                ++tally[st == LOC_FOUND ? 0 : (st == LOC_OUTSIDE ? 1 : 2)];
+                solve_store(A, frame, p, st, vid, w);
+            }
+        }
+        // neighbouring pixels of a row (they sit in neighbouring lanes: the lists keep the pixel order) form one work
+        // item of the pocket pass, which locates the second from the triangle of the first
+        const unsigned group = __match_any_sync(0xffffffffu, key);
+        const unsigned bits = __reduce_or_sync(group, heavy ? (1u << (p & 7)) : 0u);
+        if (heavy && lane == (unsigned)(__ffs(group) - 1)) {
             const unsigned slot = atomicAdd(A.heavy_count, 1u);
-            A.heavy[slot] = ((unsigned long long)n << 40) |
-                            ((unsigned long long)(blockIdx.x * (SOLVE_SPAN / 8) + b) << 8) | bits;
+            A.heavy[slot] = key | bits;
         }
     }
-    for (int k = 0; k < 4; ++k)
-        if (tally[k]) atomicAdd(&g_stats[k], tally[k]);
+    for (int k = 0; k < 3; ++k) {
+        unsigned long long v = tally[k];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && v) atomicAdd(&g_stats[k], v);
+    }
 }
 
 // The pocket pass: one warp per work item (up to 8 neighbouring pixels of a row), all 32 lanes scanning the bins of
@@ -1325,6 +1459,7 @@ __global__ void __launch_bounds__(256) irr_heavy_kernel(const SolveArgs A) {
         g.sites = A.sites + frame;
         g.flow = A.flow + 2 * frame;
         g.sign = A.sign;
+    g.inv_w = grid_inv(A.W);
         uint32_t hint[3] = {0, 0, 0};
         bool have_hint = false;
         for (int k = 0; k < 8; ++k) {
@@ -1365,7 +1500,7 @@ __global__ void __launch_bounds__(256) irr_heavy_kernel(const SolveArgs A) {
 
 // ------------------------------------------------------------------------------------------------- workspace layout
 struct WsLayout {
-    size_t sites, cover, heavy, heavy_count, hole_count, masked, bins, coarse, hullws, hullinfo, folded, chunks, opos, oids, ocount, poly, total;
+    size_t sites, cover, heavy, todo, todo_count, heavy_count, hole_count, masked, bins, coarse, hullws, hullinfo, folded, chunks, opos, oids, ocount, poly, total;
     size_t zero_begin, zero_bytes;   // region cleared before every call (bins, coarse, hull keys, folded flags)
     int nbx, nby, ncx, ncy, nb, nc;
 };
@@ -1387,6 +1522,8 @@ static WsLayout ws_layout(int N, int H, int W) {
     L.cover = o;
     o = align_up(o + px, 256);
     L.heavy = o;            // at most one item per 8 pixels
+    o = align_up(o + px + 8, 256);
+    L.todo = o;             // the same for the pixels waiting for a search
     o = align_up(o + px + 8, 256);
     L.hullinfo = o;
     o = align_up(o + (size_t)N * sizeof(HullInfo), 256);
@@ -1410,6 +1547,8 @@ static WsLayout ws_layout(int N, int H, int W) {
     L.heavy_count = o;
     o = align_up(o + 4, 256);
     L.hole_count = o;
+    o = align_up(o + 4, 256);
+    L.todo_count = o;
     o = align_up(o + 4, 256);
     L.masked = o;
     o = align_up(o + (size_t)N * 4, 256);
@@ -1631,16 +1770,26 @@ extern "C" int ofk_forward_s_ex(const float* payload, int C, const float* flow, 
         OFK_LAUNCHED();
     }
 
-    SolveArgs S{payload, flow, payload_mask, d_folded, d_bins, d_coarse, d_sites, d_info,
+    SolveArgs S{payload, flow, payload_mask, d_folded, d_masked, d_bins, d_coarse, d_sites, d_info,
                 reinterpret_cast<const fwd::HullPoly*>(base + L.poly), out, out_mask, d_cover,
                 reinterpret_cast<unsigned long long*>(base + L.heavy),
-                reinterpret_cast<unsigned int*>(base + L.heavy_count), flow_sign, C, strict, H, W, L.nbx, L.nby, L.ncx,
-                L.ncy};
+                reinterpret_cast<unsigned int*>(base + L.heavy_count),
+                reinterpret_cast<unsigned long long*>(base + L.todo), reinterpret_cast<unsigned int*>(base + L.todo_count),
+                hole_cap, flow_sign, C, strict, H, W, L.nbx, L.nby, L.ncx, L.ncy};
     dim3 vgrid((unsigned)(((size_t)H * W + SOLVE_SPAN - 1) / SOLVE_SPAN), N);
     irr_solve_kernel<<<vgrid, 256, 0, st>>>(S);
     OFK_LAUNCHED();
+    irr_search_kernel<<<sm_count() * 8, 128, 0, st>>>(S);
+    OFK_LAUNCHED();
     irr_heavy_kernel<<<sm_count() * 4, 256, 0, st>>>(S);
     OFK_LAUNCHED();
+    {
+        const size_t frame_px = (size_t)H * W;
+        const int fin_ctas = (int)std::max<size_t>(1, std::min<size_t>((frame_px + 4095) / 4096,
+                                                                       (size_t)std::max(8, 4736 / N)));
+        fwd_finalize_kernel<<<dim3(fin_ctas, N), 256, 0, st>>>(out, C, out_mask, d_cover, frame_px, d_folded);
+        OFK_LAUNCHED();
+    }
 
     if (flow_nonzero != nullptr) {
         fwd_passthrough_kernel<<<dim3(std::max(8, std::min(1184, 4736 / N)), N), 256, 0, st>>>(

@@ -92,6 +92,7 @@ extern "C" int fwd_hostsim(const float* payload, int C, const float* flow, float
     g.ncy = grid_coarse(g.nby);
     g.flow = flow;
     g.sign = sign;
+    g.inv_w = grid_inv(W);
     const int nb = grid_slots(g.nbx, g.nby);
     std::vector<uint32_t> start(nb + 1, 0), sites;
     std::vector<unsigned long long> occ((size_t)g.ncx * g.ncy, 0);
