@@ -1766,7 +1766,8 @@ extern "C" int ofk_forward_s_ex(const float* payload, int C, const float* flow, 
         const int P = 2 * W + 2 * H - 4;
         irr_border_edges_kernel<<<dim3(std::min((P + 255) / 256, 8), N), 256, 0, st>>>(Pk);
         OFK_LAUNCHED();
-        irr_pockets_kernel<<<dim3(std::max(1, std::min(32, (sm_count() * 6 + N - 1) / N)), N), 256, 0, st>>>(Pk);
+        // a CTA per hull edge while the batch is small (the pockets of a single frame in parallel)
+        irr_pockets_kernel<<<dim3(std::max(1, std::min(fwd::HULL_MAX, (sm_count() * 6 + N - 1) / N)), N), 256, 0, st>>>(Pk);
         OFK_LAUNCHED();
     }
 

@@ -50,10 +50,10 @@ def vec_agree(a, b, tol=1e-3):
     d = np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64))
     if d.max() <= tol:
         return "max |diff| %.1e" % float(d.max())
-    # forward path: cells with exactly co-circular corners (similarity transforms) have no unique Delaunay diagonal and
-    # concave pockets of the hull are not filled; only a payload that is not locally linear shows it
+    # forward path: cells with exactly co-circular corners (similarity transforms) have no unique Delaunay diagonal
+    # (DESIGN.md 2 / 4.3); only a payload that is not locally linear shows it
     bad = d.reshape(d.shape[0], d.shape[1], -1).max(-1) > tol if d.ndim >= 2 else d > tol
-    return "%.2f %% of pixels beyond %g (documented: co-circular cells / hull pockets)" % (100 * bad.mean(), tol)
+    return "%.2f %% of pixels beyond %g (documented: co-circular cells of a similarity transform, either diagonal is a Delaunay triangulation)" % (100 * bad.mean(), tol)
 
 
 print("%-66s %12s %14s %10s   %s" % ("operation (numpy in / numpy out)", "B200", "CPU oracle", "ratio", "agreement"))
