@@ -246,6 +246,11 @@ int ofk_forward_s_ex(const float* payload, int C, const float* flow, float flow_
                      const uint8_t* point_mask, const int* flow_nonzero, float* out, uint8_t* out_mask, int mask_rule,
                      int N, int H, int W, void* ws, size_t ws_bytes, ofk_stream_t stream);
 
+/* Test hook: switches passes of ofk_forward_s off for subsequent calls of this process (0 = production): 4 the pocket
+ * pass, 8 the small-face pass, 16 the tracing of a mask's outer boundary. What they would have produced is then located
+ * per pixel -- the same triangulation by another route (tests assert equal results). */
+int ofk_forward_s_set_disable(int passes);
+
 /* Test hook: cells of the displaced grid whose in-circle determinant is within +-tol take the OTHER diagonal in
  * subsequent ofk_forward_s calls of this process (0 = production behaviour). Similarity transforms leave the four
  * corners of a cell co-circular to within rounding; Qhull's diagonal there is arbitrary, and the parity tests compare

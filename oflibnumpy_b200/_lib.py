@@ -50,6 +50,7 @@ _SIGNATURES = {
     'ofk_forward_s': (_i, [_vp, _i, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     'ofk_cast': (_i, [_vp, _i, _vp, _i, _sz, _vp]),
     'ofk_forward_s_set_flip_tol': (_i, [C.c_double]),
+    'ofk_forward_s_set_disable': (_i, [C.c_int]),
     'ofk_forward_s_ex': (_i, [_vp, _i, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     'ofk_combine12_workspace': (_sz, [_i, _i, _i, _i, _i]),
     'ofk_combine12': (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),

@@ -773,9 +773,20 @@ constexpr int POCKET_STACK = 40;
 struct NoShare {
     OFK_HD bool operator()(int, int) const { return false; }
 };
-struct PerimArc {   // position t along the arc that starts at border index k0 -> site
-    int H, W, P, k0;
-    OFK_HD uint32_t operator()(int t) const { return perim_site(H, W, (k0 + t) % P); }
+// The boundary of the mesh towards the outside as a cyclic chain of sites, the mesh on the left of chain[t] ->
+// chain[t + 1]: the frame border in the order above when no point is removed (v == nullptr), else the traced loop
+// (trace_outer_loop below).
+struct Chain {
+    const uint32_t* v;
+    int n, H, W;
+};
+OFK_HD Chain perimeter_chain(int H, int W) { return Chain{nullptr, perim_count(H, W), H, W}; }
+OFK_HD uint32_t chain_site(const Chain& c, int t) { return c.v != nullptr ? c.v[t] : perim_site(c.H, c.W, t); }
+
+struct ChainArc {   // position t along the arc that starts at chain index k0 -> site
+    Chain c;
+    int k0;
+    OFK_HD uint32_t operator()(int t) const { return chain_site(c, (k0 + t) % c.n); }
 };
 template <class ArcFn, class TriFn, class ShareFn>
 OFK_HD bool pocket_triangulate(const SiteGrid& g, const ArcFn& arc, int i0, int j0, const Coop& coop, TriFn& tri,
@@ -1029,11 +1040,10 @@ OFK_HD void raster_segment(const P2& pa, const P2& pb, int W, int H, const Coop&
 // produced: seg(ia, ib, pa, pb, coop) gets the end points ordered by index. They come before the triangles of the
 // pockets (which leave produced pixels alone), the hull edge of a pocket -- pocket_chord -- after them.
 template <class SegFn>
-OFK_HD void pocket_border_edges(const SiteGrid& g, int t0, int t1, int stride, SegFn& seg) {
-    const int P = perim_count(g.H, g.W);
+OFK_HD void pocket_border_edges(const SiteGrid& g, const Chain& ch, int t0, int t1, int stride, SegFn& seg) {
     const Coop solo{0, 1};
     for (int t = t0; t < t1; t += stride) {
-        const uint32_t ia = perim_site(g.H, g.W, t), ib = perim_site(g.H, g.W, t + 1 == P ? 0 : t + 1);
+        const uint32_t ia = chain_site(ch, t), ib = chain_site(ch, t + 1 == ch.n ? 0 : t + 1);
         const P2 pa = site_pos(g, ia), pb = site_pos(g, ib);
         if (ia < ib) seg(ia, ib, pa, pb, solo);
         else seg(ib, ia, pb, pa, solo);
@@ -1041,13 +1051,72 @@ OFK_HD void pocket_border_edges(const SiteGrid& g, int t0, int t1, int stride, S
 }
 
 template <class SegFn>
-OFK_HD void pocket_chord(const SiteGrid& g, int k0, int k1, const Coop& coop, SegFn& seg) {
-    const int P = perim_count(g.H, g.W);
-    if (((k1 - k0) % P + P) % P < 2) return;
-    const uint32_t ia = perim_site(g.H, g.W, k0), ib = perim_site(g.H, g.W, k1);
+OFK_HD void pocket_chord(const SiteGrid& g, const Chain& ch, int k0, int k1, const Coop& coop, SegFn& seg) {
+    if (((k1 - k0) % ch.n + ch.n) % ch.n < 2) return;
+    const uint32_t ia = chain_site(ch, k0), ib = chain_site(ch, k1);
     const P2 pa = site_pos(g, ia), pb = site_pos(g, ib);
     if (ia < ib) seg(ia, ib, pa, pb, coop);
     else seg(ib, ia, pb, pa, coop);
+}
+
+// ---------------------------------------------------------------------------------------- outer boundary of a mask
+// With removed points the mesh ends where the point mask does. A forward pass leaves exactly such masks behind (valid
+// inside the hull of the resampled points: a rotated frame with staircase edges), and the next pass of a chain
+// (switch_ref, modes 1 / 2) takes them as its point mask: between the staircase and its hull lie hundreds of small
+// pockets per frame. The boundary is walked like the boundary of a hole (hole_loop), from the first valid site in
+// raster order, whose upper side faces the outside; the result is stored reversed, mesh on the left, like the
+// frame border. Gives up (returns -1: per-pixel search) when the chain does not fit, the start is a site without a
+// cell, or the mesh is pinched at a visited vertex (two separate open sectors: the chain would not be a simple
+// polygon). Sites without any cell inside the outside face make the pockets more than polygons: the caller checks
+// for them separately (any_isolated_site).
+OFK_HD int trace_outer_loop(const uint8_t* pm, int H, int W, uint32_t first_valid, uint32_t* out, int cap) {
+    if (pm == nullptr || H < 2 || W < 2 || first_valid >= (uint32_t)H * (uint32_t)W) return -1;
+    const int r0 = (int)(first_valid / (uint32_t)W), c0 = (int)(first_valid % (uint32_t)W);
+    const int dr[4] = {0, 1, 0, -1}, dc[4] = {1, 0, -1, 0};
+    auto quad_intact = [&](int r, int c, int q) {
+        int ci, cj;
+        quadrant_cell(r, c, q & 3, ci, cj);
+        return cell_intact(pm, H, W, ci, cj);
+    };
+    // the open sector that holds the quadrants above the start site begins after an intact quadrant
+    int k0 = 2, turns = 0;
+    while (!quad_intact(r0, c0, k0 + 3)) {
+        --k0;
+        if (++turns > 3) return -1;   // no cell touches the first site
+    }
+    k0 &= 3;
+    int ar = r0, ac = c0, k = k0, n = 0;
+    for (;;) {
+        if (n >= cap) return -1;
+        const bool q0 = quad_intact(ar, ac, 0), q1 = quad_intact(ar, ac, 1), q2 = quad_intact(ar, ac, 2),
+                   q3 = quad_intact(ar, ac, 3);
+        if ((q0 && q2 && !q1 && !q3) || (q1 && q3 && !q0 && !q2)) return -1;   // pinched
+        out[n++] = (uint32_t)(ar * W + ac);
+        const int br = ar + dr[k], bc = ac + dc[k];
+        int j = k + 1;
+        turns = 0;
+        while (!quad_intact(br, bc, j + 3)) {
+            --j;
+            if (++turns > 3) return -1;
+        }
+        ar = br;
+        ac = bc;
+        k = j & 3;
+        if (ar == r0 && ac == c0 && k == k0) break;
+    }
+    if (n < 3) return -1;
+    for (int i = 0, j = n - 1; i < j; ++i, --j) {   // the walk has the outside on its left: reversed
+        const uint32_t t = out[i];
+        out[i] = out[j];
+        out[j] = t;
+    }
+    return n;
+}
+
+// a valid site that no intact cell touches (all four quadrants open)
+OFK_HD bool site_is_isolated(const uint8_t* pm, int H, int W, int r, int c) {
+    return !cell_intact(pm, H, W, r, c) && !cell_intact(pm, H, W, r, c - 1) && !cell_intact(pm, H, W, r - 1, c - 1) &&
+           !cell_intact(pm, H, W, r - 1, c);
 }
 
 // a valid site is a boundary site when it sits on the frame border or one of its 8 neighbours has been removed

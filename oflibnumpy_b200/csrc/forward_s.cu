@@ -531,6 +531,7 @@ struct IrrArgs {
     int perimeter_only;  // no point mask at all: every frame's boundary sites are the frame border
     const int* masked;   // [N] set when the frame's point mask removes a point; a frame without removed points is
                          // handled like one without a point mask (Flow.apply passes the flow's mask, mostly all true)
+    int* isolated;       // [N] set when a valid point of a masked frame has no intact cell around it
     unsigned long long* holes;   // removed points (frame << 32 | index), the candidates for hole_fill()
     unsigned int* hole_count;
     unsigned int hole_cap;
@@ -563,12 +564,14 @@ __device__ __forceinline__ bool irr_site_of_thread(const IrrArgs& A, int n, long
     return is_boundary_site(A.point_mask ? A.point_mask + (size_t)n * A.H * A.W : nullptr, A.H, A.W, row, col);
 }
 
-// does the point mask of a frame remove anything?
+// does the point mask of a frame remove anything, and which is its first valid point (raster order)?
 __global__ void __launch_bounds__(256) fwd_scan_mask_kernel(const uint8_t* __restrict__ point_mask, size_t frame_px,
-                                                            int* __restrict__ masked) {
+                                                            int* __restrict__ masked,
+                                                            unsigned int* __restrict__ first_valid) {
     const int n = blockIdx.y;
     const uint8_t* m = point_mask + (size_t)n * frame_px;
     bool zero = false;
+    unsigned int first = 0xffffffffu;
     const size_t words = ((reinterpret_cast<uintptr_t>(m) & 15) == 0) ? frame_px / 16 : 0;
     const uint4* m4 = reinterpret_cast<const uint4*>(m);
     for (size_t k = (size_t)blockIdx.x * 256 + threadIdx.x; k < words; k += (size_t)gridDim.x * 256) {
@@ -577,9 +580,18 @@ __global__ void __launch_bounds__(256) fwd_scan_mask_kernel(const uint8_t* __res
         const uint32_t z = ((v.x - 0x01010101u) & ~v.x) | ((v.y - 0x01010101u) & ~v.y) | ((v.z - 0x01010101u) & ~v.z) |
                            ((v.w - 0x01010101u) & ~v.w);
         zero = zero || (z & 0x80808080u) != 0u;
+        if (first == 0xffffffffu && (v.x | v.y | v.z | v.w) != 0u) {
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+            for (int q = 0; q < 4 && first == 0xffffffffu; ++q)
+                if (w4[q]) first = (unsigned int)(k * 16 + q * 4 + ((__ffs(w4[q]) - 1) >> 3));
+        }
     }
-    for (size_t k = words * 16 + (size_t)blockIdx.x * 256 + threadIdx.x; k < frame_px; k += (size_t)gridDim.x * 256)
+    for (size_t k = words * 16 + (size_t)blockIdx.x * 256 + threadIdx.x; k < frame_px; k += (size_t)gridDim.x * 256) {
         zero = zero || m[k] == 0;
+        if (m[k] != 0 && (unsigned int)k < first) first = (unsigned int)k;
+    }
+    for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+    if ((threadIdx.x & 31) == 0 && first != 0xffffffffu) atomicMin(first_valid + n, first);
     if (__syncthreads_or(zero ? 1 : 0) && threadIdx.x == 0) masked[n] = 1;
 }
 
@@ -604,6 +616,9 @@ __global__ void __launch_bounds__(256) irr_sites_kernel(const IrrArgs A) {
         }
     }
     if (!site) return;
+    if (PASS == 0 && A.point_mask != nullptr && !A.perimeter_only && !frame_is_plain(A.masked, n, A.H, A.W) &&
+        site_is_isolated(A.point_mask + frame, A.H, A.W, row, col))
+        A.isolated[n] = 1;
     const uint32_t id = (uint32_t)(row * A.W + col);
     const float2 f = __ldg(reinterpret_cast<const float2*>(A.flow) + frame + id);
     const P2 p = displaced(f.x, f.y, row, col, A.sign);
@@ -937,6 +952,10 @@ struct PocketArgs {
     const uint8_t* payload_mask;
     const int* folded;
     const int* masked;       // [N] or nullptr, see IrrArgs
+    const uint32_t* chain;   // [N][chain_cap] traced outer boundary of masked frames (irr_trace_kernel)
+    const int* chain_n;      // [N] its length, <= 0: none
+    const int* hull_pos;     // [N][HULL_MAX] chain index of every hull vertex
+    int chain_cap;
     const HullPoly* poly;
     float* out;
     uint8_t* out_mask;
@@ -1028,16 +1047,125 @@ __global__ void __launch_bounds__(128) irr_holes_kernel(const PocketArgs A, cons
     if ((threadIdx.x & 31) == 0 && pixels) atomicAdd(&g_stats[0], pixels);
 }
 
+// ------------------------------------------------------------------------------------------------- outer boundary
+// trace_outer_loop() of forward_irregular.cuh, one warp per masked frame: the walk is serial, but the nine mask bytes
+// around the current vertex are fetched by nine lanes at once (one memory round trip per step). Then the chain index
+// of every hull vertex, in one more walk (the hull visits the chain in its own order).
+struct TraceArgs {
+    const uint8_t* point_mask;
+    const int* folded;
+    const int* masked;
+    const int* isolated;
+    const unsigned int* first_valid;
+    const HullPoly* poly;
+    uint32_t* chain;
+    int* chain_n;
+    int* hull_pos;
+    int chain_cap, H, W;
+};
+
+__device__ __forceinline__ unsigned neighbourhood(const uint8_t* pm, int H, int W, int r, int c, int lane) {
+    bool v = false;
+    if (lane < 9) {
+        const int rr = r + lane / 3 - 1, cc = c + lane % 3 - 1;
+        v = rr >= 0 && cc >= 0 && rr < H && cc < W && pm[(size_t)rr * W + cc] != 0;
+    }
+    return __ballot_sync(0xffffffffu, v) & 0x1ffu;   // bit 3 * (dr + 1) + (dc + 1)
+}
+// quadrant q (SE, SW, NW, NE) of the centre intact?
+__device__ __forceinline__ bool nb_quadrant(unsigned nb, int q) {
+    const unsigned masks[4] = {0x1b0u /* 4 5 7 8 */, 0x0d8u /* 3 4 6 7 */, 0x01bu /* 0 1 3 4 */, 0x036u /* 1 2 4 5 */};
+    const unsigned m = masks[q & 3];
+    return (nb & m) == m;
+}
+
+__global__ void __launch_bounds__(32) irr_trace_kernel(const TraceArgs A) {
+    const int n = blockIdx.x, lane = threadIdx.x;
+    if (lane == 0) A.chain_n[n] = 0;
+    if (A.folded[n] || A.point_mask == nullptr || frame_is_plain(A.masked, n, A.H, A.W) || A.isolated[n]) return;
+    const HullPoly& hp = A.poly[n];
+    if (!hp.ok || A.H < 3 || A.W < 3) return;
+    const unsigned int first = A.first_valid[n];
+    if (first >= (unsigned int)A.H * (unsigned int)A.W) return;
+    const uint8_t* pm = A.point_mask + (size_t)n * A.H * A.W;
+    uint32_t* out = A.chain + (size_t)n * A.chain_cap;
+    const int H = A.H, W = A.W;
+    const int r0 = (int)(first / (unsigned)W), c0 = (int)(first % (unsigned)W);
+    const int dr[4] = {0, 1, 0, -1}, dc[4] = {1, 0, -1, 0};
+    unsigned nb = neighbourhood(pm, H, W, r0, c0, lane);
+    int k0 = 2, turns = 0;
+    while (!nb_quadrant(nb, k0 + 3)) {
+        --k0;
+        if (++turns > 3) return;
+    }
+    k0 &= 3;
+    int ar = r0, ac = c0, k = k0, cnt = 0;
+    for (;;) {
+        if (cnt >= A.chain_cap) return;
+        const bool q0 = nb_quadrant(nb, 0), q1 = nb_quadrant(nb, 1), q2 = nb_quadrant(nb, 2), q3 = nb_quadrant(nb, 3);
+        if ((q0 && q2 && !q1 && !q3) || (q1 && q3 && !q0 && !q2)) return;   // pinched
+        if (lane == 0) out[cnt] = (uint32_t)(ar * W + ac);
+        ++cnt;
+        const int br = ar + dr[k], bc = ac + dc[k];
+        nb = neighbourhood(pm, H, W, br, bc, lane);
+        int j = k + 1;
+        turns = 0;
+        while (!nb_quadrant(nb, j + 3)) {
+            --j;
+            if (++turns > 3) return;
+        }
+        ar = br;
+        ac = bc;
+        k = j & 3;
+        if (ar == r0 && ac == c0 && k == k0) break;
+    }
+    if (cnt < 3) return;
+    __syncwarp();
+    for (int i = lane; i < cnt / 2; i += 32) {   // the walk has the outside on its left: reversed
+        const uint32_t t = out[i];
+        out[i] = out[cnt - 1 - i];
+        out[cnt - 1 - i] = t;
+    }
+    __syncwarp();
+    // hull vertex e sits at chain index hull_pos[e]: the hull runs through the chain in chain order
+    int* pos = A.hull_pos + (size_t)n * HULL_MAX;
+    bool ok = true;
+    if (lane == 0) {
+        int t = 0, scanned = 0;
+        for (int e = 0; e < hp.m && ok; ++e) {
+            const uint32_t id = hp.id[e];
+            while (out[t] != id) {
+                t = t + 1 == cnt ? 0 : t + 1;
+                if (++scanned > 2 * cnt) {
+                    ok = false;
+                    break;
+                }
+            }
+            pos[e] = t;
+        }
+        A.chain_n[n] = ok ? cnt : 0;
+    }
+}
+
+// the boundary chain of frame n for the pocket pass: the frame border, the traced boundary, or none (c.n == 0)
+__device__ __forceinline__ Chain frame_chain(const PocketArgs& A, int n) {
+    if (frame_is_plain(A.masked, n, A.H, A.W)) return perimeter_chain(A.H, A.W);
+    const int cn = A.chain_n != nullptr ? A.chain_n[n] : 0;
+    return Chain{A.chain + (size_t)n * A.chain_cap, cn > 0 ? cn : 0, A.H, A.W};
+}
+
 // Frames without removed points, first the pixels exactly on the displaced frame border that no cell produced (a
 // straight border: every pixel of a column after an integer shift) ...
 __global__ void __launch_bounds__(256) irr_border_edges_kernel(const PocketArgs A) {
     const int n = blockIdx.y;
-    if (A.folded[n] || !frame_is_plain(A.masked, n, A.H, A.W)) return;
+    if (A.folded[n]) return;
+    const Chain ch = frame_chain(A, n);
+    if (ch.n == 0) return;
     const size_t frame = (size_t)n * A.H * A.W;
     const SiteGrid g = pocket_grid(A, frame);
     unsigned long long pixels = 0;
     PocketSeg seg{A, frame, pixels};
-    pocket_border_edges(g, blockIdx.x * 256 + threadIdx.x, perim_count(A.H, A.W), gridDim.x * 256, seg);
+    pocket_border_edges(g, ch, blockIdx.x * 256 + threadIdx.x, ch.n, gridDim.x * 256, seg);
     for (int o = 16; o > 0; o >>= 1) pixels += __shfl_xor_sync(0xffffffffu, pixels, o);
     if ((threadIdx.x & 31) == 0 && pixels) atomicAdd(&g_stats[0], pixels);
 }
@@ -1083,9 +1211,13 @@ struct PocketShare {
 
 __global__ void __launch_bounds__(256) irr_pockets_kernel(const PocketArgs A) {
     const int n = blockIdx.y;
-    if (A.folded[n] || !frame_is_plain(A.masked, n, A.H, A.W)) return;
+    if (A.folded[n]) return;
     const HullPoly& hp = A.poly[n];
     if (!hp.ok) return;
+    const Chain ch = frame_chain(A, n);
+    if (ch.n == 0) return;
+    const bool traced = ch.v != nullptr;
+    const int* hpos = A.hull_pos + (size_t)n * HULL_MAX;
     __shared__ PocketPool pool;
     const int lane = threadIdx.x & 31;
     const Coop coop{lane, 32};
@@ -1095,9 +1227,11 @@ __global__ void __launch_bounds__(256) irr_pockets_kernel(const PocketArgs A) {
     PocketTri tri{A, frame, coop, pixels};
     PocketSeg seg{A, frame, pixels};
     PocketShare share{pool, lane};
-    const int m = hp.m, P = perim_count(A.H, A.W);
+    const int m = hp.m, P = ch.n;
     for (int e = blockIdx.x; e < m; e += gridDim.x) {
-        const int k0 = perim_index(A.H, A.W, hp.id[e]), k1 = perim_index(A.H, A.W, hp.id[e + 1 == m ? 0 : e + 1]);
+        const int e1 = e + 1 == m ? 0 : e + 1;
+        const int k0 = traced ? hpos[e] : perim_index(A.H, A.W, hp.id[e]);
+        const int k1 = traced ? hpos[e1] : perim_index(A.H, A.W, hp.id[e1]);
         if (k0 < 0 || k1 < 0) continue;
         const int len = ((k1 - k0) % P + P) % P;
         if (len < 2) continue;
@@ -1133,7 +1267,7 @@ __global__ void __launch_bounds__(256) irr_pockets_kernel(const PocketArgs A) {
             }
             i = __shfl_sync(0xffffffffu, i, 0);
             j = __shfl_sync(0xffffffffu, j, 0);
-            pocket_triangulate(g, PerimArc{A.H, A.W, P, k0}, i, j, coop, tri, share);
+            pocket_triangulate(g, ChainArc{ch, k0}, i, j, coop, tri, share);
             __syncwarp();
             if (lane == 0) {
                 pool_lock(pool);
@@ -1142,7 +1276,7 @@ __global__ void __launch_bounds__(256) irr_pockets_kernel(const PocketArgs A) {
             }
         }
         __syncthreads();   // the pixels exactly on the hull edge come after the triangles of its pocket
-        if (threadIdx.x < 32) pocket_chord(g, k0, k1, coop, seg);
+        if (threadIdx.x < 32) pocket_chord(g, ch, k0, k1, coop, seg);
     }
     for (int o = 16; o > 0; o >>= 1) pixels += __shfl_xor_sync(0xffffffffu, pixels, o);
     if (lane == 0 && pixels) atomicAdd(&g_stats[0], pixels);
@@ -1168,6 +1302,7 @@ struct SolveArgs {
     unsigned long long* todo;        // pixels that need a search: frame << 32 | pixel
     unsigned int* todo_count;
     unsigned int todo_cap;
+    int lonely_ok;                   // the pocket pass ran: a marked pixel among marked pixels is outside
     float sign;
     int C, rule_strict, H, W, nbx, nby, ncx, ncy;
 };
@@ -1301,7 +1436,7 @@ __global__ void __launch_bounds__(256) irr_solve_kernel(const SolveArgs A) {
     g.inv_w = grid_inv(A.W);
     const HullPoly& poly = A.poly[n];     // read through L1 / L2: only the pixels next to the hull get that far
     unsigned long long tally[4] = {0, 0, 0, 0};
-    const bool plain = frame_is_plain(A.masked, n, A.H, A.W) && poly.ok;   // the pockets have been filled
+    const bool plain = frame_is_plain(A.masked, n, A.H, A.W) && poly.ok && A.lonely_ok;   // the pockets have been filled
     // ---- sort out the pixels outside the hull (most of what is marked); the others go to a list of the whole batch,
     // so that the searches run on full warps (irr_search_kernel): done here, every thread on the pixel it found, they
     // were 3 lanes in 32 wide
@@ -1500,9 +1635,9 @@ __global__ void __launch_bounds__(256) irr_heavy_kernel(const SolveArgs A) {
 
 // ------------------------------------------------------------------------------------------------- workspace layout
 struct WsLayout {
-    size_t sites, cover, heavy, todo, todo_count, heavy_count, hole_count, masked, bins, coarse, hullws, hullinfo, folded, chunks, opos, oids, ocount, poly, total;
+    size_t sites, cover, heavy, todo, chain, hull_pos, chain_n, first_valid, isolated, todo_count, heavy_count, hole_count, masked, bins, coarse, hullws, hullinfo, folded, chunks, opos, oids, ocount, poly, total;
     size_t zero_begin, zero_bytes;   // region cleared before every call (bins, coarse, hull keys, folded flags)
-    int nbx, nby, ncx, ncy, nb, nc;
+    int nbx, nby, ncx, ncy, nb, nc, chain_cap;
 };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -1525,6 +1660,15 @@ static WsLayout ws_layout(int N, int H, int W) {
     o = align_up(o + px + 8, 256);
     L.todo = o;             // the same for the pixels waiting for a search
     o = align_up(o + px + 8, 256);
+    L.chain_cap = 4 * (H + W);   // traced outer boundary of a masked frame
+    L.chain = o;
+    o = align_up(o + (size_t)N * L.chain_cap * 4, 256);
+    L.hull_pos = o;
+    o = align_up(o + (size_t)N * HULL_MAX * 4, 256);
+    L.chain_n = o;
+    o = align_up(o + (size_t)N * 4, 256);
+    L.first_valid = o;      // set to ~0 before every call
+    o = align_up(o + (size_t)N * 4, 256);
     L.hullinfo = o;
     o = align_up(o + (size_t)N * sizeof(HullInfo), 256);
     L.opos = o;
@@ -1551,6 +1695,8 @@ static WsLayout ws_layout(int N, int H, int W) {
     L.todo_count = o;
     o = align_up(o + 4, 256);
     L.masked = o;
+    o = align_up(o + (size_t)N * 4, 256);
+    L.isolated = o;
     o = align_up(o + (size_t)N * 4, 256);
     L.ocount = o;
     o = align_up(o + (size_t)N * 4, 256);
@@ -1601,6 +1747,7 @@ unsigned long long stat(int which) {
 
 unsigned long long forward_s_stat(int which) { return fwdk::stat(which); }
 static std::atomic<double> g_flip_tol{0.0};
+static std::atomic<int> g_disable{0};   // test hook, see ofk_forward_s_set_disable
 
 }  // namespace ofk
 
@@ -1609,6 +1756,12 @@ using namespace ofk;
 extern "C" int ofk_forward_s_set_flip_tol(double tol) {
     OFK_CHECK_ARG(tol >= 0.0, "ofk_forward_s_set_flip_tol: negative tolerance");
     g_flip_tol.store(tol);
+    return OFK_OK;
+}
+
+extern "C" int ofk_forward_s_set_disable(int passes) {
+    OFK_CHECK_ARG(passes >= 0, "ofk_forward_s_set_disable: negative mask");
+    g_disable.store(passes);
     return OFK_OK;
 }
 
@@ -1697,13 +1850,16 @@ extern "C" int ofk_forward_s_ex(const float* payload, int C, const float* flow, 
     // the list of removed points shares its buffer with the work items of the pocket pass (used one after the other)
     const unsigned int hole_cap = (unsigned int)std::min<size_t>(((size_t)N * H * W + 8) / 8, 0xffffffffu);
     int* d_masked = point_mask != nullptr ? reinterpret_cast<int*>(base + L.masked) : nullptr;
+    unsigned int* d_first = reinterpret_cast<unsigned int*>(base + L.first_valid);
+    int* d_isolated = reinterpret_cast<int*>(base + L.isolated);
     if (point_mask != nullptr) {
+        OFK_CUDA(cudaMemsetAsync(d_first, 0xFF, sizeof(unsigned int) * (size_t)N, st));
         fwd_scan_mask_kernel<<<dim3(std::max(1, std::min(64, (sm_count() * 8 + N - 1) / N)), N), 256, 0, st>>>(
-            point_mask, (size_t)H * W, d_masked);
+            point_mask, (size_t)H * W, d_masked, d_first);
         OFK_LAUNCHED();
     }
     IrrArgs I{flow, point_mask, d_folded, d_bins, d_coarse, d_sites, flow_sign, H, W, L.nbx, L.nby, L.ncx, L.ncy,
-              (point_mask == nullptr && H >= 3 && W >= 3) ? 1 : 0, d_masked,
+              (point_mask == nullptr && H >= 3 && W >= 3) ? 1 : 0, d_masked, d_isolated,
               reinterpret_cast<unsigned long long*>(base + L.heavy),
               reinterpret_cast<unsigned int*>(base + L.hole_count), hole_cap};
     const long long cand = I.perimeter_only ? 2ll * W + 2ll * (H - 2) : (long long)H * W;
@@ -1756,15 +1912,27 @@ extern "C" int ofk_forward_s_ex(const float* payload, int C, const float* flow, 
     hull_wrap_kernel<<<N, 256, 0, st>>>(O);
     OFK_LAUNCHED();
 
-    PocketArgs Pk{payload, flow, payload_mask, d_folded, d_masked, reinterpret_cast<const fwd::HullPoly*>(base + L.poly),
-                  out, out_mask, d_cover, flow_sign, C, strict, H, W};
-    if (point_mask != nullptr && H >= 3 && W >= 3) {
+    uint32_t* d_chain = reinterpret_cast<uint32_t*>(base + L.chain);
+    int* d_chain_n = reinterpret_cast<int*>(base + L.chain_n);
+    int* d_hull_pos = reinterpret_cast<int*>(base + L.hull_pos);
+    const int disable = g_disable.load();
+    if (point_mask != nullptr && !(disable & 16)) {   // masked frames: the outer boundary of the mask as the chain
+        TraceArgs T{point_mask, d_folded, d_masked, d_isolated, d_first,
+                    reinterpret_cast<const fwd::HullPoly*>(base + L.poly), d_chain, d_chain_n, d_hull_pos, L.chain_cap,
+                    H, W};
+        irr_trace_kernel<<<N, 32, 0, st>>>(T);
+        OFK_LAUNCHED();
+    }
+    PocketArgs Pk{payload, flow, payload_mask, d_folded, d_masked, d_chain,
+                  (point_mask != nullptr && !(disable & 16)) ? d_chain_n : nullptr,
+                  d_hull_pos, L.chain_cap, reinterpret_cast<const fwd::HullPoly*>(base + L.poly), out, out_mask, d_cover,
+                  flow_sign, C, strict, H, W};
+    if (point_mask != nullptr && H >= 3 && W >= 3 && !(disable & 8)) {
         irr_holes_kernel<<<sm_count() * 8, 128, 0, st>>>(Pk, point_mask, I.holes, I.hole_count, hole_cap);
         OFK_LAUNCHED();
     }
-    if (H >= 3 && W >= 3) {   // frames without removed points (per-frame test inside)
-        const int P = 2 * W + 2 * H - 4;
-        irr_border_edges_kernel<<<dim3(std::min((P + 255) / 256, 8), N), 256, 0, st>>>(Pk);
+    if (H >= 3 && W >= 3 && !(disable & 4)) {   // frames with a boundary chain (per-frame test inside)
+        irr_border_edges_kernel<<<dim3(std::min((L.chain_cap + 255) / 256, 8), N), 256, 0, st>>>(Pk);
         OFK_LAUNCHED();
         // a CTA per hull edge while the batch is small (the pockets of a single frame in parallel)
         irr_pockets_kernel<<<dim3(std::max(1, std::min(fwd::HULL_MAX, (sm_count() * 6 + N - 1) / N)), N), 256, 0, st>>>(Pk);
@@ -1776,7 +1944,7 @@ extern "C" int ofk_forward_s_ex(const float* payload, int C, const float* flow, 
                 reinterpret_cast<unsigned long long*>(base + L.heavy),
                 reinterpret_cast<unsigned int*>(base + L.heavy_count),
                 reinterpret_cast<unsigned long long*>(base + L.todo), reinterpret_cast<unsigned int*>(base + L.todo_count),
-                hole_cap, flow_sign, C, strict, H, W, L.nbx, L.nby, L.ncx, L.ncy};
+                hole_cap, (disable & 4) ? 0 : 1, flow_sign, C, strict, H, W, L.nbx, L.nby, L.ncx, L.ncy};
     dim3 vgrid((unsigned)(((size_t)H * W + SOLVE_SPAN - 1) / SOLVE_SPAN), N);
     irr_solve_kernel<<<vgrid, 256, 0, st>>>(S);
     OFK_LAUNCHED();

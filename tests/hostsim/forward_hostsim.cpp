@@ -58,7 +58,7 @@ extern "C" int fwd_hostsim(const float* payload, int C, const float* flow, float
     use_prefilter &= 1;
     std::vector<uint8_t> cover((size_t)H * W, 0);
     Frame f{payload, C, flow, sign, payload_mask, point_mask, out, out_mask, rule_strict, H, W, cover.data()};
-    memset(stats, 0, 8 * sizeof(long long));
+    memset(stats, 0, 12 * sizeof(long long));
     // ---- regular part: intact cells
     for (int i = 0; i + 1 < H; ++i) {
         for (int j = 0; j + 1 < W; ++j) {
@@ -144,8 +144,49 @@ extern "C" int fwd_hostsim(const float* payload, int C, const float* flow, float
         hull.m = 0;
         poly.ok = 0;
     }
-    // ---- hull pockets of a frame without removed points: triangulated arc by arc, rasterised directly
-    if (point_mask == nullptr && H >= 3 && W >= 3 && poly.ok && (flags & 4) == 0) {
+    // ---- hull pockets: between the boundary chain of the mesh (the frame border, or the traced outer boundary of the
+    // point mask) and its hull, triangulated arc by arc, rasterised directly
+    std::vector<uint32_t> chain_store;
+    std::vector<int> hull_pos;
+    Chain ch{nullptr, 0, H, W};
+    bool have_chain = false;
+    if (poly.ok && H >= 3 && W >= 3 && (flags & 4) == 0) {
+        bool removed_any = false;
+        if (point_mask != nullptr)
+            for (size_t k = 0; k < (size_t)H * W && !removed_any; ++k) removed_any = point_mask[k] == 0;
+        if (!removed_any) {
+            ch = perimeter_chain(H, W);
+            hull_pos.resize(poly.m);
+            have_chain = true;
+            for (int e = 0; e < poly.m; ++e) {
+                hull_pos[e] = perim_index(H, W, poly.id[e]);
+                if (hull_pos[e] < 0) have_chain = false;
+            }
+        } else if ((flags & 16) == 0) {
+            uint32_t first = 0xffffffffu;
+            bool isolated = false;
+            for (int r = 0; r < H; ++r)
+                for (int c = 0; c < W; ++c)
+                    if (point_mask[(size_t)r * W + c]) {
+                        if (first == 0xffffffffu) first = (uint32_t)(r * W + c);
+                        isolated = isolated || site_is_isolated(point_mask, H, W, r, c);
+                    }
+            chain_store.resize(4 * (size_t)(H + W));
+            const int n = isolated ? -1 : trace_outer_loop(point_mask, H, W, first, chain_store.data(), (int)chain_store.size());
+            if (n > 0) {
+                ch = Chain{chain_store.data(), n, H, W};
+                hull_pos.assign(poly.m, -1);
+                for (int t = 0; t < n; ++t)
+                    for (int e = 0; e < poly.m; ++e)
+                        if (poly.id[e] == chain_store[t] && hull_pos[e] < 0) hull_pos[e] = t;
+                have_chain = true;
+                for (int e = 0; e < poly.m; ++e)
+                    if (hull_pos[e] < 0) have_chain = false;
+            }
+        }
+    }
+    if (have_chain) {
+        ++stats[9];
         const Coop solo{0, 1};
         const uint8_t* pm = payload_mask;
         auto seg = [&](uint32_t ia, uint32_t ib, const P2& pa, const P2& pb, const Coop& co) {
@@ -160,10 +201,9 @@ extern "C" int fwd_hostsim(const float* payload, int C, const float* flow, float
             };
             raster_segment(pa, pb, W, H, co, pixel);
         };
-        pocket_border_edges(g, 0, perim_count(H, W), 1, seg);
+        pocket_border_edges(g, ch, 0, ch.n, 1, seg);
         for (int e = 0; e < poly.m; ++e) {
-            const int k0 = perim_index(H, W, poly.id[e]), k1 = perim_index(H, W, poly.id[e + 1 == poly.m ? 0 : e + 1]);
-            if (k0 < 0 || k1 < 0) continue;
+            const int k0 = hull_pos[e], k1 = hull_pos[e + 1 == poly.m ? 0 : e + 1];
             auto tri = [&](uint32_t ia, uint32_t ib, uint32_t ic, const P2& pa, const P2& pb, const P2& pc) {
                 auto pixel = [&](int x, int y, double w0, double w1, double w2) {
                     const size_t px = (size_t)y * W + x;
@@ -181,11 +221,10 @@ extern "C" int fwd_hostsim(const float* payload, int C, const float* flow, float
                 };
                 raster_triangle(pa, pb, pc, ia, ib, ic, W, H, solo, pixel);
             };
-            const int P = perim_count(H, W);
             NoShare noshare;
-            const PerimArc arc{H, W, P, k0};
-            if (!pocket_triangulate(g, arc, 0, ((k1 - k0) % P + P) % P, solo, tri, noshare)) ++stats[3];
-            pocket_chord(g, k0, k1, solo, seg);
+            const ChainArc arc{ch, k0};
+            if (!pocket_triangulate(g, arc, 0, ((k1 - k0) % ch.n + ch.n) % ch.n, solo, tri, noshare)) ++stats[3];
+            pocket_chord(g, ch, k0, k1, solo, seg);
         }
     }
     // ---- small faces left by removed points: triangulated by the thread of their first removed point
@@ -209,7 +248,7 @@ extern "C" int fwd_hostsim(const float* payload, int C, const float* flow, float
                     };
                     raster_triangle(pa, pb, pc, ia, ib, ic, W, H, Coop{0, 1}, pixel);
                 };
-                if (hole_fill(g, point_mask, r, c, tri)) ++stats[4];
+                if (hole_fill(g, point_mask, r, c, tri)) ++stats[8];
             }
     }
     // ---- irregular part

@@ -39,7 +39,7 @@ def sim(tmp_path_factory):
         c = 0 if pay is None else pay.shape[2]
         out = np.zeros((h, w, max(c, 1)), np.float32)
         om = np.zeros((h, w), np.uint8)
-        stats = np.zeros(8, np.int64)
+        stats = np.zeros(12, np.int64)
         pm = None if payload_mask is None else np.ascontiguousarray(payload_mask).view(np.uint8)
         pt = None if point_mask is None else np.ascontiguousarray(point_mask).view(np.uint8)
         fl = np.ascontiguousarray(flow, np.float32)
@@ -200,7 +200,7 @@ def test_enumerated_triangles_equal_the_per_pixel_search(sim, masked):
     m = inp['mask'] if masked else None
     a_v, a_m = sim(img, v, 1.0, m, m)
     produced = int(sim.stats[1])
-    b_v, b_m = sim(img, v, 1.0, m, m, flags=1 | 4 | 8)
+    b_v, b_m = sim(img, v, 1.0, m, m, flags=1 | 4 | 8 | 16)
     assert produced > 1000 and int(sim.stats[1]) >= produced      # the search path now finds all of them itself
     assert np.array_equal(a_m, b_m)
     assert np.abs(a_v - b_v)[a_m].max() <= 1e-4
@@ -219,8 +219,33 @@ def test_enumerated_faces_equal_the_search_on_random_masks(sim, density):
         yy, xx = np.mgrid[:h, :w].astype(np.float32)
         pay = np.stack([xx, yy, rng.random((h, w)).astype(np.float32) * 255], -1)
         a_v, a_m = sim(pay, v, 1.0, m, m)
-        faces = int(sim.stats[4])
-        b_v, b_m = sim(pay, v, 1.0, m, m, flags=1 | 4 | 8)
+        faces = int(sim.stats[8])
+        b_v, b_m = sim(pay, v, 1.0, m, m, flags=1 | 4 | 8 | 16)
         assert faces > 20
         assert np.array_equal(a_m, b_m)
         assert np.abs(a_v - b_v)[a_m].max() <= 1e-3
+
+
+@pytest.mark.parametrize('angle', [4.0, 17.0, 45.0])
+def test_pockets_of_a_mask_left_by_a_forward_pass(sim, angle):
+    """A forward pass leaves a mask that is valid inside the hull of the resampled points -- a rotated frame with
+    staircase edges -- and the next pass of a chain (switch_ref, modes 1 / 2) uses it as its point mask. The boundary of
+    such a mask is traced (trace_outer_loop) and the pockets between the staircase and its hull are triangulated like
+    those of the frame border: same result as the per-pixel search (flag 16 switches the tracing off)."""
+    h, w = 160, 240
+    yy, xx = np.mgrid[:h, :w].astype(np.float64)
+    a = np.deg2rad(angle)
+    u = (xx - w / 2) * np.cos(a) + (yy - h / 2) * np.sin(a)
+    t = -(xx - w / 2) * np.sin(a) + (yy - h / 2) * np.cos(a)
+    m = (np.abs(u) < 0.42 * w) & (np.abs(t) < 0.38 * h)
+    rng = np.random.default_rng(int(angle))
+    v = (gi.smooth_field(h, w) * 0.5).astype(np.float32)
+    pay = np.stack([xx, yy, rng.random((h, w)) * 255], -1).astype(np.float32)
+    a_v, a_m = sim(pay, v, 1.0, m, m)
+    chains = int(sim.stats[9])
+    b_v, b_m = sim(pay, v, 1.0, m, m, flags=1 | 16)
+    c_v, c_m = sim(pay, v, 1.0, m, m, flags=1 | 4 | 8 | 16)
+    assert chains == 1 and int(sim.stats[9]) == 0
+    assert np.array_equal(a_m, b_m) and np.array_equal(a_m, c_m)
+    assert np.abs(a_v - b_v)[a_m].max() <= 1e-3 and np.abs(a_v - c_v)[a_m].max() <= 1e-3
+    assert a_m.sum() > 0.3 * h * w

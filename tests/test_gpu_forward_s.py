@@ -386,3 +386,49 @@ def test_forward_s_is_deterministic(of):
     for _ in range(5):
         again = fs.apply(g['in_img_f32c3'], return_valid_area=True)
         assert np.array_equal(first[0], again[0]) and np.array_equal(first[1], again[1])
+
+
+def _rotated_frame_mask(h, w, angle):
+    yy, xx = np.mgrid[:h, :w].astype(np.float64)
+    a = np.deg2rad(angle)
+    u = (xx - w / 2) * np.cos(a) + (yy - h / 2) * np.sin(a)
+    t = -(xx - w / 2) * np.sin(a) + (yy - h / 2) * np.cos(a)
+    return (np.abs(u) < 0.42 * w) & (np.abs(t) < 0.38 * h)
+
+
+def test_enumerated_triangles_equal_the_per_pixel_search_on_the_device(of):
+    """The passes that triangulate explicitly -- hull pockets along the frame border or along the traced boundary of a
+    mask that a forward pass left behind (a rotated frame with staircase edges), small faces of removed points -- give
+    what the per-pixel search through the Delaunay triangulation of the boundary sites gives when they are switched off
+    (ofk_forward_s_set_disable): same masks, values equal to rounding. One batch mixes all kinds of frames."""
+    from oflibnumpy_b200 import _lib, _ops
+    from oflibnumpy_b200.device import DeviceArray
+    h, w = 240, 352
+    rng = np.random.default_rng(21)
+    base = gi.smooth_field(h, w).astype(np.float32)
+    flows = np.stack([base, base * 0.5, base, base * 0.7, base * 0.3])
+    masks = np.ones((5, h, w), bool)
+    masks[1] = rng.random((h, w)) > 0.03
+    masks[2] = _rotated_frame_mask(h, w, 7.0)
+    masks[3] = _rotated_frame_mask(h, w, 31.0)
+    masks[4] = rng.random((h, w)) > 0.15
+    yy, xx = np.mgrid[:h, :w].astype(np.float32)
+    pay = np.stack([np.stack([xx, yy, rng.random((h, w)).astype(np.float32) * 255], -1)] * 5)
+    d_f, d_p = DeviceArray.from_numpy(flows), DeviceArray.from_numpy(np.ascontiguousarray(pay))
+    d_m = DeviceArray.from_numpy(masks.view(np.uint8))
+    before = [_lib.call('ofk_rt_path_count', k) for k in (6, 8)]
+    o1, m1 = _ops.forward_s(d_f, 1.0, d_p, d_m, d_m)
+    o1, m1 = o1.numpy(), m1.numpy()
+    enumerated = _lib.call('ofk_rt_path_count', 6) - before[0]
+    _lib.call('ofk_forward_s_set_disable', 4 | 8 | 16)
+    try:
+        o2, m2 = _ops.forward_s(d_f, 1.0, d_p, d_m, d_m)
+        o2, m2 = o2.numpy(), m2.numpy()
+    finally:
+        _lib.call('ofk_forward_s_set_disable', 0)
+    assert enumerated > 1000
+    assert _lib.call('ofk_rt_path_count', 8) == before[1]
+    for n in range(5):
+        assert np.array_equal(m1[n], m2[n]), 'frame %d: %d mask mismatches' % (n, int((m1[n] != m2[n]).sum()))
+        assert np.abs(o1[n] - o2[n])[m1[n] != 0].max() <= 1e-3, 'frame %d' % n
+        assert m1[n].any() and not m1[n].all()
