@@ -480,9 +480,15 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 2) c3_ws_kernel(const __grid_
         // the warp's 4 result rows go out as two bulk tensor stores (clipped at the frame border by the hardware)
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) {
-            tma_store_3d(&maps.ov, ps.p + (int)wrp * 4 * TS, tx0, ty0 + (int)wrp * 4, n);
-            tma_store_3d(&maps.om, ps.pm + (int)wrp * 4 * TS, tx0, ty0 + (int)wrp * 4, n);
+        // operands broadcast from lane 0: tells the compiler they are warp-uniform (uniform registers for the tensor
+        // stores instead of a per-operand waterfall loop)
+        const int u_tx = __shfl_sync(0xffffffffu, tx0, 0), u_ty = __shfl_sync(0xffffffffu, ty0 + (int)wrp * 4, 0),
+                  u_n = __shfl_sync(0xffffffffu, n, 0);
+        const uint32_t u_src = __shfl_sync(0xffffffffu, smem_u32(ps.p + (int)wrp * 4 * TS), 0),
+                       u_srcm = __shfl_sync(0xffffffffu, smem_u32(ps.pm + (int)wrp * 4 * TS), 0);
+        if (elect_one()) {
+            tma_store_3d_u(&maps.ov, u_src, u_tx, u_ty, u_n);
+            tma_store_3d_u(&maps.om, u_srcm, u_tx, u_ty, u_n);
             bulk_commit();
             if (prev_s >= 0) {
                 bulk_wait_read<1>();                 // the previous tile's rows have been read out of shared memory
@@ -495,7 +501,7 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 2) c3_ws_kernel(const __grid_
         if (++s == NP) { s = 0; s_ph ^= 1; }
         if (++b == NB) { b = 0; b_ph ^= 1; }
     }
-    if (lane == 0) bulk_wait_all();
+    if (elect_one()) bulk_wait_all();   // the lane that committed the groups
 }
 
 // ------------------------------------------------------------------------------------------------ zero tests

@@ -58,65 +58,62 @@ struct Maps {
     CUtensorMap f, fm, ib, pmb, oi, om;
 };
 
+// Rounding of acc = sum(t * w) + RBIAS to a multiple of 1024. Round half up: RBIAS = 512, acc >> 10. cvRound (round half
+// to even) without a tie test: RBIAS = 511 and the bit above the fraction is added back before the shift -- a carry out
+// of the low 10 bits then needs either a fraction > 1/2 (the added bit makes no difference) or an exact tie with an odd
+// integer part, which is the one case that has to round up.
+template <bool HALF_EVEN>
+struct Rnd {
+    static constexpr uint32_t BIAS = HALF_EVEN ? 511u : 512u;
+    static __device__ __forceinline__ uint32_t fin(uint32_t acc) {
+        // (acc & 1024) >> 10 written as a high multiply: LOP3 + LEA.HI + SHF (the plain form costs a fourth instruction)
+        return HALF_EVEN ? (acc + __umulhi(acc & 1024u, 1u << 22)) >> 10 : acc >> 10;
+    }
+};
+__device__ __forceinline__ void weights_u8(unsigned a, unsigned b, uint32_t& W0, uint32_t& W1) {
+    const uint32_t pa = a * 65535u + 32u;              // (32 - a) | a << 16
+    W1 = pa * b;                                       // {(32-a)b, ab}
+    W0 = pa * 32u - W1;                                // {(32-a)(32-b), a(32-b)}: exact, no borrow between the halves
+}
 // the three result bytes of one pixel (v0, v1, v2: values 0..255) from the two 12-byte windows around its taps
 template <bool HALF_EVEN>
 __device__ __forceinline__ void blend_u8x3(uint32_t r0w0, uint32_t r0w1, uint32_t r0w2, uint32_t r1w0, uint32_t r1w1,
                                            uint32_t r1w2, unsigned sh8, unsigned a, unsigned b, uint32_t& W0,
                                            uint32_t& W1, uint32_t& v0, uint32_t& v1, uint32_t& v2) {
+    using R = Rnd<HALF_EVEN>;
     const uint32_t lo0 = __funnelshift_r(r0w0, r0w1, sh8), hi0 = __funnelshift_r(r0w1, r0w2, sh8);
     const uint32_t lo1 = __funnelshift_r(r1w0, r1w1, sh8), hi1 = __funnelshift_r(r1w1, r1w2, sh8);
     // lo = [c0t0 c1t0 c2t0 c0t1], hi = [c1t1 c2t1 . .]  ->  X = [c0t0 c0t1 c1t0 c1t1], Y = [c2t0 c2t1 . .]
     const uint32_t X0 = __byte_perm(lo0, hi0, 0x4130), Y0 = __byte_perm(lo0, hi0, 0x0052);
     const uint32_t X1 = __byte_perm(lo1, hi1, 0x4130), Y1 = __byte_perm(lo1, hi1, 0x0052);
-    const uint32_t pa = a * 65535u + 32u;              // (32 - a) | a << 16
-    W0 = pa * (32u - b);                               // {(32-a)(32-b), a(32-b)}: exact, no carry between the halves
-    W1 = pa * b;                                       // {(32-a)b, ab}
-    const uint32_t acc0 = __dp2a_lo(W1, X1, __dp2a_lo(W0, X0, 512u));
-    const uint32_t acc1 = __dp2a_hi(W1, X1, __dp2a_hi(W0, X0, 512u));
-    const uint32_t acc2 = __dp2a_lo(W1, Y1, __dp2a_lo(W0, Y0, 512u));
-    v0 = acc0 >> 10; v1 = acc1 >> 10; v2 = acc2 >> 10;               // round half up
-    if (HALF_EVEN) {
-        // cvRound sends exact ties (acc % 1024 == 0 after the +512) to the even neighbour; rare, so one test for all
-        const uint32_t t0 = acc0 & 1023u, t1 = acc1 & 1023u, t2 = acc2 & 1023u;
-        if (min(t0, min(t1, t2)) == 0u) {
-            if (t0 == 0u) v0 &= ~1u;
-            if (t1 == 0u) v1 &= ~1u;
-            if (t2 == 0u) v2 &= ~1u;
-        }
-    }
+    weights_u8(a, b, W0, W1);
+    v0 = R::fin(__dp2a_lo(W1, X1, __dp2a_lo(W0, X0, R::BIAS)));
+    v1 = R::fin(__dp2a_hi(W1, X1, __dp2a_hi(W0, X0, R::BIAS)));
+    v2 = R::fin(__dp2a_lo(W1, Y1, __dp2a_lo(W0, Y0, R::BIAS)));
 }
 
-template <bool HALF_EVEN>
-__device__ __forceinline__ uint32_t round_u8(uint32_t acc) {      // acc = sum t*w + 512
-    uint32_t v = acc >> 10;
-    if (HALF_EVEN && (acc & 1023u) == 0u) v &= ~1u;
-    return v;
-}
-__device__ __forceinline__ void weights_u8(unsigned a, unsigned b, uint32_t& W0, uint32_t& W1) {
-    const uint32_t pa = a * 65535u + 32u;              // (32 - a) | a << 16
-    W0 = pa * (32u - b);
-    W1 = pa * b;
-}
 // 1 channel: the two taps of a row are adjacent bytes (2 aligned words per row cover them)
 template <bool HALF_EVEN>
 __device__ __forceinline__ uint32_t blend_u8x1(uint32_t r0w0, uint32_t r0w1, uint32_t r1w0, uint32_t r1w1, unsigned sh8,
                                                unsigned a, unsigned b, uint32_t& W0, uint32_t& W1) {
+    using R = Rnd<HALF_EVEN>;
     const uint32_t lo0 = __funnelshift_r(r0w0, r0w1, sh8), lo1 = __funnelshift_r(r1w0, r1w1, sh8);
     weights_u8(a, b, W0, W1);
-    return round_u8<HALF_EVEN>(__dp2a_lo(W1, lo1, __dp2a_lo(W0, lo0, 512u)));
+    return R::fin(__dp2a_lo(W1, lo1, __dp2a_lo(W0, lo0, R::BIAS)));
 }
 // 4 channels: a pixel is one aligned word; returns the four result bytes packed
 template <bool HALF_EVEN>
 __device__ __forceinline__ uint32_t blend_u8x4(uint32_t t00, uint32_t t01, uint32_t t10, uint32_t t11, unsigned a,
                                                unsigned b, uint32_t& W0, uint32_t& W1) {
+    using R = Rnd<HALF_EVEN>;
     // [c0t0 c0t1 c1t0 c1t1] and [c2t0 c2t1 c3t0 c3t1] per row
     const uint32_t X0 = __byte_perm(t00, t01, 0x5140), Y0 = __byte_perm(t00, t01, 0x7362);
     const uint32_t X1 = __byte_perm(t10, t11, 0x5140), Y1 = __byte_perm(t10, t11, 0x7362);
     weights_u8(a, b, W0, W1);
-    const uint32_t v0 = round_u8<HALF_EVEN>(__dp2a_lo(W1, X1, __dp2a_lo(W0, X0, 512u)));
-    const uint32_t v1 = round_u8<HALF_EVEN>(__dp2a_hi(W1, X1, __dp2a_hi(W0, X0, 512u)));
-    const uint32_t v2 = round_u8<HALF_EVEN>(__dp2a_lo(W1, Y1, __dp2a_lo(W0, Y0, 512u)));
-    const uint32_t v3 = round_u8<HALF_EVEN>(__dp2a_hi(W1, Y1, __dp2a_hi(W0, Y0, 512u)));
+    const uint32_t v0 = R::fin(__dp2a_lo(W1, X1, __dp2a_lo(W0, X0, R::BIAS)));
+    const uint32_t v1 = R::fin(__dp2a_hi(W1, X1, __dp2a_hi(W0, X0, R::BIAS)));
+    const uint32_t v2 = R::fin(__dp2a_lo(W1, Y1, __dp2a_lo(W0, Y0, R::BIAS)));
+    const uint32_t v3 = R::fin(__dp2a_hi(W1, Y1, __dp2a_hi(W0, Y0, R::BIAS)));
     return v0 | (v1 << 8) | (v2 << 16) | (v3 << 24);
 }
 
@@ -483,23 +480,29 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 3) warp_u8_ws_kernel(const __
         uint8_t* mrow = ps.fm + own;                                        // validity bytes, in place
         uint8_t* orow = reinterpret_cast<uint8_t*>(ps.f) + own3;            // image bytes, in place
 
-        unsigned fmv[4];
-        int dxb[4], dy[4], ixs[4], iys[4];
+        // flow-mask bytes of the thread's pixels: read only where the validity byte is not already in place (see below)
+        auto load_fmv = [&](unsigned (&fmv)[4]) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) fmv[j] = (FM && MM != MM_NONE) ? mrow[j * TS] : 1u;
+        };
+        // Integer taps stay biased by the quantiser's magic number in the main path (rx = ix + KB): the bias folds into
+        // the per-tile box origin, which saves the subtraction per coordinate; ix / iy proper are formed where a slow
+        // path needs them. (Coordinates beyond the fast quantiser's range, NaN and Inf give integers far outside
+        // [-2^16, 2^16] either way and can never pass the box test; frames are smaller than 32768.)
+        constexpr int KB = 0x4B400000 >> 5;
+        const int cx = info.x + C * KB, cz = info.z + KB;
+        int dxb[4], dy[4], rx[4], ry[4];
         unsigned fa[4], fb[4];
         bool ok = true;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float2 fj = frow[j * TS];
-            fmv[j] = (FM && MM != MM_NONE) ? mrow[j * TS] : 1u;
             const float X = __fmaf_rn(sign, fj.x, xg), Y = __fmaf_rn(sign, fj.y, yg + (float)j);
-            const QCoord qx = quantise_fast(X), qy = quantise_fast(Y);
-            ixs[j] = qx.i; iys[j] = qy.i;
-            fa[j] = (unsigned)qx.f; fb[j] = (unsigned)qy.f;
-            dxb[j] = C * qx.i - info.x;
-            dy[j] = qy.i - info.z;
-            // Covered by the box? Everything else is decided per pixel. No range test is needed for the fast quantiser:
-            // it is exact for |X| < 2^17, and beyond that (or for NaN / Inf) the integer it produces is far outside
-            // [-2^16, 2^16], so such a pixel can never pass the box test (frames are smaller than 32768).
+            const int bx = __float_as_int(__fmaf_rn(X, 32.0f, 12582912.0f)), by = __float_as_int(__fmaf_rn(Y, 32.0f, 12582912.0f));
+            rx[j] = bx >> 5; ry[j] = by >> 5;
+            fa[j] = (unsigned)bx & 31u; fb[j] = (unsigned)by & 31u;
+            dxb[j] = C * rx[j] - cx;
+            dy[j] = ry[j] - cz;
             ok = ok && (unsigned)dxb[j] <= (unsigned)(BWB - 2 * C) && (unsigned)dy[j] <= (unsigned)(BH - 2);
         }
         if (__all_sync(0xffffffffu, ok)) {
@@ -509,7 +512,7 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 3) warp_u8_ws_kernel(const __
             for (int j = 0; j < 4; ++j) {
                 load_taps<C>(bs.img, (unsigned)(dy[j] * BWB + dxb[j]), w[j]);
                 if (MM == MM_PMASK) {
-                    const uint8_t* mm = bs.m + (dy[j] * BMW + (ixs[j] - info.y));
+                    const uint8_t* mm = bs.m + (dy[j] * BMW + (rx[j] - KB - info.y));
                     mt[j] = (uint32_t)mm[0] | ((uint32_t)mm[1] << 8) | ((uint32_t)mm[BMW] << 16) |
                             ((uint32_t)mm[BMW + 1] << 24);
                 }
@@ -522,20 +525,30 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 3) warp_u8_ws_kernel(const __
             dep = __reduce_or_sync(0xffffffffu, dep);
             if (lane == 0) mbar_arrive_after(&sm.bempty[b], dep, &sm.sink[wrp]);
             if (lane == 0 && wrp == 0) OFK_TR(i, 10);
+            if (MM == MM_GEOM && info.w) {
+                // The box lies inside the frame (tile-uniform; all tiles but those along the frame border): every tap is
+                // inside, so the validity byte is the flow-mask byte -- which already sits in the tile, in place.
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                uint32_t W0, W1;
-                blend_store<HALF_EVEN, C>(w[j], (unsigned)(dy[j] * BWB + dxb[j]), fa[j], fb[j], orow + j * (TS * C), W0, W1);
-                if (MM == MM_PMASK) {
-                    const unsigned valid = __dp2a_hi(W1, mt[j], __dp2a_lo(W0, mt[j], 0u)) >= s_pass;
-                    mrow[j * TS] = (uint8_t)(valid & fmv[j]);
-                } else if (MM == MM_GEOM) {
-                    unsigned valid = 1u;
-                    if (!info.w) {                      // tile-uniform: the box reaches over the frame border
-                        const uint32_t in = taps_in_frame(ixs[j], iys[j], H, W);
-                        valid = __dp2a_hi(W1, in, __dp2a_lo(W0, in, 0u)) >= s_pass;
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t W0, W1;
+                    blend_store<HALF_EVEN, C>(w[j], (unsigned)(dy[j] * BWB + dxb[j]), fa[j], fb[j], orow + j * (TS * C), W0, W1);
+                    if (!FM) mrow[j * TS] = (uint8_t)1;
+                }
+            } else {
+                unsigned fmv[4];
+                load_fmv(fmv);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t W0, W1;
+                    blend_store<HALF_EVEN, C>(w[j], (unsigned)(dy[j] * BWB + dxb[j]), fa[j], fb[j], orow + j * (TS * C), W0, W1);
+                    if (MM == MM_PMASK) {
+                        const unsigned valid = __dp2a_hi(W1, mt[j], __dp2a_lo(W0, mt[j], 0u)) >= s_pass;
+                        mrow[j * TS] = (uint8_t)(valid & fmv[j]);
+                    } else if (MM == MM_GEOM) {         // the box reaches over the frame border
+                        const uint32_t in = taps_in_frame(rx[j] - KB, ry[j] - KB, H, W);
+                        const unsigned valid = __dp2a_hi(W1, in, __dp2a_lo(W0, in, 0u)) >= s_pass;
+                        mrow[j * TS] = (uint8_t)(valid & fmv[j]);
                     }
-                    mrow[j * TS] = (uint8_t)(valid & fmv[j]);
                 }
             }
         } else {
@@ -547,11 +560,13 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 3) warp_u8_ws_kernel(const __
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const bool inbox = (unsigned)dxb[j] <= (unsigned)(BWB - 2 * C) && (unsigned)dy[j] <= (unsigned)(BH - 2);
-                need_global = need_global || !(inbox || ixs[j] < -1 || iys[j] < -1 || ixs[j] >= fw || iys[j] >= fh);
+                need_global = need_global || !(inbox || rx[j] < KB - 1 || ry[j] < KB - 1 || rx[j] - KB >= fw || ry[j] - KB >= fh);
             }
             if (__any_sync(0xffffffffu, need_global)) {
                 mixed_rows<C, HALF_EVEN, MM, FM, SM>(&sm, s, b, img, pmask, sign, H, W, rule);
             } else {
+                unsigned fmv[4];
+                load_fmv(fmv);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const bool inbox = (unsigned)dxb[j] <= (unsigned)(BWB - 2 * C) && (unsigned)dy[j] <= (unsigned)(BH - 2);
@@ -564,11 +579,11 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 3) warp_u8_ws_kernel(const __
                         blend_store<HALF_EVEN, C>(wj, o, fa[j], fb[j], dst, W0, W1);
                         uint32_t in;
                         if (MM == MM_PMASK) {
-                            const uint8_t* mm = bs.m + (dy[j] * BMW + (ixs[j] - info.y));
+                            const uint8_t* mm = bs.m + (dy[j] * BMW + (rx[j] - KB - info.y));
                             in = (uint32_t)mm[0] | ((uint32_t)mm[1] << 8) | ((uint32_t)mm[BMW] << 16) |
                                  ((uint32_t)mm[BMW + 1] << 24);
                         } else {
-                            in = taps_in_frame(ixs[j], iys[j], H, W);
+                            in = taps_in_frame(rx[j] - KB, ry[j] - KB, H, W);
                         }
                         valid = __dp2a_hi(W1, in, __dp2a_lo(W0, in, 0u)) >= s_pass;
                     } else {
@@ -584,9 +599,15 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 3) warp_u8_ws_kernel(const __
         // the warp's 4 result rows go out as bulk tensor stores (clipped at the frame border by the hardware)
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) {
-            tma_store_3d(&maps.oi, ps.f + (int)wrp * 4 * TS, C * tx0, ty0 + (int)wrp * 4, n);
-            if (MM != MM_NONE) tma_store_3d(&maps.om, ps.fm + (int)wrp * 4 * TS, tx0, ty0 + (int)wrp * 4, n);
+        // operands broadcast from lane 0: tells the compiler they are warp-uniform (uniform registers for the tensor
+        // store instead of a per-operand waterfall loop)
+        const int u_tx = __shfl_sync(0xffffffffu, tx0, 0), u_ty = __shfl_sync(0xffffffffu, ty0 + (int)wrp * 4, 0),
+                  u_n = __shfl_sync(0xffffffffu, n, 0);
+        const uint32_t u_src = __shfl_sync(0xffffffffu, smem_u32(ps.f + (int)wrp * 4 * TS), 0),
+                       u_srcm = __shfl_sync(0xffffffffu, smem_u32(ps.fm + (int)wrp * 4 * TS), 0);
+        if (elect_one()) {
+            tma_store_3d_u(&maps.oi, u_src, C * u_tx, u_ty, u_n);
+            if (MM != MM_NONE) tma_store_3d_u(&maps.om, u_srcm, u_tx, u_ty, u_n);
             bulk_commit();
             if (prev_s >= 0) {
                 bulk_wait_read<1>();                 // the previous tile's rows have been read out of shared memory
@@ -598,7 +619,7 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 3) warp_u8_ws_kernel(const __
         if (++s == NP) { s = 0; s_ph ^= 1; }
         if (++b == NB) { b = 0; b_ph ^= 1; }
     }
-    if (lane == 0) bulk_wait_all();
+    if (elect_one()) bulk_wait_all();   // the lane that committed the groups
 }
 
 constexpr int WS_NP = 6, WS_NB = 2, WS_LA = 3, WS_PW = 1;   // measured best: one producer warp (a P loader warp costs the 3rd CTA its registers)

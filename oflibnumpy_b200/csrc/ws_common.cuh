@@ -59,6 +59,21 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
                  ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
+__device__ __forceinline__ void tma_store_3d_u(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
