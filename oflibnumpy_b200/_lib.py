@@ -99,7 +99,8 @@ def symbols():
 
 
 def library_path():
-    return _build.lib_path()
+    """The in-tree library; OFK_LIB_PATH names another build of it (A/B measurements of two builds inside one job)."""
+    return os.environ.get('OFK_LIB_PATH') or _build.lib_path()
 
 
 def load():

@@ -480,12 +480,9 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 2) c3_ws_kernel(const __grid_
         // the warp's 4 result rows go out as two bulk tensor stores (clipped at the frame border by the hardware)
         fence_async_smem();
         __syncwarp();
-        // operands broadcast from lane 0: tells the compiler they are warp-uniform (uniform registers for the tensor
-        // stores instead of a per-operand waterfall loop)
-        const int u_tx = __shfl_sync(0xffffffffu, tx0, 0), u_ty = __shfl_sync(0xffffffffu, ty0 + (int)wrp * 4, 0),
-                  u_n = __shfl_sync(0xffffffffu, n, 0);
-        const uint32_t u_src = __shfl_sync(0xffffffffu, smem_u32(ps.p + (int)wrp * 4 * TS), 0),
-                       u_srcm = __shfl_sync(0xffffffffu, smem_u32(ps.pm + (int)wrp * 4 * TS), 0);
+        // (issued under elect.sync: the compiler moves the operands to uniform registers without a waterfall loop)
+        const int u_tx = tx0, u_ty = ty0 + (int)wrp * 4, u_n = n;
+        const uint32_t u_src = smem_u32(ps.p + (int)wrp * 4 * TS), u_srcm = smem_u32(ps.pm + (int)wrp * 4 * TS);
         if (elect_one()) {
             tma_store_3d_u(&maps.ov, u_src, u_tx, u_ty, u_n);
             tma_store_3d_u(&maps.om, u_srcm, u_tx, u_ty, u_n);

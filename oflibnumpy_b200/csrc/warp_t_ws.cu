@@ -5,7 +5,7 @@
 // Same pipeline as combine3_ws.cu: CTA = 1 producer warp + 8 consumer warps, persistent over 32x32 output tiles.
 //   producer : TMA-loads the flow tile (and the flow-mask tile) ahead of time, estimates the bounding box of the
 //              tile's sample positions from the tile perimeter and TMA-loads that box of the image -- as rows of
-//              3*W bytes, 160 bytes x 48 rows, start aligned down to 16 bytes -- and, if a target mask is resampled, the
+//              3*W bytes, 192 bytes x 48 rows, start aligned down to 16 bytes -- and, if a target mask is resampled, the
 //              matching box of the mask. Hardware zero fill outside the frame == cv2.remap's BORDER_CONSTANT(0).
 //   consumers: both horizontal taps of a row (6 bytes at an arbitrary byte offset) come out of three aligned shared-
 //              memory words; the blend is pure integer (cv2.remap's uint8 fixed-point path and its int16 path are both
@@ -27,11 +27,21 @@ using namespace ws;
 
 constexpr int TS = 32;
 constexpr int BH = 48;            // box rows
-constexpr int BMW = 64;           // mask box width (bytes): start is aligned down to 16
 constexpr int NCW = 8;            // consumer warps
+#ifndef OFK_BOX3
+#define OFK_BOX3 192
+#endif
 // image box width in bytes for C interleaved uint8 channels: 48 pixels x C + up to 15 bytes of alignment slack, rounded
-// up to the 16 bytes TMA needs (C = 1: 64, C = 3: 160, C = 4: 208)
-__host__ __device__ constexpr int box_bytes(int C) { return (48 * C + 15 + 15) / 16 * 16; }
+// up to the 16 bytes TMA needs (C = 1: 64, C = 4: 208). C = 3 would be 160 bytes = 40 words per box row: under a rotation
+// the 32 pixels of a warp row sample 2-3 consecutive box rows, each segment 8 words further along, and with a row pitch
+// of 8 banks (mod 32) the first and third segment land on the same banks (either sense of rotation: 8k +- 8k) -- measured
+// 2.15 wavefronts per tap load. 192 bytes = 48 words = 16 banks (mod 32) keeps the segments apart: 24k, 8k.
+__host__ __device__ constexpr int box_bytes(int C) { return C == 3 ? OFK_BOX3 : (48 * C + 15 + 15) / 16 * 16; }
+// pixels of a box row that are usable whatever the 16-byte alignment of its start
+__host__ __device__ constexpr int box_px(int C) { return (box_bytes(C) - 15) / C; }
+// mask box width (bytes = pixels): its start is the first needed pixel aligned down to 16, the image box reaches at most
+// (box_bytes - 2C) / C + 15 <= 77 pixels (+ 1 tap) beyond that
+constexpr int BMW = 80;
 // BH rows, rounded up to 128 with room for the word loads that run a few bytes past the last tap
 __host__ __device__ constexpr int img_stage(int C) { return (BH * box_bytes(C) + 16 + 127) / 128 * 128; }
 
@@ -435,7 +445,7 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 3) warp_u8_ws_kernel(const __
                 y0 = max(-1, min(H - 1, y0)); y1 = max(-1, min(H - 1, y1));
                 // centre the needed range [x0, x1 + 1] in the box (spare margin on both sides for curved flows)
                 const int needw = x1 + 2 - x0, needh = y1 + 2 - y0;
-                const int vx0 = x0 - max(0, (48 - needw) / 2);
+                const int vx0 = x0 - max(0, (box_px(C) - needw) / 2);
                 const int bx0 = (C * vx0) & ~15;             // 16-byte aligned box start, in bytes of the C*W-byte row
                 const int mx0 = vx0 & ~15;
                 const int by0 = y0 - max(0, (BH - needh) / 2);
@@ -599,12 +609,9 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 3) warp_u8_ws_kernel(const __
         // the warp's 4 result rows go out as bulk tensor stores (clipped at the frame border by the hardware)
         fence_async_smem();
         __syncwarp();
-        // operands broadcast from lane 0: tells the compiler they are warp-uniform (uniform registers for the tensor
-        // store instead of a per-operand waterfall loop)
-        const int u_tx = __shfl_sync(0xffffffffu, tx0, 0), u_ty = __shfl_sync(0xffffffffu, ty0 + (int)wrp * 4, 0),
-                  u_n = __shfl_sync(0xffffffffu, n, 0);
-        const uint32_t u_src = __shfl_sync(0xffffffffu, smem_u32(ps.f + (int)wrp * 4 * TS), 0),
-                       u_srcm = __shfl_sync(0xffffffffu, smem_u32(ps.fm + (int)wrp * 4 * TS), 0);
+        // (issued under elect.sync: the compiler moves the operands to uniform registers without a waterfall loop)
+        const int u_tx = tx0, u_ty = ty0 + (int)wrp * 4, u_n = n;
+        const uint32_t u_src = smem_u32(ps.f + (int)wrp * 4 * TS), u_srcm = smem_u32(ps.fm + (int)wrp * 4 * TS);
         if (elect_one()) {
             tma_store_3d_u(&maps.oi, u_src, C * u_tx, u_ty, u_n);
             if (MM != MM_NONE) tma_store_3d_u(&maps.om, u_srcm, u_tx, u_ty, u_n);
