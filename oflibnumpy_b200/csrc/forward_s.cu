@@ -315,7 +315,10 @@ constexpr int REC_OK = 1 << 15;    // record flag: the cell is a positively orie
 // in-circle determinant, weights and payload in float64. Without the queue the 1..4 candidates of a cell are a
 // divergent loop that runs its longest trip count on every warp (measured: 765 thread instructions per pixel).
 template <int CT>
-__global__ void __launch_bounds__(256, 3) fwd_raster_kernel(const RasterArgs A) {
+#ifndef OFK_RASTER_CTAS
+#define OFK_RASTER_CTAS 3
+#endif
+__global__ void __launch_bounds__(256, OFK_RASTER_CTAS) fwd_raster_kernel(const RasterArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int PC = CT > 0 ? CT : 0;
     P2* s_pos = reinterpret_cast<P2*>(smem);
@@ -325,30 +328,52 @@ __global__ void __launch_bounds__(256, 3) fwd_raster_kernel(const RasterArgs A) 
     uint8_t* s_pm = reinterpret_cast<uint8_t*>(s_q + 8 * QCAP);
     uint8_t* s_pt = s_pm + NV;
     const int n = blockIdx.z, i0 = blockIdx.y * TH, j0 = blockIdx.x * TW;
-    if (A.folded[n] == 2) return;   // passed through (zero flow)
     const size_t frame = (size_t)n * A.H * A.W;
     const float2* fl = reinterpret_cast<const float2*>(A.flow) + frame;
-    // pixel origin of the tile's local float32 coordinates: the displaced centre vertex
-    int ox, oy;
-    {
-        const int gi = min(i0 + TH / 2, A.H - 1), gj = min(j0 + TW / 2, A.W - 1);
-        const float2 f = __ldg(fl + (size_t)gi * A.W + gj);
-        const P2 pc = displaced(f.x, f.y, gi, gj, A.sign);
-        ox = (int)fmin(fmax(rint(pc.x), -1048576.0), 1048576.0);
-        oy = (int)fmin(fmax(rint(pc.y), -1048576.0), 1048576.0);
-    }
-    for (int v = threadIdx.x; v < NV; v += 256) {
+    // Staging: every global load of the tile (frame state, centre vertex, the thread's <= 5 vertices with payload and
+    // mask bytes) is requested before the first one is used -- one memory round trip per CTA instead of one per loop
+    // trip plus two dependent ones in front (ncu: half of the kernel's stall samples sat on these loads).
+    constexpr int VPT = (NV + 255) / 256;
+    const int fstate = A.folded[n];   // 2 = passed through (set by an earlier kernel); other CTAs may store 1 meanwhile
+    const int cgi = min(i0 + TH / 2, A.H - 1), cgj = min(j0 + TW / 2, A.W - 1);
+    const float2 fc = __ldg(fl + (size_t)cgi * A.W + cgj);
+    float2 fv[VPT];
+    float pay[VPT][PC > 0 ? PC : 1];
+    uint8_t pmv[VPT], ptv[VPT];
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+        const int v = min((int)threadIdx.x + k * 256, NV - 1);   // (the clamped duplicates are not stored)
         const int r = v / SW, c = v - r * SW;
         const int gi = min(i0 + r, A.H - 1), gj = min(j0 + c, A.W - 1);
         const size_t g = (size_t)gi * A.W + gj;
-        const float2 f = __ldg(fl + g);
-        const P2 p = displaced(f.x, f.y, gi, gj, A.sign);
-        s_pos[v] = p;
-        s_posf[v] = make_float2((float)(p.x - (double)ox), (float)(p.y - (double)oy));
+        fv[k] = __ldg(fl + g);
 #pragma unroll
-        for (int k = 0; k < PC; ++k) s_pay[v * PC + k] = __ldg(A.payload + (frame + g) * PC + k);
-        s_pm[v] = A.payload_mask ? A.payload_mask[frame + g] : (uint8_t)1;
-        s_pt[v] = A.point_mask ? A.point_mask[frame + g] : (uint8_t)1;
+        for (int q = 0; q < PC; ++q) pay[k][q] = __ldg(A.payload + (frame + g) * PC + q);
+        pmv[k] = A.payload_mask ? __ldg(A.payload_mask + frame + g) : (uint8_t)1;
+        ptv[k] = A.point_mask ? __ldg(A.point_mask + frame + g) : (uint8_t)1;
+    }
+    if (fstate == 2) return;   // passed through (zero flow)
+    // pixel origin of the tile's local float32 coordinates: the displaced centre vertex
+    int ox, oy;
+    {
+        const P2 pc = displaced(fc.x, fc.y, cgi, cgj, A.sign);
+        ox = (int)fmin(fmax(rint(pc.x), -1048576.0), 1048576.0);
+        oy = (int)fmin(fmax(rint(pc.y), -1048576.0), 1048576.0);
+    }
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+        const int v = (int)threadIdx.x + k * 256;
+        if (v < NV) {
+            const int r = v / SW, c = v - r * SW;
+            const int gi = min(i0 + r, A.H - 1), gj = min(j0 + c, A.W - 1);
+            const P2 p = displaced(fv[k].x, fv[k].y, gi, gj, A.sign);
+            s_pos[v] = p;
+            s_posf[v] = make_float2((float)(p.x - (double)ox), (float)(p.y - (double)oy));
+#pragma unroll
+            for (int q = 0; q < PC; ++q) s_pay[v * PC + q] = pay[k][q];
+            s_pm[v] = pmv[k];
+            s_pt[v] = ptv[k];
+        }
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
