@@ -25,6 +25,8 @@
 // diagonal (similarity transforms of the pixel grid); Qhull's pick there is an artefact of its facet merging.
 #include <algorithm>
 
+#include <mutex>
+
 #include "ofk_common.cuh"
 #include "forward_irregular.cuh"
 
@@ -1660,7 +1662,7 @@ __global__ void __launch_bounds__(256) irr_heavy_kernel(const SolveArgs A) {
 
 // ------------------------------------------------------------------------------------------------- workspace layout
 struct WsLayout {
-    size_t sites, cover, heavy, todo, chain, hull_pos, chain_n, first_valid, isolated, todo_count, heavy_count, hole_count, masked, bins, coarse, hullws, hullinfo, folded, chunks, opos, oids, ocount, poly, total;
+    size_t sites, cover, heavy, todo, chain, hull_pos, chain_n, first_valid, isolated, todo_count, heavy_count, hole_count, masked, bins, coarse, hullws, hullinfo, folded, state_side, chunks, opos, oids, ocount, poly, total;
     size_t zero_begin, zero_bytes;   // region cleared before every call (bins, coarse, hull keys, folded flags)
     int nbx, nby, ncx, ncy, nb, nc, chain_cap;
 };
@@ -1711,6 +1713,8 @@ static WsLayout ws_layout(int N, int H, int W) {
     o = align_up(o + (size_t)N * sizeof(HullWs), 256);
     L.folded = o;
     o = align_up(o + (size_t)N * 4, 256);
+    L.state_side = o;
+    o = align_up(o + (size_t)N * 4, 256);
     L.chunks = o;
     o = align_up(o + (size_t)N * ((L.nb + SCAN_CHUNK - 1) / SCAN_CHUNK) * 4, 256);
     L.heavy_count = o;
@@ -1737,9 +1741,11 @@ __global__ void hull_ws_init_kernel(HullWs* ws, int N) {
 
 // Frames whose flow is zero below the threshold are not resampled: apply_flow returns the target itself there
 // (utils.py:215-216). frame_state: 0 = resample, 1 = folded (set by the raster kernel), 2 = pass through.
-__global__ void fwd_mark_inactive_kernel(const int* __restrict__ flow_nonzero, int* __restrict__ frame_state, int N) {
+// state_side is the copy read by the kernels that run beside the raster kernel (see ofk_forward_s_ex): 0 or 2 only.
+__global__ void fwd_mark_inactive_kernel(const int* __restrict__ flow_nonzero, int* __restrict__ frame_state,
+                                         int* __restrict__ state_side, int N) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n < N && flow_nonzero[n] == 0) frame_state[n] = 2;
+    if (n < N && flow_nonzero[n] == 0) frame_state[n] = state_side[n] = 2;
 }
 
 __global__ void __launch_bounds__(256) fwd_passthrough_kernel(const float* __restrict__ payload, int C,
@@ -1773,6 +1779,40 @@ unsigned long long stat(int which) {
 unsigned long long forward_s_stat(int which) { return fwdk::stat(which); }
 static std::atomic<double> g_flip_tol{0.0};
 static std::atomic<int> g_disable{0};   // test hook, see ofk_forward_s_set_disable
+
+// The boundary-site / hull chain does not depend on the raster kernel: it runs beside it on a library-owned side stream
+// (forked from and joined back into the caller's stream with events). One per device; the enqueue of a call holds the
+// mutex, so that concurrent callers cannot interleave their fork / join records on the shared events.
+struct SideStream {
+    std::mutex mu;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    int state = 0;   // 0 = not created yet, 1 = ready, -1 = unavailable
+};
+static SideStream g_side[64];
+static bool overlap_enabled() {
+    static std::atomic<int> v{-1};
+    if (v.load() < 0) {
+        const char* e = getenv("OFK_FWD_OVERLAP");   // test hook: 0 = everything on the caller's stream
+        v.store((e != nullptr && e[0] == '0') ? 0 : 1);
+    }
+    return v.load() == 1;
+}
+// with the mutex held
+static bool side_ready(SideStream& sd) {
+    if (sd.state == 0) {
+        int lo = 0, hi = 0;
+        sd.state = -1;
+        if (cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess &&
+            cudaStreamCreateWithPriority(&sd.stream, cudaStreamNonBlocking, hi) == cudaSuccess &&
+            cudaEventCreateWithFlags(&sd.fork, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&sd.join, cudaEventDisableTiming) == cudaSuccess)
+            sd.state = 1;
+        else
+            cudaGetLastError();
+    }
+    return sd.state == 1;
+}
 
 }  // namespace ofk
 
@@ -1844,6 +1884,7 @@ extern "C" int ofk_forward_s_ex(const float* payload, int C, const float* flow, 
     HullWs* d_hullws = reinterpret_cast<HullWs*>(base + L.hullws);
     fwd::HullInfo* d_info = reinterpret_cast<fwd::HullInfo*>(base + L.hullinfo);
     int* d_folded = reinterpret_cast<int*>(base + L.folded);
+    int* d_state_side = reinterpret_cast<int*>(base + L.state_side);
     const size_t px = (size_t)N * H * W;
     const int strict = mask_rule == OFK_RULE_STRICT ? 1 : 0;
 
@@ -1852,8 +1893,27 @@ extern "C" int ofk_forward_s_ex(const float* payload, int C, const float* flow, 
     hull_ws_init_kernel<<<(N * fwd::HULL_DIRS + 255) / 256, 256, 0, st>>>(d_hullws, N);
     OFK_LAUNCHED();
     if (flow_nonzero != nullptr) {
-        fwd_mark_inactive_kernel<<<(N + 255) / 256, 256, 0, st>>>(flow_nonzero, d_folded, N);
+        fwd_mark_inactive_kernel<<<(N + 255) / 256, 256, 0, st>>>(flow_nonzero, d_folded, d_state_side, N);
         OFK_LAUNCHED();
+    }
+
+    // ---- fork: the site / hull chain below goes to the side stream (`ss`), the raster kernel stays on `st`
+    cudaStream_t ss = st;
+    std::unique_lock<std::mutex> side_lock;
+    SideStream* side = nullptr;
+    {
+        int dev = 0;
+        if (overlap_enabled() && H > 1 && W > 1 && cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
+            side_lock = std::unique_lock<std::mutex>(g_side[dev].mu);
+            if (side_ready(g_side[dev])) {
+                side = &g_side[dev];
+                ss = side->stream;
+                OFK_CUDA(cudaEventRecord(side->fork, st));
+                OFK_CUDA(cudaStreamWaitEvent(ss, side->fork, 0));
+            } else {
+                side_lock.unlock();
+            }
+        }
     }
 
     // ---- regular part
@@ -1872,39 +1932,41 @@ extern "C" int ofk_forward_s_ex(const float* payload, int C, const float* flow, 
     }
 
     // ---- irregular part: boundary sites -> bins -> hull filter -> per-pixel point location
+    // (up to the join below on the side stream; these kernels see the frame states 0 / 2 only, a frame the raster kernel
+    // finds folded is processed like any other here and skipped by everything after the join)
     // the list of removed points shares its buffer with the work items of the pocket pass (used one after the other)
     const unsigned int hole_cap = (unsigned int)std::min<size_t>(((size_t)N * H * W + 8) / 8, 0xffffffffu);
     int* d_masked = point_mask != nullptr ? reinterpret_cast<int*>(base + L.masked) : nullptr;
     unsigned int* d_first = reinterpret_cast<unsigned int*>(base + L.first_valid);
     int* d_isolated = reinterpret_cast<int*>(base + L.isolated);
     if (point_mask != nullptr) {
-        OFK_CUDA(cudaMemsetAsync(d_first, 0xFF, sizeof(unsigned int) * (size_t)N, st));
-        fwd_scan_mask_kernel<<<dim3(std::max(1, std::min(64, (sm_count() * 8 + N - 1) / N)), N), 256, 0, st>>>(
+        OFK_CUDA(cudaMemsetAsync(d_first, 0xFF, sizeof(unsigned int) * (size_t)N, ss));
+        fwd_scan_mask_kernel<<<dim3(std::max(1, std::min(64, (sm_count() * 8 + N - 1) / N)), N), 256, 0, ss>>>(
             point_mask, (size_t)H * W, d_masked, d_first);
         OFK_LAUNCHED();
     }
-    IrrArgs I{flow, point_mask, d_folded, d_bins, d_coarse, d_sites, flow_sign, H, W, L.nbx, L.nby, L.ncx, L.ncy,
+    IrrArgs I{flow, point_mask, d_state_side, d_bins, d_coarse, d_sites, flow_sign, H, W, L.nbx, L.nby, L.ncx, L.ncy,
               (point_mask == nullptr && H >= 3 && W >= 3) ? 1 : 0, d_masked, d_isolated,
               reinterpret_cast<unsigned long long*>(base + L.heavy),
               reinterpret_cast<unsigned int*>(base + L.hole_count), hole_cap};
     const long long cand = I.perimeter_only ? 2ll * W + 2ll * (H - 2) : (long long)H * W;
     dim3 sgrid((unsigned)((cand + 255) / 256), N);
-    irr_sites_kernel<0><<<sgrid, 256, 0, st>>>(I);
+    irr_sites_kernel<0><<<sgrid, 256, 0, ss>>>(I);
     OFK_LAUNCHED();
     const int chunks = (L.nb + SCAN_CHUNK - 1) / SCAN_CHUNK;
     uint32_t* d_chunks = reinterpret_cast<uint32_t*>(base + L.chunks);
-    irr_scan_sums_kernel<<<dim3(chunks, N), 256, 0, st>>>(d_bins, L.nb, d_chunks, chunks);
+    irr_scan_sums_kernel<<<dim3(chunks, N), 256, 0, ss>>>(d_bins, L.nb, d_chunks, chunks);
     OFK_LAUNCHED();
-    irr_scan_chunks_kernel<<<N, 32, 0, st>>>(d_chunks, chunks);
+    irr_scan_chunks_kernel<<<N, 32, 0, ss>>>(d_chunks, chunks);
     OFK_LAUNCHED();
-    irr_scan_final_kernel<<<dim3(chunks, N), 256, 0, st>>>(d_bins, L.nb, d_chunks, chunks);
+    irr_scan_final_kernel<<<dim3(chunks, N), 256, 0, ss>>>(d_bins, L.nb, d_chunks, chunks);
     OFK_LAUNCHED();
-    irr_sites_kernel<1><<<sgrid, 256, 0, st>>>(I);
+    irr_sites_kernel<1><<<sgrid, 256, 0, ss>>>(I);
     OFK_LAUNCHED();
 
     HullArgs Hh;
     Hh.flow = flow;
-    Hh.folded = d_folded;
+    Hh.folded = d_state_side;
     Hh.bins = d_bins;
     Hh.sites = d_sites;
     Hh.ws = d_hullws;
@@ -1918,23 +1980,23 @@ extern "C" int ofk_forward_s_ex(const float* payload, int C, const float* flow, 
     Hh.W = W;
     Hh.nb = L.nb;
     dim3 hgrid((unsigned)((cand + 256 * HULL_ITEMS - 1) / (256 * HULL_ITEMS)), N);
-    hull_sites_kernel<0><<<hgrid, 256, 0, st>>>(Hh);
+    hull_sites_kernel<0><<<hgrid, 256, 0, ss>>>(Hh);
     OFK_LAUNCHED();
-    hull_sites_kernel<1><<<hgrid, 256, 0, st>>>(Hh);
+    hull_sites_kernel<1><<<hgrid, 256, 0, ss>>>(Hh);
     OFK_LAUNCHED();
-    hull_frame_kernel<0><<<N, 32, 0, st>>>(Hh);
+    hull_frame_kernel<0><<<N, 32, 0, ss>>>(Hh);
     OFK_LAUNCHED();
-    hull_sites_kernel<2><<<hgrid, 256, 0, st>>>(Hh);
+    hull_sites_kernel<2><<<hgrid, 256, 0, ss>>>(Hh);
     OFK_LAUNCHED();
-    hull_frame_kernel<1><<<N, 32, 0, st>>>(Hh);
+    hull_frame_kernel<1><<<N, 32, 0, ss>>>(Hh);
     OFK_LAUNCHED();
 
-    OuterArgs O{flow, d_folded, d_bins, d_sites, d_info, reinterpret_cast<fwd::P2*>(base + L.opos),
+    OuterArgs O{flow, d_state_side, d_bins, d_sites, d_info, reinterpret_cast<fwd::P2*>(base + L.opos),
                 reinterpret_cast<uint32_t*>(base + L.oids), reinterpret_cast<unsigned int*>(base + L.ocount),
                 reinterpret_cast<fwd::HullPoly*>(base + L.poly), flow_sign, H, W, L.nb};
-    hull_outer_kernel<<<dim3((unsigned)std::min<long long>((cand + 255) / 256, 64), N), 256, 0, st>>>(O);
+    hull_outer_kernel<<<dim3((unsigned)std::min<long long>((cand + 255) / 256, 64), N), 256, 0, ss>>>(O);
     OFK_LAUNCHED();
-    hull_wrap_kernel<<<N, 256, 0, st>>>(O);
+    hull_wrap_kernel<<<N, 256, 0, ss>>>(O);
     OFK_LAUNCHED();
 
     uint32_t* d_chain = reinterpret_cast<uint32_t*>(base + L.chain);
@@ -1942,11 +2004,17 @@ extern "C" int ofk_forward_s_ex(const float* payload, int C, const float* flow, 
     int* d_hull_pos = reinterpret_cast<int*>(base + L.hull_pos);
     const int disable = g_disable.load();
     if (point_mask != nullptr && !(disable & 16)) {   // masked frames: the outer boundary of the mask as the chain
-        TraceArgs T{point_mask, d_folded, d_masked, d_isolated, d_first,
+        TraceArgs T{point_mask, d_state_side, d_masked, d_isolated, d_first,
                     reinterpret_cast<const fwd::HullPoly*>(base + L.poly), d_chain, d_chain_n, d_hull_pos, L.chain_cap,
                     H, W};
-        irr_trace_kernel<<<N, 32, 0, st>>>(T);
+        irr_trace_kernel<<<N, 32, 0, ss>>>(T);
         OFK_LAUNCHED();
+    }
+    // ---- join
+    if (side != nullptr) {
+        OFK_CUDA(cudaEventRecord(side->join, ss));
+        OFK_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+        side_lock.unlock();
     }
     PocketArgs Pk{payload, flow, payload_mask, d_folded, d_masked, d_chain,
                   (point_mask != nullptr && !(disable & 16)) ? d_chain_n : nullptr,

@@ -432,3 +432,68 @@ def test_enumerated_triangles_equal_the_per_pixel_search_on_the_device(of):
         assert np.array_equal(m1[n], m2[n]), 'frame %d: %d mask mismatches' % (n, int((m1[n] != m2[n]).sum()))
         assert np.abs(o1[n] - o2[n])[m1[n] != 0].max() <= 1e-3, 'frame %d' % n
         assert m1[n].any() and not m1[n].all()
+
+
+_OVERLAP_CODE = r'''
+import hashlib, sys, threading
+import numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import golden_inputs as gi
+import oflibnumpy_b200 as of
+from oflibnumpy_b200.device import Stream
+h, w, n = 270, 480, 6
+rng = np.random.default_rng(5)
+flows = np.stack([np.asarray(of.from_transforms(gi.cfg4_transforms(i), (h, w), 's')) for i in range(n)])
+flows[1] = gi.smooth_field(h, w)                       # curved border: hull pockets
+yy, xx = np.mgrid[:h, :w].astype(np.float32)
+flows[2, ..., 0] = 60 * np.sin(xx / 9)                 # folds: redone by the order-independent resolve
+flows[3] = 0                                           # zero flow: passed through
+masks = rng.random((n, h, w)) > 0.03
+masks[4] = True
+dig = hashlib.sha256()
+def run(tag):
+    fb = of.FlowBatch(flows, 's', masks)
+    for res in (fb.invert(), fb.switch_ref()):
+        v, m = res.numpy()
+        dig.update(np.ascontiguousarray(m).tobytes()); dig.update(np.ascontiguousarray(v).tobytes())
+run('main')
+# two host threads enqueue ofk_forward_s on two streams at once (C ABI, explicit streams): the shared side stream
+# serialises their chains
+from oflibnumpy_b200 import _lib
+from oflibnumpy_b200.device import DeviceArray
+d_fl = DeviceArray.from_numpy(flows)
+d_pm = DeviceArray.from_numpy(masks.view(np.uint8))
+wsb = _lib.call('ofk_forward_s_workspace', n, h, w)
+bufs = [(DeviceArray.empty((n, h, w, 2), np.float32), DeviceArray.empty((n, h, w), np.uint8),
+         DeviceArray.empty((wsb,), np.uint8), Stream()) for _ in range(2)]
+of.device.synchronize()
+def worker(k):
+    o_v, o_m, ws, st = bufs[k]
+    for _ in range(3):
+        _lib.call('ofk_forward_s', d_fl.ptr, 2, d_fl.ptr, 1.0, d_pm.ptr, d_pm.ptr, o_v.ptr, o_m.ptr, _lib.RULE_STRICT, n, h,
+                  w, ws.ptr, wsb, st.handle)
+    st.synchronize()
+ts = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
+[t.start() for t in ts]; [t.join() for t in ts]
+out = [hashlib.sha256(b[1].numpy().tobytes() + b[0].numpy().tobytes()).hexdigest() for b in bufs]
+assert out[0] == out[1]
+print('DIGEST', dig.hexdigest(), out[0])
+'''
+
+
+def test_side_stream_overlap_gives_the_same_bytes():
+    """ofk_forward_s runs its site / hull chain on a side stream beside the raster kernel (fork / join with events).
+    The result must be byte-identical to everything on one stream (OFK_FWD_OVERLAP=0, read once per process): batch with
+    a curved field, a folding frame, a zero-flow frame and removed points; and two host threads on two streams."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = _OVERLAP_CODE % (os.path.dirname(here), here)
+    digests = []
+    for env_extra in ({}, {'OFK_FWD_OVERLAP': '0'}):
+        res = subprocess.run([sys.executable, '-c', code], env=dict(os.environ, **env_extra), capture_output=True,
+                             text=True, timeout=900)
+        assert res.returncode == 0, res.stdout + res.stderr
+        digests.append([l for l in res.stdout.splitlines() if l.startswith('DIGEST')][0])
+    assert digests[0] == digests[1]
