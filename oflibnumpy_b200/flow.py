@@ -610,6 +610,37 @@ class Flow(object):
             raise ValueError("Error visualising flow: Mode needs to be either 'bgr', 'rgb', or 'hsv'")
         return _ops.visualise(self._vd(), self._md(), mode, show_mask, show_mask_borders, range_max, DEFAULT_THRESHOLD)
 
+    # ---- host-side presentation / estimation (not on the hot path, delegated)
+    def _host_reference(self):
+        """The same flow as an object of the reference package on a host copy: `matrix` (OpenCV's robust estimators),
+        `visualise_arrows` and the `show*` GUI helpers are OpenCV drawing / windows on the host and are not rebuilt
+        here. Needs `oflibnumpy` importable next to this package."""
+        try:
+            import oflibnumpy
+        except ImportError as e:
+            raise ImportError("oflibnumpy_b200 delegates matrix / visualise_arrows / show* to the reference package on "
+                              "a host copy of the flow: install oflibnumpy to use them") from e
+        return oflibnumpy.Flow(np.array(self.vecs), self._ref, np.array(self.mask))
+
+    def matrix(self, dof=None, method=None, masked=None):
+        """flow_class.py:797-867 on a host copy (cv2.estimateAffinePartial2D / estimateAffine2D / findHomography)."""
+        return self._host_reference().matrix(dof, method, masked)
+
+    def visualise_arrows(self, grid_dist=None, img=None, scaling=None, show_mask=None, show_mask_borders=None,
+                         colour=None, thickness=None):
+        """flow_class.py:953-1059 on a host copy (OpenCV drawing)."""
+        return self._host_reference().visualise_arrows(grid_dist, img, scaling, show_mask, show_mask_borders, colour,
+                                                       thickness)
+
+    def show(self, wait=None, show_mask=None, show_mask_borders=None):
+        """flow_class.py:1061-1077 on a host copy (cv2.imshow)."""
+        return self._host_reference().show(wait, show_mask, show_mask_borders)
+
+    def show_arrows(self, wait=None, grid_dist=None, img=None, scaling=None, show_mask=None, show_mask_borders=None,
+                    colour=None):
+        """flow_class.py:1079-1111 on a host copy (cv2.imshow)."""
+        return self._host_reference().show_arrows(wait, grid_dist, img, scaling, show_mask, show_mask_borders, colour)
+
     def get_padding(self):
         """[top, bottom, left, right] as in the reference (flow_class.py:1197-1228); masked min/max on the device."""
         mny, mxy, mnx, mxx = (float(x) for x in _ops.extent(self._vd(), self._md(), 1.0 if self._ref == 't' else -1.0,

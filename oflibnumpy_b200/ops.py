@@ -17,7 +17,8 @@ from .validation import (get_valid_ref, validate_shape, validate_flow_array, val
 __all__ = ['apply_flow', 'combine_flows', 'invert_flow', 'switch_flow_ref', 'valid_target', 'valid_source',
            'get_flow_padding', 'from_matrix', 'from_transforms', 'matrix_from_transforms', 'matrix_from_transform',
            'is_zero_flow', 'threshold_vectors', 'points_inside_area', 'resize_flow', 'track_pts', 'load_kitti',
-           'load_sintel', 'load_sintel_mask']
+           'load_sintel', 'load_sintel_mask', 'visualise_flow', 'get_flow_matrix', 'visualise_flow_arrows', 'show_flow',
+           'show_flow_arrows', 'visualise_definition']
 
 from .io import load_kitti, load_sintel, load_sintel_mask  # noqa: E402,F401
 
@@ -266,3 +267,43 @@ def _combine2_t_device(a, b):
                                      pos_f32=True)
     resampled = Flow._wrap(vals, 't', _ops.greater(mval, 0.99))
     return b - resampled
+
+
+# ---- host-side presentation / estimation wrappers of flow_operations.py:25-68,251-350 (not on
+# ---- the hot path). visualise_flow runs on the device like Flow.visualise; the others delegate like the Flow methods.
+def visualise_flow(flow, mode, range_max=None):
+    """flow_operations.py:274-284."""
+    return Flow(flow).visualise(mode, range_max=range_max)
+
+
+def get_flow_matrix(flow, ref, dof=None, method=None):
+    """flow_operations.py:251-271."""
+    return Flow(flow, ref).matrix(
+        dof, method, masked=False)
+
+
+def visualise_flow_arrows(flow, ref, grid_dist=None, img=None, scaling=None, colour=None):
+    """flow_operations.py:287-312."""
+    return Flow(flow, ref).visualise_arrows(
+        grid_dist, img, scaling, False, False, colour)
+
+
+def show_flow(flow, wait=None):
+    """flow_operations.py:315-323."""
+    return Flow(flow).show(wait)
+
+
+def show_flow_arrows(flow, ref, wait=None, grid_dist=None, img=None, scaling=None, colour=None):
+    """flow_operations.py:326-350."""
+    return Flow(flow, ref).show_arrows(wait, grid_dist, img, scaling,
+                                                                                         False, False, colour)
+
+
+def visualise_definition(mode, shape=None, insert_text=None):
+    """flow_operations.py:25-67: the colour-wheel legend, drawn by the reference package on the host."""
+    try:
+        from oflibnumpy import visualise_definition as ref_visualise_definition
+    except ImportError as e:
+        raise ImportError("oflibnumpy_b200 delegates visualise_definition to the reference package: install oflibnumpy "
+                          "to use it") from e
+    return ref_visualise_definition(mode, shape, insert_text)

@@ -939,3 +939,23 @@ def test_torch_cuda_tensors_pass_through_zero_copy(of):
     fb = of.FlowBatch(torch.stack([tv, tv]), 't', torch.stack([tm, tm]))
     r = fb.combine_with(fb, 3)
     assert np.array_equal(r.vecs.numpy()[1], c_n.vecs)
+
+
+def test_matrix_delegates_to_the_reference_on_a_host_copy(of):
+    """Flow.matrix (OpenCV's robust estimators, SURVEY section 2 row 19: out of the hot path) runs on the reference package
+    with a host copy of the flow; with the vendored reference on the path it recovers the generating transform."""
+    import sys
+    ref_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'baseline', '_ref')
+    if not os.path.isdir(os.path.join(ref_dir, 'oflibnumpy')):
+        pytest.skip("vendored reference not present (baseline/_ref)")
+    sys.path.insert(0, ref_dir)
+    try:
+        tr = [['rotation', 30, 20, 12], ['translation', 4.5, -3.0]]
+        f = of.Flow.from_transforms(tr, (60, 80), 's')
+        m = f.matrix(dof=4, method='ransac')
+        np.testing.assert_allclose(m, of.matrix_from_transforms(tr), atol=1e-3)
+        assert of.get_flow_matrix(f.vecs, 's', dof=6, method='lmeds').shape == (3, 3)
+        assert f.visualise_arrows(grid_dist=10).shape == (60, 80, 3)
+        assert of.visualise_flow(f.vecs, 'bgr').shape == (60, 80, 3)
+    finally:
+        sys.path.remove(ref_dir)

@@ -207,3 +207,20 @@ def test_percentile_from_order_statistics_matches_numpy():
             k0, k1, gamma = _ops.percentile_plan(n)
             got = _ops.percentile_from_order_stats(srt[k0], srt[k1], gamma)
             assert got == float(np.percentile(a, 99)), (n, scale, got, float(np.percentile(a, 99)))
+
+
+def test_host_side_presentation_api_is_present():
+    """matrix / visualise_arrows / show* and their ndarray wrappers exist with the reference's signatures (they delegate
+    to the reference package on a host copy: SURVEY section 2 rows 19-21, not on the hot path)."""
+    import inspect
+    import oflibnumpy_b200 as of
+    sigs = {'matrix': ['self', 'dof', 'method', 'masked'],
+            'visualise_arrows': ['self', 'grid_dist', 'img', 'scaling', 'show_mask', 'show_mask_borders', 'colour',
+                                 'thickness'],
+            'show': ['self', 'wait', 'show_mask', 'show_mask_borders'],
+            'show_arrows': ['self', 'wait', 'grid_dist', 'img', 'scaling', 'show_mask', 'show_mask_borders', 'colour']}
+    for name, args in sigs.items():
+        assert list(inspect.signature(getattr(of.Flow, name)).parameters) == args, name
+    for name in ('visualise_flow', 'get_flow_matrix', 'visualise_flow_arrows', 'show_flow', 'show_flow_arrows',
+                 'visualise_definition'):
+        assert callable(getattr(of, name)), name
