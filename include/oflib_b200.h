@@ -237,7 +237,9 @@ int ofk_decode_sintel_mask(const uint8_t* invalid, uint8_t* mask, size_t n_pixel
  * are resolved deterministically (largest source index wins, cells with a removed corner left empty).
  * ofk_forward_s_ex: flow_nonzero (int32 [N], device, e.g. from ofk_nonzero_flags(flow, NULL, 1e-3)) or NULL; frames
  * with 0 are passed through (out = payload, out_mask = payload_mask) like apply_flow's early return for a flow that is
- * zero below the threshold (utils.py:215-216). */
+ * zero below the threshold (utils.py:215-216).
+ * Asynchronous on `stream` like every ofk_* call; internally the part that does not depend on the cell rasteriser runs
+ * on a library-owned side stream per device, forked from and joined back into `stream` with events inside the call. */
 size_t ofk_forward_s_workspace(int N, int H, int W);
 int ofk_forward_s(const float* payload, int C, const float* flow, float flow_sign, const uint8_t* payload_mask,
                   const uint8_t* point_mask, float* out, uint8_t* out_mask, int mask_rule, int N, int H, int W,

@@ -629,7 +629,12 @@ __global__ void __launch_bounds__((NCW + PW) * 32, 3) warp_u8_ws_kernel(const __
     if (elect_one()) bulk_wait_all();   // the lane that committed the groups
 }
 
-constexpr int WS_NP = 6, WS_NB = 2, WS_LA = 3, WS_PW = 1;   // measured best: one producer warp (a P loader warp costs the 3rd CTA its registers)
+#ifndef OFK_WS_NP
+#define OFK_WS_NP 6
+#define OFK_WS_NB 2
+#define OFK_WS_LA 3
+#endif
+constexpr int WS_NP = OFK_WS_NP, WS_NB = OFK_WS_NB, WS_LA = OFK_WS_LA, WS_PW = 1;   // measured best: one producer warp (a P loader warp costs the 3rd CTA its registers)
 
 template <int C, bool HALF_EVEN, int MM, bool FM>
 static int launch_variant(const Maps& maps, const uint8_t* img, const uint8_t* pmask, float sign, int rule, int H, int W,
