@@ -855,7 +855,10 @@ OFK_HD bool pocket_triangulate(const SiteGrid& g, const ArcFn& arc, int i0, int 
 // along the first direction, turning back from k + 1, that has an intact cell on its right. Faces that are larger,
 // touch the frame border, are pinched at a vertex, hold a site or surround an island of intact cells are left to the
 // per-pixel search.
-constexpr int HOLE_MAXV = 48;
+#ifndef OFK_HOLE_MAXV
+#define OFK_HOLE_MAXV 48
+#endif
+constexpr int HOLE_MAXV = OFK_HOLE_MAXV;
 
 // cell (ci, cj) = the pixels (ci, cj), (ci, cj+1), (ci+1, cj), (ci+1, cj+1); intact when all four are present
 OFK_HD bool cell_intact(const uint8_t* point_mask, int H, int W, int ci, int cj) {
