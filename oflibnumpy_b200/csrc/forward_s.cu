@@ -1274,22 +1274,28 @@ __global__ void __launch_bounds__(256) irr_pockets_kernel(const PocketArgs A) {
         for (;;) {
             int got = 0, i = 0, j = 0;
             if (lane == 0) {
-                pool_lock(pool);
-                if (pool.n > 0) {
-                    --pool.n;
-                    i = pool.lo[pool.n];
-                    j = pool.hi[pool.n];
-                    ++pool.active;
-                    got = 1;
-                } else if (pool.active == 0) {
-                    got = -1;
+                // Idle warps look at the pool without taking its lock (ncu: seven polling warps per CTA spent 40 % of the
+                // kernel's instructions on the lock and kept the one working warp waiting for it whenever it wanted to
+                // hand over a part); only a warp that sees work, or sees the end, confirms under the lock.
+                const int seen_n = *(volatile int*)&pool.n, seen_active = *(volatile int*)&pool.active;
+                if (seen_n > 0 || seen_active == 0) {
+                    pool_lock(pool);
+                    if (pool.n > 0) {
+                        --pool.n;
+                        i = pool.lo[pool.n];
+                        j = pool.hi[pool.n];
+                        ++pool.active;
+                        got = 1;
+                    } else if (pool.active == 0) {
+                        got = -1;
+                    }
+                    pool_unlock(pool);
                 }
-                pool_unlock(pool);
             }
             got = __shfl_sync(0xffffffffu, got, 0);
             if (got < 0) break;
             if (got == 0) {
-                __nanosleep(200);
+                __nanosleep(400);
                 continue;
             }
             i = __shfl_sync(0xffffffffu, i, 0);
