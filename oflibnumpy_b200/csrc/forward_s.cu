@@ -1202,9 +1202,14 @@ __global__ void __launch_bounds__(256) irr_border_edges_kernel(const PocketArgs 
 // and the rows; when it splits a part, the longer half goes to a small pool in shared memory that idle warps draw from.
 constexpr int POOL_CAP = 16, POOL_MIN_LEN = 24;
 
+constexpr int TRI_CAP = 96;
 struct PocketPool {
     int lo[POOL_CAP], hi[POOL_CAP];
     int n, active, lock;
+    // triangles found by a warp that is splitting an arc, rasterised by the CTA's idle warps (a quarter of the time of a
+    // split went into rasterising its long thin triangle row by row, on the critical path of a sequential recursion)
+    int tn;
+    uint32_t ta[TRI_CAP], tb[TRI_CAP], tc[TRI_CAP];
 };
 
 __device__ __forceinline__ void pool_lock(PocketPool& p) {
@@ -1236,6 +1241,30 @@ struct PocketShare {
     }
 };
 
+// tri() of pocket_triangulate inside the pockets kernel: queue the triangle for an idle warp, rasterise it on the spot
+// only when the queue is full
+struct PocketTriDefer {
+    PocketTri now;
+    PocketPool& pool;
+    int lane;
+    __device__ __forceinline__ void operator()(uint32_t ia, uint32_t ib, uint32_t ic, const P2& pa, const P2& pb,
+                                               const P2& pc) {
+        int took = 0;
+        if (lane == 0 && *(volatile int*)&pool.tn < TRI_CAP) {
+            pool_lock(pool);
+            if (pool.tn < TRI_CAP) {
+                pool.ta[pool.tn] = ia;
+                pool.tb[pool.tn] = ib;
+                pool.tc[pool.tn] = ic;
+                ++pool.tn;
+                took = 1;
+            }
+            pool_unlock(pool);
+        }
+        if (__shfl_sync(0xffffffffu, took, 0) == 0) now(ia, ib, ic, pa, pb, pc);
+    }
+};
+
 __global__ void __launch_bounds__(256) irr_pockets_kernel(const PocketArgs A) {
     const int n = blockIdx.y;
     if (A.folded[n]) return;
@@ -1251,7 +1280,8 @@ __global__ void __launch_bounds__(256) irr_pockets_kernel(const PocketArgs A) {
     const size_t frame = (size_t)n * A.H * A.W;
     const SiteGrid g = pocket_grid(A, frame);
     unsigned long long pixels = 0;
-    PocketTri tri{A, frame, coop, pixels};
+    PocketTri tri_now{A, frame, coop, pixels};
+    PocketTriDefer tri{tri_now, pool, lane};
     PocketSeg seg{A, frame, pixels};
     PocketShare share{pool, lane};
     const int m = hp.m, P = ch.n;
@@ -1267,18 +1297,21 @@ __global__ void __launch_bounds__(256) irr_pockets_kernel(const PocketArgs A) {
             pool.lo[0] = 0;
             pool.hi[0] = len;
             pool.n = 1;
+            pool.tn = 0;
             pool.active = 0;
             pool.lock = 0;
         }
         __syncthreads();
         for (;;) {
             int got = 0, i = 0, j = 0;
+            uint32_t ta = 0, tb = 0, tc = 0;
             if (lane == 0) {
                 // Idle warps look at the pool without taking its lock (ncu: seven polling warps per CTA spent 40 % of the
                 // kernel's instructions on the lock and kept the one working warp waiting for it whenever it wanted to
                 // hand over a part); only a warp that sees work, or sees the end, confirms under the lock.
-                const int seen_n = *(volatile int*)&pool.n, seen_active = *(volatile int*)&pool.active;
-                if (seen_n > 0 || seen_active == 0) {
+                const int seen_n = *(volatile int*)&pool.n, seen_tn = *(volatile int*)&pool.tn,
+                          seen_active = *(volatile int*)&pool.active;
+                if (seen_n > 0 || seen_tn > 0 || seen_active == 0) {
                     pool_lock(pool);
                     if (pool.n > 0) {
                         --pool.n;
@@ -1286,6 +1319,14 @@ __global__ void __launch_bounds__(256) irr_pockets_kernel(const PocketArgs A) {
                         j = pool.hi[pool.n];
                         ++pool.active;
                         got = 1;
+                    } else if (pool.tn > 0) {
+                        --pool.tn;
+                        i = pool.tn;          // slot: copied out below, still under the lock
+                        ta = pool.ta[i];
+                        tb = pool.tb[i];
+                        tc = pool.tc[i];
+                        ++pool.active;
+                        got = 2;
                     } else if (pool.active == 0) {
                         got = -1;
                     }
@@ -1296,6 +1337,19 @@ __global__ void __launch_bounds__(256) irr_pockets_kernel(const PocketArgs A) {
             if (got < 0) break;
             if (got == 0) {
                 __nanosleep(400);
+                continue;
+            }
+            if (got == 2) {   // a queued triangle
+                ta = __shfl_sync(0xffffffffu, ta, 0);
+                tb = __shfl_sync(0xffffffffu, tb, 0);
+                tc = __shfl_sync(0xffffffffu, tc, 0);
+                tri_now(ta, tb, tc, site_pos(g, ta), site_pos(g, tb), site_pos(g, tc));
+                __syncwarp();
+                if (lane == 0) {
+                    pool_lock(pool);
+                    --pool.active;
+                    pool_unlock(pool);
+                }
                 continue;
             }
             i = __shfl_sync(0xffffffffu, i, 0);
