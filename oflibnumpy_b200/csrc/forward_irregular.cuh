@@ -787,6 +787,19 @@ struct ChainArc {   // position t along the arc that starts at chain index k0 ->
     Chain c;
     int k0;
     OFK_HD uint32_t operator()(int t) const { return chain_site(c, (k0 + t) % c.n); }
+    OFK_HD P2 position(const SiteGrid& g, int t) const { return site_pos(g, (*this)(t)); }
+};
+// The same arc with the sites and displaced positions of its first `ncached` vertices held in a table (shared memory
+// in the pockets kernel): a split scans its part of the arc vertex by vertex, and chain index -> site -> flow load ->
+// float64 position is most of what a scan step costs. Same values, fetched instead of recomputed.
+struct ChainArcCached {
+    Chain c;
+    int k0;
+    const uint32_t* ids;
+    const P2* pos;
+    int ncached;
+    OFK_HD uint32_t operator()(int t) const { return t < ncached ? ids[t] : chain_site(c, (k0 + t) % c.n); }
+    OFK_HD P2 position(const SiteGrid& g, int t) const { return t < ncached ? pos[t] : site_pos(g, (*this)(t)); }
 };
 template <class ArcFn, class TriFn, class ShareFn>
 OFK_HD bool pocket_triangulate(const SiteGrid& g, const ArcFn& arc, int i0, int j0, const Coop& coop, TriFn& tri,
@@ -800,7 +813,7 @@ OFK_HD bool pocket_triangulate(const SiteGrid& g, const ArcFn& arc, int i0, int 
         int i = lo[sp], j = hi[sp];
         while (j - i >= 2) {
             const uint32_t ia = arc(i), ib = arc(j);
-            const P2 pa = site_pos(g, ia), pb = site_pos(g, ib);
+            const P2 pa = arc.position(g, i), pb = arc.position(g, j);
             const double ex = dsub(pb.x, pa.x), ey = dsub(pb.y, pa.y);
             ArcBest b;
             b.id = NO_SITE;
@@ -811,7 +824,7 @@ OFK_HD bool pocket_triangulate(const SiteGrid& g, const ArcFn& arc, int i0, int 
             b.umax = dfma(ex, ex, dmul(ey, ey));
             for (int t = i + 1 + coop.lane; t < j; t += coop.n) {
                 const uint32_t id = arc(t);
-                const P2 p = site_pos(g, id);
+                const P2 p = arc.position(g, t);
                 const double o = orient(pa, pb, p);
                 const double u = dfma(dsub(p.x, pa.x), ex, dmul(dsub(p.y, pa.y), ey));
                 b.omin = fmin(b.omin, o);
@@ -872,6 +885,7 @@ struct HoleLoop {
     int n;
     uint32_t v[HOLE_MAXV];   // boundary sites, the face on the RIGHT of v[t] -> v[t + 1] (the order of a pocket's arc)
     OFK_HD uint32_t operator()(int t) const { return v[t]; }
+    OFK_HD P2 position(const SiteGrid& g, int t) const { return site_pos(g, v[t]); }
 };
 
 // quadrant q (0..3 = SE, SW, NW, NE) of site (r, c) as a cell

@@ -1275,6 +1275,11 @@ __global__ void __launch_bounds__(256) irr_pockets_kernel(const PocketArgs A) {
     const bool traced = ch.v != nullptr;
     const int* hpos = A.hull_pos + (size_t)n * HULL_MAX;
     __shared__ PocketPool pool;
+    // sites and positions of the arc under the hull edge at hand (see ChainArcCached); longer arcs (4K frames) keep the
+    // head of the arc here and compute the rest on the fly
+    constexpr int ARC_CACHE = 2304;
+    __shared__ P2 s_arc_pos[ARC_CACHE];
+    __shared__ uint32_t s_arc_id[ARC_CACHE];
     const int lane = threadIdx.x & 31;
     const Coop coop{lane, 32};
     const size_t frame = (size_t)n * A.H * A.W;
@@ -1293,6 +1298,12 @@ __global__ void __launch_bounds__(256) irr_pockets_kernel(const PocketArgs A) {
         const int len = ((k1 - k0) % P + P) % P;
         if (len < 2) continue;
         __syncthreads();
+        const int ncached = min(len + 1, ARC_CACHE);
+        for (int t = threadIdx.x; t < ncached; t += 256) {
+            const uint32_t id = chain_site(ch, (k0 + t) % P);
+            s_arc_id[t] = id;
+            s_arc_pos[t] = site_pos(g, id);
+        }
         if (threadIdx.x == 0) {
             pool.lo[0] = 0;
             pool.hi[0] = len;
@@ -1354,7 +1365,7 @@ __global__ void __launch_bounds__(256) irr_pockets_kernel(const PocketArgs A) {
             }
             i = __shfl_sync(0xffffffffu, i, 0);
             j = __shfl_sync(0xffffffffu, j, 0);
-            pocket_triangulate(g, ChainArc{ch, k0}, i, j, coop, tri, share);
+            pocket_triangulate(g, ChainArcCached{ch, k0, s_arc_id, s_arc_pos, ncached}, i, j, coop, tri, share);
             __syncwarp();
             if (lane == 0) {
                 pool_lock(pool);
