@@ -687,19 +687,38 @@ struct ArcBest {
     double omin, omax, umin, umax;   // range of orient(a, b, .) and of (. - a) . (b - a) over the arc's vertices
 };
 
+#if defined(__CUDA_ARCH__)
+// warp-wide minimum / maximum of a double as a float rounded outwards (one REDUX on an order-preserving integer key
+// instead of five rounds of 64-bit shuffles): for bounds that only have to be conservative
+__device__ __forceinline__ int arc_float_key(float f) {
+    const int k = __float_as_int(f);
+    return k >= 0 ? k : k ^ 0x7fffffff;
+}
+__device__ __forceinline__ double arc_warp_min(double v) {
+    const int k = __reduce_min_sync(0xffffffffu, arc_float_key(__double2float_rd(v)));
+    return (double)__int_as_float(k >= 0 ? k : k ^ 0x7fffffff);
+}
+__device__ __forceinline__ double arc_warp_max(double v) {
+    const int k = __reduce_max_sync(0xffffffffu, arc_float_key(__double2float_ru(v)));
+    return (double)__int_as_float(k >= 0 ? k : k ^ 0x7fffffff);
+}
+#endif
+
 OFK_HD void arc_reduce(ArcBest& b, const P2& pa, const P2& pb, uint32_t ia, uint32_t ib, const Coop& coop) {
 #if defined(__CUDA_ARCH__)
     if (coop.n == 1) return;
+    // the extent of the part (it only feeds the conservative pixel test of pocket_may_hold_pixel) ...
+    b.omin = arc_warp_min(b.omin);
+    b.omax = arc_warp_max(b.omax);
+    b.umin = arc_warp_min(b.umin);
+    b.umax = arc_warp_max(b.umax);
+    // ... and the apex: exact, a tree of in-circle tests
     for (int o = 16; o > 0; o >>= 1) {
         ArcBest ob;
         ob.id = __shfl_xor_sync(0xffffffffu, b.id, o);
         ob.t = __shfl_xor_sync(0xffffffffu, b.t, o);
         ob.p.x = __shfl_xor_sync(0xffffffffu, b.p.x, o);
         ob.p.y = __shfl_xor_sync(0xffffffffu, b.p.y, o);
-        b.omin = fmin(b.omin, __shfl_xor_sync(0xffffffffu, b.omin, o));
-        b.omax = fmax(b.omax, __shfl_xor_sync(0xffffffffu, b.omax, o));
-        b.umin = fmin(b.umin, __shfl_xor_sync(0xffffffffu, b.umin, o));
-        b.umax = fmax(b.umax, __shfl_xor_sync(0xffffffffu, b.umax, o));
         if (ob.id == NO_SITE || ob.id == b.id) continue;
         if (b.id == NO_SITE || incircle_sign(pa, pb, b.p, ob.p, ia, ib, b.id, ob.id) > 0) {
             b.id = ob.id;
