@@ -41,7 +41,10 @@ __host__ __device__ constexpr int box_bytes(int C) { return C == 3 ? OFK_BOX3 : 
 __host__ __device__ constexpr int box_px(int C) { return (box_bytes(C) - 15) / C; }
 // mask box width (bytes = pixels): its start is the first needed pixel aligned down to 16, the image box reaches at most
 // (box_bytes - 2C) / C + 15 <= 77 pixels (+ 1 tap) beyond that
-constexpr int BMW = 80;
+#ifndef OFK_BMW
+#define OFK_BMW 80
+#endif
+constexpr int BMW = OFK_BMW;
 // BH rows, rounded up to 128 with room for the word loads that run a few bytes past the last tap
 __host__ __device__ constexpr int img_stage(int C) { return (BH * box_bytes(C) + 16 + 127) / 128 * 128; }
 

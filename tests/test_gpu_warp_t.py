@@ -959,3 +959,32 @@ def test_matrix_delegates_to_the_reference_on_a_host_copy(of):
         assert of.visualise_flow(f.vecs, 'bgr').shape == (60, 80, 3)
     finally:
         sys.path.remove(ref_dir)
+
+
+def test_resampled_mask_where_the_image_box_reaches_beyond_the_estimate(of):
+    """The producer sizes the source box of a tile from 16 sampled pixels; pixels between the samples may land anywhere
+    inside the (wider) image box. Every such pixel must find its four mask taps inside the mask box as well: with a
+    64-byte mask box whose start is rounded down to 16 pixels the right-most 4 pixels of the image box were not
+    covered when the first needed pixel sat at 12..15 (mod 16) -- the mask box is 80 wide since. Translations over all
+    16 alignments, with outliers placed off the sample grid that push single pixels to both ends of the image box;
+    image, resampled validity and geometric validity against the oracle, bit for bit."""
+    rng = np.random.default_rng(123)
+    h, w = 96, 256
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    tmask = rng.random((h, w)) > 0.3
+    fmask = rng.random((h, w)) > 0.05
+    ys, xs = np.mgrid[:h, :w]
+    off_grid = ~(np.isin(xs % 32, (0, 10, 21, 31)) & np.isin(ys % 32, (0, 10, 21, 31)))
+    for shift in range(16):
+        for reach in (-13.25, -9.5, 9.5, 13.25):
+            f = np.zeros((h, w, 2), np.float32)
+            f[..., 0] = -(shift + 0.375)                 # 't' flows sample at x - flow: the box starts at x0 + shift
+            f[..., 1] = 0.625
+            pick = off_grid & (rng.random((h, w)) < 0.02)
+            f[pick, 0] -= np.float32(reach)
+            fl, rf = of.Flow(f, 't', fmask), R.make(f, 't', fmask)
+            for kw in ({'target_mask': tmask}, {}):
+                w1, m1 = fl.apply(img, return_valid_area=True, **kw)
+                w2, m2 = R.apply(rf, img, return_valid_area=True, **kw)
+                same(w1, w2)
+                same(m1, m2)
